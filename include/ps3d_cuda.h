@@ -1,0 +1,120 @@
+/* libps3d_cuda — C ABI of the B200 implementation of the ps3d time-step path.
+ *
+ * This is the drop-in boundary for the Fortran host program (matt-frey/ps3d):
+ * each entry point replaces a public module procedure of the reference (cited
+ * as file:line under /root/reference) and is meant to be bound from Fortran
+ * with `bind(C)` interfaces inside thin replacement module bodies (see
+ * INTEGRATION.md).  Conventions:
+ *   - every function returns an int status (0 = PS3D_OK); the reference's
+ *     `stop` / `mpi_stop` / `MPI_Abort` paths become non-zero statuses and the
+ *     Fortran shim maps them to `mpi_exit_on_error` (mpi_utils.f90:15-31);
+ *     `ps3d_cuda_last_error()` returns the message;
+ *   - one host thread per rank, non-reentrant, one global context per process
+ *     (the reference keeps all state in module globals: fields.f90:17-38,
+ *     inversion_utils.f90:37-78, sta3dfft.f90:18-28);
+ *   - host arrays are plain `double*` in the reference's own layout
+ *     `f(0:nz, 0:ny-1, 0:nx-1)` (Fortran order, z fastest; fields.f90:59-65),
+ *     i.e. C `f[x][y][z]` with nz+1 contiguous doubles per column;
+ *   - the library fails (PS3D_ERR_NO_DEVICE) when no CUDA device is present:
+ *     there is no CPU path.
+ */
+#ifndef PS3D_CUDA_H
+#define PS3D_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    PS3D_OK = 0,
+    PS3D_ERR_NOT_INITIALISED = 1,
+    PS3D_ERR_BAD_ARGUMENT = 2,
+    PS3D_ERR_UNSUPPORTED_SIZE = 3,   /* stafft.f90:87-95 "Factorisation not possible" analogue */
+    PS3D_ERR_NO_DEVICE = 4,
+    PS3D_ERR_DEVICE = 5,
+    PS3D_ERR_UNSUPPORTED = 6
+};
+
+/* options.f90:67 `filtering` */
+enum { PS3D_FILTER_HOU_LI = 0, PS3D_FILTER_23_RULE = 1 };
+/* options.f90:61 `length_scale` */
+enum { PS3D_LSCALE_KOLMOGOROV = 0, PS3D_LSCALE_GEOPHYSICAL = 1 };
+/* options.f90:24 `stepper` */
+enum { PS3D_STEPPER_CN2 = 0, PS3D_STEPPER_IMPL_RK4 = 1 };
+/* options.f90:55 `pretype` (advance.f90:385-408) */
+enum { PS3D_PRE_CONSTANT = 0, PS3D_PRE_VORCH = 1, PS3D_PRE_BFMAX = 2, PS3D_PRE_ROLL_MEAN_MAX_STRAIN = 3,
+       PS3D_PRE_MAX_STRAIN = 4, PS3D_PRE_US_MAX_STRAIN = 5 };
+/* resident fields (fields.f90:17-23) for ps3d_cuda_download / ps3d_cuda_upload */
+enum { PS3D_F_SVOR = 0, PS3D_F_VOR = 1, PS3D_F_VEL = 2, PS3D_F_SVEL = 3, PS3D_F_SVORTS = 4,
+       PS3D_F_PRES = 5, PS3D_F_DELTA = 6 };
+/* slots of the diag_out[16] array filled by ps3d_cuda_adapt / ps3d_cuda_advance
+ * (advance.f90:188-193,315-321,366) */
+enum { PS3D_D_VORTMAX = 0, PS3D_D_VORTRMS, PS3D_D_VORCH, PS3D_D_VORMEAN_X, PS3D_D_VORMEAN_Y, PS3D_D_VORMEAN_Z,
+       PS3D_D_BFMAX, PS3D_D_GGMAX, PS3D_D_UMAX, PS3D_D_VMAX, PS3D_D_WMAX, PS3D_D_USGGMAX, PS3D_D_LSGGMAX,
+       PS3D_D_RMV, PS3D_D_DT, PS3D_D_PREFACTOR };
+
+const char* ps3d_cuda_last_error(void);
+
+/* mpi_layout_init (mpi_layout.f90:53) + update_parameters (parameters.f90:61) +
+ * initialise_fft (sta3dfft.f90:53).  rank/nranks: slab decomposition over the
+ * GPUs of one box; nccl_id: 128-byte ncclUniqueId shared by all ranks (NULL
+ * when nranks == 1). */
+int ps3d_cuda_init(int nx, int ny, int nz, const double lower[3], const double extent[3],
+                   int rank, int nranks, const void* nccl_id);
+/* init_inversion (inversion_utils.f90:222) */
+int ps3d_cuda_init_inversion(int filtering_id);
+/* init_diffusion (inversion_utils.f90:124); returns the (hyper)viscosity */
+int ps3d_cuda_init_diffusion(int nnu, double prediss, int length_scale_id, double te, double en, double* nu_out);
+/* finalise_inversion + finalise_fft (inversion_utils.f90:459, sta3dfft.f90:112) */
+int ps3d_cuda_finalise(void);
+
+/* ---- operator mode: host pointers in, host pointers out (H2D/D2H each call) ---- */
+int ps3d_cuda_fftxyp2s(const double* fp, double* fs);                 /* sta3dfft.f90:136 */
+int ps3d_cuda_fftxys2p(const double* fs, double* fp);                 /* sta3dfft.f90:202 */
+int ps3d_cuda_fftsine(double* fs);                                    /* sta3dfft.f90:264 */
+int ps3d_cuda_fftcosine(double* fs);                                  /* sta3dfft.f90:282 */
+int ps3d_cuda_diffx(const double* fs, double* ds);                    /* sta3dfft.f90:304 */
+int ps3d_cuda_diffy(const double* fs, double* ds);                    /* sta3dfft.f90:345 */
+int ps3d_cuda_central_diffz(const double* fs, double* ds);            /* inversion_utils.f90:653 */
+int ps3d_cuda_field_combine_semi_spectral(double* sf);                /* inversion_utils.f90:617 */
+int ps3d_cuda_field_decompose_semi_spectral(double* sfc);             /* inversion_utils.f90:563 */
+int ps3d_cuda_field_combine_physical(const double* sf, double* fc);   /* inversion_utils.f90:599 */
+int ps3d_cuda_field_decompose_physical(const double* fc, double* sf); /* inversion_utils.f90:549 */
+
+/* ---- resident mode: state lives in HBM (what the time loop uses) ---- */
+/* setup_fields (utils.f90:160-165): vor(0:nz,y,x,1:3) -> decompose x3, ini_vor_mean */
+int ps3d_cuda_upload_vorticity(const double* vor_phys);
+int ps3d_cuda_vor2vel(void);                                          /* inversion.f90:23 */
+int ps3d_cuda_source(void);                                           /* inversion.f90:378 */
+/* adapt (advance.f90:109) incl. bstep%set_diffusion; pressure/divergence are lazy (see download) */
+int ps3d_cuda_adapt(double t, double t_limit, double alpha, int pretype_id, int roll_mean_win_size,
+                    double* dt, double diag_out[16]);
+int ps3d_cuda_stepper_setup(int stepper_id);                          /* cn2.f90:83 / impl_rk4.f90:57 */
+int ps3d_cuda_set_diffusion(double dt, double prefactor);             /* cn2.f90:40 / impl_rk4.f90:37 */
+int ps3d_cuda_step(double* t, double dt);                             /* cn2.f90:92 / impl_rk4.f90:76 */
+/* advance (advance.f90:77-104) minus write_step */
+int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, int roll_mean_win_size,
+                      double* dt_out, double diag_out[16]);
+/* field_netcdf.f90:216-230 reads these; comp = 0..2 (ignored for pres/delta, which are
+ * computed on demand from the current state: fields_derived.f90:67,161) */
+int ps3d_cuda_download(int field_id, int comp, double* host);
+int ps3d_cuda_upload(int field_id, int comp, const double* host);
+/* out[0..2] = kinetic energy, enstrophy (field_diagnostics.f90:85,172), helicity
+ * (plotting/nc_reader.py:94-101 trapezoid mean of u.omega); out[3..7] reserved */
+int ps3d_cuda_diagnostics(double out[8]);
+
+/* ---- introspection for benchmarks ---- */
+/* number of kernels this library has launched since init */
+long long ps3d_cuda_kernel_launches(void);
+/* time the last ps3d_cuda_advance spent on the device (CUDA events), milliseconds */
+double ps3d_cuda_last_advance_ms(void);
+/* run `reps` back-to-back launches of one hot kernel on resident data and return the
+ * average device time per launch in ms (CUDA events on the library's stream).
+ * which: 0 = forward y sweep, 1 = forward x sweep, 2 = inverse x sweep,
+ *        3 = inverse y sweep, 4 = vor2vel column kernel, 5 = source column kernel */
+int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

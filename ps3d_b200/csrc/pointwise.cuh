@@ -1,0 +1,307 @@
+// Streaming kernels: layout repack at the host boundary, the time-stepper
+// updates (reference src/stepper/cn2.f90:92-181, impl_rk4.f90:76-364, using
+// the identity decompose(c(ky,kx) * combine(q)) == c*q so that no z transform
+// is needed), the mean-vorticity fix (field_diagnostics.f90:584-619), the
+// adapt()/diagnostic reductions (advance.f90:171-313,
+// field_diagnostics.f90:85-206,405-579) and the per-point strain eigenvalue
+// sweep (advance.f90:222-276, utils/jacobi.f90:19-51,215-305).
+//
+// All reductions are two-stage with a fixed grid and fixed tree, i.e.
+// deterministic and independent of scheduling (no floating-point atomics).
+#pragma once
+
+#include "rt.h"
+
+namespace ps3d {
+
+// ---- host-boundary repack ---------------------------------------------------
+// natural Fortran order  f(0:nz, y, x)  <->  internal [x][rowmap(y)][pz]
+__global__ void k_repack_in(const double* __restrict__ nat, double* __restrict__ dev, int nxl, int ny, int nzp,
+                            int pz, const int* __restrict__ rowmap) {
+    const long long n = (long long)nxl * ny * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        const long long xy = i / pz;
+        const int y = (int)(xy % ny);
+        const long long x = xy / ny;
+        const int yy = rowmap ? rowmap[y] : y;
+        dev[(x * ny + yy) * pz + z] = (z < nzp) ? nat[(x * ny + y) * nzp + z] : 0.0;
+    }
+}
+
+__global__ void k_repack_out(const double* __restrict__ dev, double* __restrict__ nat, int nxl, int ny, int nzp,
+                             int pz, const int* __restrict__ rowmap) {
+    const long long n = (long long)nxl * ny * nzp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % nzp);
+        const long long xy = i / nzp;
+        const int y = (int)(xy % ny);
+        const long long x = xy / ny;
+        const int yy = rowmap ? rowmap[y] : y;
+        nat[i] = dev[(x * ny + yy) * pz + z];
+    }
+}
+
+// ---- time steppers ------------------------------------------------------------
+struct StepArgs {
+    double* svor[3];
+    double* svorts[3];
+    double* wa[3];          // cn2: vortsm      rk4: svori
+    double* wb[3];          // rk4: svorf
+    const double* f2d;      // cn2: vdiss*filt2d (per column)   rk4: unused
+    const double* filtz;    // cn2: z part of the filter, [nz+1], 1 at rows 0 and nz
+    const double* mq;       // rk4: emq (per column)
+    const double* pq;       // rk4: epq or filt(0,:,:) (per column)
+    const double* vd;       // cn2: vdiss (per column) — used for the (0,0) column where filt = 1
+    double c1, c2;          // cn2: dt/2.   rk4: stage coefficients
+    int stage;              // cn2: 0 = first update (defines vortsm), 1 = iteration. rk4: 1..4
+    long long ncol;         // nx*nyl
+    int nz, pz;
+    int has00;
+};
+
+// cn2.f90:120-135 / :162-173 with combine -> vdiss -> decompose collapsed.
+__global__ void k_cn2_update(StepArgs a) {
+    const long long n = a.ncol * a.pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % a.pz);
+        if (z > a.nz) continue;
+        const long long col = i / a.pz;
+        double fac = __ldg(&a.f2d[col]) * __ldg(&a.filtz[z]);
+        if (a.has00 && col == 0) fac = __ldg(&a.vd[0]);      // filt(:,0,0) = 1 (inversion_utils.f90:275-277)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double s = a.svorts[c][i];
+            double sm;
+            if (a.stage == 0) { sm = a.svor[c][i] + a.c1 * s; a.wa[c][i] = sm; }
+            else sm = a.wa[c][i];
+            a.svor[c][i] = fac * (sm + a.c1 * s);
+        }
+    }
+}
+
+// impl_rk4.f90:212-364, substeps one..four, combine/decompose pairs collapsed.
+__global__ void k_rk4_update(StepArgs a) {
+    const long long n = a.ncol * a.pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % a.pz);
+        if (z > a.nz) continue;
+        const long long col = i / a.pz;
+        const double mq = __ldg(&a.mq[col]), pq = __ldg(&a.pq[col]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double s = pq * a.svorts[c][i];
+            a.svorts[c][i] = s;
+            if (a.stage == 1) {
+                const double qi = a.svor[c][i];
+                a.wa[c][i] = qi;
+                a.svor[c][i] = mq * (qi + a.c1 * s);
+                a.wb[c][i] = qi + a.c2 * s;
+            } else if (a.stage == 4) {
+                a.svor[c][i] = mq * (a.wb[c][i] + a.c1 * s);
+            } else {
+                a.svor[c][i] = mq * (a.wa[c][i] + a.c1 * s);
+                a.wb[c][i] = a.wb[c][i] + a.c2 * s;
+            }
+        }
+    }
+}
+
+// per-column factor tables for the steppers
+//   mode 0 (cn2.f90:59):       o1 = 1/(1 + dfac*vhdis),  o2 = o1 * filt2d
+//   mode 1 (impl_rk4.f90:43-47,87-89): e = exp(dfac*vhdis); o1 = 1/e (emq), o2 = e*filt2d (epq)
+//   mode 2: o1 = o1^2 (emq**2, :151)     mode 3: o2 = o2^2 (epq**2, :185)
+__global__ void k_step_factors(int mode, double dfac, const double* __restrict__ vhdis, const double* __restrict__ filt2d,
+                               double* __restrict__ o1, double* __restrict__ o2, long long ncol) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncol; i += (long long)gridDim.x * blockDim.x) {
+        if (mode == 0) {
+            const double v = 1.0 / (1.0 + dfac * vhdis[i]);
+            o1[i] = v; o2[i] = v * filt2d[i];
+        } else if (mode == 1) {
+            const double e = exp(dfac * vhdis[i]);
+            o1[i] = 1.0 / e; o2[i] = e * filt2d[i];
+        } else if (mode == 2) {
+            o1[i] = o1[i] * o1[i];
+        } else {
+            o2[i] = o2[i] * o2[i];
+        }
+    }
+}
+
+// ---- block reduction helper -----------------------------------------------------
+// op 0 = sum, 1 = max.  All threads call; result valid in thread 0.  `red` has blockDim.x doubles.
+__device__ __forceinline__ double block_reduce(double v, int op, double* red) {
+    const int t = threadIdx.x;
+    __syncthreads();
+    red[t] = v;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s) red[t] = op ? fmax(red[t], red[t + s]) : red[t] + red[t + s];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+// final stage: out[q] = reduce_{b} partial[b*nq + q] in a fixed order
+__global__ void k_reduce_final(const double* __restrict__ partial, int nblk, int nq, unsigned opmask,
+                               double* __restrict__ out) {
+    PS_SMEM(double, red);
+    for (int q = 0; q < nq; ++q) {
+        const int op = (opmask >> q) & 1;
+        double v = op ? -1.0e300 : 0.0;
+        for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+            const double p = partial[(long long)b * nq + q];
+            v = op ? fmax(v, p) : v + p;
+        }
+        v = block_reduce(v, op, red);
+        if (threadIdx.x == 0) out[q] = v;
+    }
+}
+
+// ---- mean vorticity (field_diagnostics.f90:584-619) -------------------------------
+// savg = (svor(0)+svor(nz))/2 + 1/nz * sum_k dst(svor)(k).  The sum over the sine
+// transform is the dot product with wz[j] = sqrt(2/nz) sum_k sin(pi j k/nz)
+// (= sqrt(2/nz) cot(pi j/(2 nz)) for odd j, 0 for even j), precomputed on the host.
+// mode 0: ini_mean = savg.  mode 1: svor(0), svor(nz) += ini_mean - savg.
+__global__ void k_vor_mean(double* svor0, double* svor1, const double* __restrict__ wz, int nz, double fnzi,
+                           double* ini_mean, int mode) {
+    PS_SMEM(double, red);
+    for (int c = 0; c < 2; ++c) {
+        double* col = c ? svor1 : svor0;
+        double v = 0.0;
+        for (int j = 1 + threadIdx.x; j < nz; j += blockDim.x) v += __ldg(&wz[j]) * col[j];
+        v = block_reduce(v, 0, red);
+        if (threadIdx.x == 0) {
+            const double savg = 0.5 * (col[0] + col[nz]) + fnzi * v;
+            if (mode == 0) ini_mean[c] = savg;
+            else { const double d = ini_mean[c] - savg; col[0] += d; col[nz] += d; }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- field reductions ------------------------------------------------------------
+enum { RQ_MAXW2 = 0, RQ_SUMW2, RQ_SUMW0, RQ_SUMW1, RQ_SUMW2C, RQ_MAXU, RQ_MAXV, RQ_MAXWV, RQ_SUMU2, RQ_SUMUW, RQ_N };
+constexpr unsigned RQ_OPMASK = (1u << RQ_MAXW2) | (1u << RQ_MAXU) | (1u << RQ_MAXV) | (1u << RQ_MAXWV);
+
+struct FieldPtrs { const double* vor[3]; const double* vel[3]; };
+
+// trapezoid-weighted sums / maxima over the physical fields
+__global__ void k_field_reduce(FieldPtrs f, long long ncol, int nz, int pz, double* __restrict__ partial) {
+    PS_SMEM(double, red);
+    double acc[RQ_N];
+#pragma unroll
+    for (int q = 0; q < RQ_N; ++q) acc[q] = ((RQ_OPMASK >> q) & 1) ? -1.0e300 : 0.0;
+    const long long n = ncol * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        if (z > nz) continue;
+        const double w = (z == 0 || z == nz) ? 0.5 : 1.0;
+        const double a = f.vor[0][i], b = f.vor[1][i], c = f.vor[2][i];
+        const double u = f.vel[0][i], v = f.vel[1][i], ww = f.vel[2][i];
+        const double w2 = a * a + b * b + c * c;
+        acc[RQ_MAXW2] = fmax(acc[RQ_MAXW2], fabs(w2));
+        acc[RQ_SUMW2] += w * w2;
+        acc[RQ_SUMW0] += w * a; acc[RQ_SUMW1] += w * b; acc[RQ_SUMW2C] += w * c;
+        acc[RQ_MAXU] = fmax(acc[RQ_MAXU], u); acc[RQ_MAXV] = fmax(acc[RQ_MAXV], v); acc[RQ_MAXWV] = fmax(acc[RQ_MAXWV], ww);
+        acc[RQ_SUMU2] += w * (u * u + v * v + ww * ww);
+        acc[RQ_SUMUW] += w * (u * a + v * b + ww * c);
+    }
+    for (int q = 0; q < RQ_N; ++q) {
+        const double r = block_reduce(acc[q], (RQ_OPMASK >> q) & 1, red);
+        if (threadIdx.x == 0) partial[(long long)blockIdx.x * RQ_N + q] = r;
+    }
+}
+
+// get_char_vorticity (field_diagnostics.f90:501-545): sums over cell-averaged |omega|
+__global__ void k_char_vorticity(FieldPtrs f, long long ncol, int nz, int pz, double vortrms,
+                                 double* __restrict__ partial) {
+    PS_SMEM(double, red);
+    double l1 = 0.0, l2 = 0.0;
+    const long long n = ncol * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        if (z < 1 || z > nz) continue;
+        const double v1 = 0.5 * fabs(f.vor[0][i - 1] + f.vor[0][i]);
+        const double v2 = 0.5 * fabs(f.vor[1][i - 1] + f.vor[1][i]);
+        const double v3 = 0.5 * fabs(f.vor[2][i - 1] + f.vor[2][i]);
+        if (v1 + v2 + v3 > vortrms) {
+            l1 += v1 + v2 + v3;
+            l2 += v1 * v1 + v2 * v2 + v3 * v3;
+        }
+    }
+    const double r1 = block_reduce(l1, 0, red);
+    const double r2 = block_reduce(l2, 0, red);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 2] = r1; partial[blockIdx.x * 2 + 1] = r2; }
+}
+
+// ---- Jacobi eigenvalues of the symmetrised strain (jacobi.f90) -----------------
+__device__ __forceinline__ void givens(double aij, double di, double dj, double& s, double& t, double& tau) {
+    const double eps = 2.220446049250313e-16;
+    const double g = 100.0 * fabs(aij);
+    const double h = dj - di;
+    if (fabs(h) + g == fabs(h)) {
+        t = aij / (h + copysign(eps, h));
+    } else {
+        const double theta = 0.5 * h / (aij + copysign(eps, aij));
+        t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+        if (theta < 0.0) t = -t;
+    }
+    const double c = 1.0 / sqrt(1.0 + t * t);
+    s = t * c;
+    tau = s / (1.0 + c);
+}
+
+// returns max |eigenvalue| (advance.f90:261-264)
+__device__ __forceinline__ double jacobi_max_abs(double d1, double a12, double a13, double d2, double a23, double d3) {
+    double b1 = d1, b2 = d2, b3 = d3;
+    double sm = fabs(a12) + fabs(a13) + fabs(a23);
+    int guard = 0;
+    while (sm > 1.0e-15 && guard < 100) {
+        double z1 = 0.0, z2 = 0.0, z3 = 0.0, s, t, tau, h, g, hh;
+        // (1,2)
+        givens(a12, d1, d2, s, t, tau);
+        h = t * a12; z1 -= h; z2 += h; d1 -= h; d2 += h; a12 = 0.0;
+        g = a13; hh = a23; a13 = g - s * (hh + g * tau); a23 = hh + s * (g - hh * tau);
+        // (1,3)
+        givens(a13, d1, d3, s, t, tau);
+        h = t * a13; z1 -= h; z3 += h; d1 -= h; d3 += h; a13 = 0.0;
+        g = a12; hh = a23; a12 = g - s * (hh + g * tau); a23 = hh + s * (g - hh * tau);
+        // (2,3)
+        givens(a23, d2, d3, s, t, tau);
+        h = t * a23; z2 -= h; z3 += h; d2 -= h; d3 += h; a23 = 0.0;
+        g = a12; hh = a13; a12 = g - s * (hh + g * tau); a13 = hh + s * (g - hh * tau);
+        b1 += z1; b2 += z2; b3 += z3;
+        d1 = b1; d2 = b2; d3 = b3;
+        sm = fabs(a12) + fabs(a13) + fabs(a23);
+        ++guard;
+    }
+    return fmax(fmax(fabs(d1), fabs(d2)), fabs(d3));
+}
+
+struct StrainPtrs { const double* dudx; const double* dudy; const double* dvdy; const double* dwdx; const double* dwdy;
+                    const double* vor[3]; };
+
+// partial[b*3 + {0,1,2}] = max over all points / points with iz = nz / iz = 0
+__global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, double* __restrict__ partial) {
+    PS_SMEM(double, red);
+    double gg = 0.0, us = 0.0, ls = 0.0;
+    const long long n = ncol * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        if (z > nz) continue;
+        const double ux = f.dudx[i], uy = f.dudy[i], vy = f.dvdy[i], wx = f.dwdx[i], wy = f.dwdy[i];
+        // advance.f90:252-257
+        const double l = jacobi_max_abs(ux, uy + 0.5 * f.vor[2][i], wx + 0.5 * f.vor[1][i], vy,
+                                        wy - 0.5 * f.vor[0][i], -(ux + vy));
+        gg = fmax(gg, l);
+        if (z == nz) us = fmax(us, l);
+        if (z == 0) ls = fmax(ls, l);
+    }
+    const double r0 = block_reduce(gg, 1, red);
+    const double r1 = block_reduce(us, 1, red);
+    const double r2 = block_reduce(ls, 1, red);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 3] = r0; partial[blockIdx.x * 3 + 1] = r1; partial[blockIdx.x * 3 + 2] = r2; }
+}
+
+}  // namespace ps3d

@@ -1,0 +1,998 @@
+// libps3d_cuda: context, host-side orchestration and the C ABI (include/ps3d_cuda.h).
+//
+// Host logic restated from the reference (file:line under /root/reference/src):
+//   init          <- mpi/mpi_layout.f90:53, utils/parameters.f90:61, fft/sta3dfft.f90:53
+//   init_inversion<- inversion/inversion_utils.f90:222-455 (2-D / 1-D tables only)
+//   vor2vel/source<- inversion/inversion.f90:23-226, 298-388
+//   adapt         <- stepper/advance.f90:109-410, utils/rolling_mean.f90:36-69
+//   steppers      <- stepper/cn2.f90:40-181, stepper/impl_rk4.f90:37-207
+#include <cstdarg>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/ps3d_cuda.h"
+#include "rt.h"
+#include "fft_core.cuh"
+#include "line_fft.cuh"
+#include "zcol.cuh"
+#include "pointwise.cuh"
+
+namespace ps3d {
+
+std::string g_last_error;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+struct StatusError { int code; };
+[[noreturn]] static void fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    throw StatusError{code};
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) { release(); p = (T*)ps_malloc(count * sizeof(T)); n = count; }
+    void release() { if (p) ps_free(p); p = nullptr; n = 0; }
+    void upload(const std::vector<T>& h, ps_stream_t s) {
+        if (h.size() != n) alloc(h.size());
+        ps_h2d(p, h.data(), h.size() * sizeof(T), s);
+        ps_sync(s);
+    }
+};
+
+static const int RED_BLOCKS = 1184;   // 148 SMs x 8
+static const int RED_THREADS = 256;
+
+struct RollingMean {   // utils/rolling_mean.f90:36-69
+    std::vector<double> history;
+    int inew = 1, iold = 1, length = 0;
+    double sma = 0.0;
+    bool filled = false;
+    void alloc(int n) { if (history.empty()) history.assign(n, 0.0); length = n; }
+    double get_next(double vnew) {
+        if (filled) {
+            const double vold = history[iold - 1];
+            iold = iold % length + 1;
+            sma = sma + (vnew - vold) / (double)length;
+            history[inew - 1] = vnew;
+            inew = inew % length + 1;
+        } else {
+            history[inew - 1] = vnew;
+            double s = 0.0;
+            for (int i = 0; i < inew; ++i) s += history[i];
+            sma = s / (double)inew;
+            filled = (length == inew);
+            inew = inew % length + 1;
+        }
+        return sma;
+    }
+};
+
+struct Ctx {
+    int nx = 0, ny = 0, nz = 0, nzp = 0, pz = 0;
+    int rank = 0, nranks = 1, nxl = 0, nyl = 0;
+    double lower[3], extent[3], upper[3], dx[3];
+    long long ncell = 0;
+    size_t nint = 0;     // doubles per internal field (nxl*ny*pz == nx*nyl*pz)
+    size_t nnat = 0;     // doubles per host field on this rank (nxl*ny*nzp)
+    ps_stream_t stream = 0;
+    bool inversion_ready = false, diffusion_ready = false;
+    int filtering = 0, nnu = 3, stepper = PS3D_STEPPER_CN2;
+    bool stepper_ready = false;
+    double vvisc = 0.0;
+    RollingMean rollmean;
+    long long launches = 0;
+    double last_advance_ms = 0.0;
+
+    DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[6];
+    DevBuf<double> stage;                 // natural-layout staging for the host boundary
+    DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
+    DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
+    DevBuf<double2> tw;
+    DevBuf<long long> ro_phys_y, ro_spec_y, ro_x;
+    DevBuf<int> permy;
+    int ntw = 0;
+    std::vector<double> h_rkx, h_rky, h_rkz, h_k2l2, h_filt2d;   // host copies ([kx][kyl] local order)
+    std::vector<int> h_ky_of_kyl;
+    double* h_red = nullptr;              // host landing buffer for reductions
+#ifndef PS3D_EMU
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#endif
+
+    SpecGeom geom() const {
+        SpecGeom g;
+        g.nx = nx; g.nyl = nyl; g.nz = nz; g.pz = pz;
+        g.has00 = (rank == 0);
+        g.kxd = kxd.p; g.kyd = kyd.p; g.k2l2 = k2l2.p; g.k2l2i = k2l2i.p;
+        g.zm = zm.p; g.zp = zp.p; g.rkz = rkz.p; g.gamtop = gamtop.p; g.gambot = gambot.p;
+        g.Lz = extent[2]; g.dzi = 1.0 / dx[2]; g.hdzi = 0.5 * (1.0 / dx[2]);
+        g.tw = tw.p; g.ntw = ntw;
+        return g;
+    }
+    int ngroups() const { return (nx / 2 + 1) * (nyl / 2); }
+};
+
+static Ctx* g_ctx = nullptr;
+
+static Ctx& ctx() {
+    if (!g_ctx) fail(PS3D_ERR_NOT_INITIALISED, "ps3d_cuda_init has not been called");
+    return *g_ctx;
+}
+
+static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// ---------------------------------------------------------------------------
+// kernel launch helpers with compile-time size dispatch
+// ---------------------------------------------------------------------------
+#ifndef PS3D_EMU
+template <class K>
+static void allow_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        PS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+#else
+template <class K>
+static void allow_smem(K, size_t) {}
+#endif
+
+#define PS_FOR_LINE_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
+#define PS_FOR_Z_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512)
+
+template <int N>
+static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles) {
+    const size_t sm = line_smem_bytes<N>();
+    const dim3 grid(ntiles), block(N / 2);
+    if (!inv) {
+        if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS>), grid, block, sm, c.stream, a); }
+        else { allow_smem(k_line_fwd<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN>), grid, block, sm, c.stream, a); }
+    } else {
+        if (pro == PRO_DIFF) { allow_smem(k_line_inv<N, PRO_DIFF>, sm); PS_LAUNCH((k_line_inv<N, PRO_DIFF>), grid, block, sm, c.stream, a); }
+        else { allow_smem(k_line_inv<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_inv<N, PRO_PLAIN>), grid, block, sm, c.stream, a); }
+    }
+    ++c.launches;
+}
+
+static void launch_line(Ctx& c, int n, bool inv, int pro, const LineArgs& a, int ntiles) {
+    switch (n) {
+#define X(NN) case NN: launch_line_n<NN>(c, inv, pro, a, ntiles); break;
+        PS_FOR_LINE_SIZES(X)
+#undef X
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "line length %d not supported (power of two, 8..1024)", n);
+    }
+}
+
+// one x or y sweep.  axis: 0 = x, 1 = y.
+struct Sweep { int axis; bool inv; int pro; const double* in[4]; double add1, add3; double* out; };
+
+static void run_sweep(Ctx& c, const Sweep& s) {
+    LineArgs a;
+    a.in0 = s.in[0]; a.in1 = s.in[1]; a.in2 = s.in[2]; a.in3 = s.in[3];
+    a.add1 = s.add1; a.add3 = s.add3;
+    a.out = s.out;
+    a.nzc = c.pz / 8;
+    a.tw = c.tw.p;
+    int n, nouter;
+    if (s.axis == 1) {
+        n = c.ny; nouter = c.nxl;
+        // physical side [xl][y][pz]; spectral side [xl][ky'][pz] (== [kx][kyl][pz] for one rank)
+        a.in_os = (long long)c.ny * c.pz; a.out_os = (long long)c.ny * c.pz;
+        a.in_rowoff = s.inv ? c.ro_spec_y.p : c.ro_phys_y.p;
+        a.out_rowoff = s.inv ? c.ro_phys_y.p : c.ro_spec_y.p;
+        a.kdiff = c.kyline.p;
+    } else {
+        n = c.nx; nouter = c.nyl;
+        a.in_os = c.pz; a.out_os = c.pz;
+        a.in_rowoff = c.ro_x.p; a.out_rowoff = c.ro_x.p;
+        a.kdiff = c.kxl.p;
+    }
+    a.scale = 1.0 / std::sqrt((double)n);
+    a.twscale = c.ntw / n;
+    launch_line(c, n, s.inv, s.pro, a, nouter * a.nzc);
+}
+
+static void require_single_rank(Ctx& c) {
+    if (c.nranks != 1) fail(PS3D_ERR_UNSUPPORTED, "multi-rank slab exchange is not available in this build");
+}
+
+// fftxyp2s on internal layouts: physical [x][y][pz] -> semi-spectral [kx][ky'][pz]
+static void fft2d_fwd(Ctx& c, const double* in, double* out, double* tmp) {
+    require_single_rank(c);
+    Sweep sy{1, false, PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, tmp};
+    run_sweep(c, sy);
+    Sweep sx{0, false, PRO_PLAIN, {tmp, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
+    run_sweep(c, sx);
+}
+
+// a*(b+add1) - c*(d+add3) -> forward 2-D FFT
+static void fft2d_fwd_cross(Ctx& c, const double* a, const double* b, double add1, const double* cc, const double* d,
+                            double add3, double* out, double* tmp) {
+    require_single_rank(c);
+    Sweep sy{1, false, PRO_CROSS, {a, b, cc, d}, add1, add3, tmp};
+    run_sweep(c, sy);
+    Sweep sx{0, false, PRO_PLAIN, {tmp, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
+    run_sweep(c, sx);
+}
+
+// fftxys2p (optionally of d/dx or d/dy of the input): [kx][ky'][pz] -> [x][y][pz]
+static void fft2d_inv(Ctx& c, const double* in, double* out, double* tmp, bool dx, bool dy) {
+    require_single_rank(c);
+    Sweep sx{0, true, dx ? PRO_DIFF : PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, tmp};
+    run_sweep(c, sx);
+    Sweep sy{1, true, dy ? PRO_DIFF : PRO_PLAIN, {tmp, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
+    run_sweep(c, sy);
+}
+
+template <int NZ>
+static void launch_zop_n(Ctx& c, int op, const double* in, double* out) {
+    const size_t sm = zop_smem_bytes<NZ>();
+    allow_smem(k_zop<NZ>, sm);
+    PS_LAUNCH((k_zop<NZ>), dim3(c.ngroups()), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom(), op, in, out);
+    ++c.launches;
+}
+static void launch_zop(Ctx& c, int op, const double* in, double* out) {
+    switch (c.nz) {
+#define X(NN) case NN: launch_zop_n<NN>(c, op, in, out); break;
+        PS_FOR_Z_SIZES(X)
+#undef X
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..512)", c.nz);
+    }
+}
+
+template <int NZ>
+static void launch_v2v_n(Ctx& c, const V2VArgs& a) {
+    const size_t sm = v2v_smem_bytes<NZ>();
+    allow_smem(k_vor2vel_spec<NZ>, sm);
+    PS_LAUNCH((k_vor2vel_spec<NZ>), dim3(c.ngroups()), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom(), a);
+    ++c.launches;
+}
+static void launch_v2v(Ctx& c, const V2VArgs& a) {
+    switch (c.nz) {
+#define X(NN) case NN: launch_v2v_n<NN>(c, a); break;
+        PS_FOR_Z_SIZES(X)
+#undef X
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..512)", c.nz);
+    }
+}
+
+template <int NZ>
+static void launch_src_n(Ctx& c, const SrcArgs& a) {
+    const size_t sm = src_smem_bytes<NZ>();
+    allow_smem(k_source_spec<NZ>, sm);
+    PS_LAUNCH((k_source_spec<NZ>), dim3(c.ngroups()), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom(), a);
+    ++c.launches;
+}
+static void launch_src(Ctx& c, const SrcArgs& a) {
+    switch (c.nz) {
+#define X(NN) case NN: launch_src_n<NN>(c, a); break;
+        PS_FOR_Z_SIZES(X)
+#undef X
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..512)", c.nz);
+    }
+}
+
+static int stream_blocks(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16); }
+
+// ---------------------------------------------------------------------------
+// host boundary: natural Fortran layout <-> internal layouts
+// ---------------------------------------------------------------------------
+static void to_device(Ctx& c, const double* host, double* dev, bool spectral) {
+    ps_h2d(c.stage.p, host, c.nnat * sizeof(double), c.stream);
+    PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.stage.p, dev, c.nxl,
+              c.ny, c.nzp, c.pz, spectral ? (const int*)c.permy.p : (const int*)nullptr);
+    ++c.launches;
+}
+static void to_host(Ctx& c, const double* dev, double* host, bool spectral) {
+    PS_LAUNCH((k_repack_out), dim3(stream_blocks(c.nnat)), dim3(256), 0, c.stream, dev, c.stage.p, c.nxl, c.ny, c.nzp,
+              c.pz, spectral ? (const int*)c.permy.p : (const int*)nullptr);
+    ++c.launches;
+    ps_d2h(host, c.stage.p, c.nnat * sizeof(double), c.stream);
+    ps_sync(c.stream);
+}
+
+// ---------------------------------------------------------------------------
+// init
+// ---------------------------------------------------------------------------
+static void do_init(int nx, int ny, int nz, const double* lower, const double* extent, int rank, int nranks) {
+    if (g_ctx) fail(PS3D_ERR_BAD_ARGUMENT, "ps3d_cuda_init called twice without ps3d_cuda_finalise");
+    if (!lower || !extent) fail(PS3D_ERR_BAD_ARGUMENT, "null lower/extent");
+    if (!pow2(nx) || !pow2(ny) || !pow2(nz) || nx < 8 || ny < 8 || nz < 8 || nx > 1024 || ny > 1024 || nz > 512)
+        fail(PS3D_ERR_UNSUPPORTED_SIZE,
+             "grid %dx%dx%d: this build supports power-of-two nx, ny in 8..1024 and nz in 8..512", nx, ny, nz);
+    if (nranks < 1 || rank < 0 || rank >= nranks || nx % nranks || (ny / 2) % nranks)
+        fail(PS3D_ERR_BAD_ARGUMENT, "bad rank layout %d/%d for %dx%d", rank, nranks, nx, ny);
+    for (int i = 0; i < 3; ++i)
+        if (!(extent[i] > 0.0)) fail(PS3D_ERR_BAD_ARGUMENT, "domain extent must be positive (sta2dfft.f90:59-74)");
+#ifndef PS3D_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        fail(PS3D_ERR_NO_DEVICE, "no CUDA device: libps3d_cuda has no CPU path");
+    PS_CUDA_TRY(cudaSetDevice(rank % ndev));
+#endif
+    Ctx* c = new Ctx();
+    g_ctx = c;
+    c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
+    c->pz = (c->nzp + 7) / 8 * 8;
+    c->rank = rank; c->nranks = nranks;
+    c->nxl = nx / nranks; c->nyl = ny / nranks;
+    for (int i = 0; i < 3; ++i) {
+        c->lower[i] = lower[i]; c->extent[i] = extent[i];
+        c->upper[i] = lower[i] + extent[i];
+    }
+    c->dx[0] = extent[0] / (double)nx; c->dx[1] = extent[1] / (double)ny; c->dx[2] = extent[2] / (double)nz;
+    c->ncell = (long long)nx * ny * nz;
+    c->nint = (size_t)c->nxl * ny * c->pz;
+    c->nnat = (size_t)c->nxl * ny * c->nzp;
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PS_CUDA_TRY(cudaEventCreate(&c->ev0));
+    PS_CUDA_TRY(cudaEventCreate(&c->ev1));
+    PS_CUDA_TRY(cudaMallocHost((void**)&c->h_red, 64 * sizeof(double)));
+#else
+    c->h_red = (double*)calloc(64, sizeof(double));
+#endif
+    ps_stream_t s = c->stream;
+
+    // twiddles: exp(2 pi i m / ntw), ntw = max(nx, ny, 2 nz)
+    c->ntw = std::max(std::max(nx, ny), 2 * nz);
+    {
+        std::vector<double2> tw(c->ntw);
+        for (int m = 0; m < c->ntw; ++m) {
+            const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)c->ntw;
+            tw[m] = make_double2((double)cosl(ang), (double)sinl(ang));
+        }
+        // exact values on the axes / diagonals
+        const int q = c->ntw / 4;
+        tw[0] = make_double2(1.0, 0.0); tw[q] = make_double2(0.0, 1.0);
+        tw[2 * q] = make_double2(-1.0, 0.0); tw[3 * q] = make_double2(0.0, -1.0);
+        c->tw.upload(tw, s);
+    }
+    // wavenumbers: sta2dfft.f90:59-66, sta3dfft.f90:89-108, deriv1d.f90:17-22
+    const double pi = std::acos(-1.0);
+    c->h_rkx.assign(nx, 0.0); c->h_rky.assign(ny, 0.0); c->h_rkz.assign(nz + 1, 0.0);
+    {
+        const double scx = pi / extent[0], scy = pi / extent[1], scz = pi / extent[2];
+        for (int k = 1; k < nx / 2; ++k) { c->h_rkx[k] = scx * (double)(2 * k); c->h_rkx[nx - k] = c->h_rkx[k]; }
+        c->h_rkx[nx / 2] = scx * (double)nx;
+        for (int k = 1; k < ny / 2; ++k) { c->h_rky[k] = scy * (double)(2 * k); c->h_rky[ny - k] = c->h_rky[k]; }
+        c->h_rky[ny / 2] = scy * (double)ny;
+        for (int k = 1; k <= nz; ++k) c->h_rkz[k] = scz * (double)k;
+        std::vector<double> kxl(nx / 2 + 1, 0.0), kyl(ny / 2 + 1, 0.0);
+        for (int k = 1; k < nx / 2; ++k) kxl[k] = c->h_rkx[k];     // 0 at k = 0 and nx/2 (sta3dfft.f90:321-335)
+        for (int k = 1; k < ny / 2; ++k) kyl[k] = c->h_rky[k];
+        c->kxl.upload(kxl, s); c->kyline.upload(kyl, s); c->kxd.upload(kxl, s);
+        c->rkz.upload(c->h_rkz, s);
+    }
+    // paired ky order: ky' = 2a + sy;  a = 0: (0, ny/2);  a >= 1: (a, ny - a)
+    {
+        std::vector<int> perm(ny);
+        perm[0] = 0; perm[ny / 2] = 1;
+        for (int k = 1; k < ny / 2; ++k) { perm[k] = 2 * k; perm[ny - k] = 2 * k + 1; }
+        c->permy.upload(perm, s);
+        c->h_ky_of_kyl.assign(c->nyl, 0);
+        std::vector<double> kyd(c->nyl / 2, 0.0);
+        for (int k = 0; k < ny; ++k) {
+            const int kp = perm[k];
+            if (kp / c->nyl == rank) c->h_ky_of_kyl[kp % c->nyl] = k;
+        }
+        for (int ap = 0; ap < c->nyl / 2; ++ap) {
+            const int a = (rank * c->nyl) / 2 + ap;
+            kyd[ap] = (a == 0) ? 0.0 : c->h_rky[a];
+        }
+        c->kyd.upload(kyd, s);
+        std::vector<long long> rp(ny), rs(ny), rx(nx);
+        for (int k = 0; k < ny; ++k) {
+            rp[k] = (long long)k * c->pz;
+            const int kp = perm[k];
+            const int d = kp / c->nyl, kl = kp % c->nyl;
+            rs[k] = ((long long)d * c->nxl * c->nyl + kl) * c->pz;
+        }
+        for (int k = 0; k < nx; ++k) rx[k] = (long long)k * c->nyl * c->pz;
+        c->ro_phys_y.upload(rp, s); c->ro_spec_y.upload(rs, s); c->ro_x.upload(rx, s);
+    }
+    c->stage.alloc(c->nnat);
+    for (int i = 0; i < 6; ++i) c->W[i].alloc(c->nint);
+    c->partial.alloc((size_t)RED_BLOCKS * 16);
+    c->red.alloc(64);
+}
+
+static void do_init_inversion(int filtering) {
+    Ctx& c = ctx();
+    if (c.inversion_ready) return;                       // inversion_utils.f90:227-229
+    if (filtering != PS3D_FILTER_HOU_LI && filtering != PS3D_FILTER_23_RULE)
+        fail(PS3D_ERR_BAD_ARGUMENT, "unknown filtering id %d", filtering);
+    c.filtering = filtering;
+    const int nx = c.nx, ny = c.ny, nz = c.nz, nyl = c.nyl;
+    ps_stream_t s = c.stream;
+    // k2l2, k2l2i (inversion_utils.f90:240-258), one row per slot pair b = min(kx, nx-kx)
+    std::vector<double> k2((size_t)(nx / 2 + 1) * nyl), k2i(k2.size());
+    for (int b = 0; b <= nx / 2; ++b)
+        for (int kl = 0; kl < nyl; ++kl) {
+            const int ky = c.h_ky_of_kyl[kl];
+            double v = c.h_rkx[b] * c.h_rkx[b] + c.h_rky[ky] * c.h_rky[ky];
+            double vi;
+            if (b == 0 && ky == 0) { v = 0.0; vi = 0.0; } else vi = 1.0 / v;
+            k2[(size_t)b * nyl + kl] = v; k2i[(size_t)b * nyl + kl] = vi;
+        }
+    c.k2l2.upload(k2, s); c.k2l2i.upload(k2i, s);
+    // full [kx][kyl] copies for the steppers
+    c.h_k2l2.assign((size_t)nx * nyl, 0.0);
+    for (int kx = 0; kx < nx; ++kx)
+        for (int kl = 0; kl < nyl; ++kl)
+            c.h_k2l2[(size_t)kx * nyl + kl] = k2[(size_t)std::min(kx, nx - kx) * nyl + kl];
+    // de-aliasing filter, separable parts (inversion_utils.f90:377-455)
+    double rkxmax = 0, rkymax = 0, rkzmax = 0;
+    for (double v : c.h_rkx) rkxmax = std::max(rkxmax, v);
+    for (double v : c.h_rky) rkymax = std::max(rkymax, v);
+    for (double v : c.h_rkz) rkzmax = std::max(rkzmax, v);
+    std::vector<double> filtz(nz + 1, 1.0);
+    c.h_filt2d.assign((size_t)nx * nyl, 0.0);
+    if (filtering == PS3D_FILTER_HOU_LI) {
+        const double kxmaxi = 1.0 / rkxmax, kymaxi = 1.0 / rkymax, kzmaxi = 1.0 / rkzmax;
+        for (int kx = 0; kx < nx; ++kx)
+            for (int kl = 0; kl < nyl; ++kl) {
+                const double skx = -36.0 * std::pow(kxmaxi * c.h_rkx[kx], 36);
+                const double sky = -36.0 * std::pow(kymaxi * c.h_rky[c.h_ky_of_kyl[kl]], 36);
+                c.h_filt2d[(size_t)kx * nyl + kl] = std::exp(skx + sky);
+            }
+        for (int kz = 1; kz < nz; ++kz) filtz[kz] = std::exp(-36.0 * std::pow(kzmaxi * c.h_rkz[kz], 36));
+    } else {
+        const double f23 = 2.0 / 3.0;
+        for (int kx = 0; kx < nx; ++kx)
+            for (int kl = 0; kl < nyl; ++kl)
+                c.h_filt2d[(size_t)kx * nyl + kl] =
+                    ((c.h_rkx[kx] <= f23 * rkxmax) ? 1.0 : 0.0) * ((c.h_rky[c.h_ky_of_kyl[kl]] <= f23 * rkymax) ? 1.0 : 0.0);
+        for (int kz = 1; kz < nz; ++kz) filtz[kz] = (c.h_rkz[kz] <= f23 * rkzmax) ? 1.0 : 0.0;
+    }
+    if (c.rank == 0) c.h_filt2d[0] = 1.0;                // filt(:,0,0) = 1 (inversion_utils.f90:275-277)
+    c.filt2d.upload(c.h_filt2d, s); c.filtz.upload(filtz, s);
+    // zm, zp (inversion_utils.f90:293-297); gamtop, gambot (:350-369)
+    std::vector<double> zm(nz + 1), zp(nz + 1), gt(nz + 1), gb(nz + 1), wz(nz + 1, 0.0);
+    for (int iz = 0; iz <= nz; ++iz) {
+        const double z = c.lower[2] + c.dx[2] * (double)iz;
+        zm[iz] = c.upper[2] - z;
+        zp[iz] = z - c.lower[2];
+    }
+    for (int iz = 0; iz <= nz; ++iz) {
+        const double ph = zp[iz] / c.extent[2];
+        gt[iz] = 0.5 * c.extent[2] * (ph * ph - 1.0 / 3.0);
+    }
+    for (int iz = 0; iz <= nz; ++iz) gb[iz] = gt[nz - iz];
+    // weights of sum_k dst(x)(k) (field_diagnostics.f90:592-596)
+    for (int j = 1; j < nz; j += 2) {
+        const long double a = 3.14159265358979323846264338327950288L * (long double)j / (2.0L * (long double)nz);
+        wz[j] = (double)(std::sqrt(2.0L / (long double)nz) * (cosl(a) / sinl(a)));
+    }
+    c.zm.upload(zm, s); c.zp.upload(zp, s); c.gamtop.upload(gt, s); c.gambot.upload(gb, s); c.wz.upload(wz, s);
+    for (int i = 0; i < 3; ++i) {
+        c.svor[i].alloc(c.nint); c.vor[i].alloc(c.nint); c.vel[i].alloc(c.nint);
+        c.svel[i].alloc(c.nint); c.svorts[i].alloc(c.nint);
+    }
+    c.ini_mean.alloc(2);
+    c.vhdis.alloc((size_t)nx * nyl); c.fac1.alloc((size_t)nx * nyl); c.fac2.alloc((size_t)nx * nyl);
+    c.inversion_ready = true;
+}
+
+static Ctx& ready() {
+    Ctx& c = ctx();
+    if (!c.inversion_ready) fail(PS3D_ERR_NOT_INITIALISED, "Error: Inversion not initialised!");
+    return c;
+}
+
+static double do_init_diffusion(int nnu, double prediss, int lscale, double te, double en) {
+    Ctx& c = ready();
+    // get_viscosity (inversion_utils.f90:157-184)
+    double rkxmax = 0, rkymax = 0;
+    for (double v : c.h_rkx) rkxmax = std::max(rkxmax, v);
+    for (double v : c.h_rky) rkymax = std::max(rkymax, v);
+    const double K2max = std::pow(std::max(rkxmax, rkymax), 2);
+    const double rkmsi = 1.0 / K2max;
+    double vis;
+    if (lscale == PS3D_LSCALE_KOLMOGOROV) vis = prediss * std::pow(K2max * te / en, 1.0 / 3.0) * std::pow(rkmsi, nnu);
+    else if (lscale == PS3D_LSCALE_GEOPHYSICAL) vis = prediss * std::pow(rkmsi, nnu);
+    else fail(PS3D_ERR_BAD_ARGUMENT, "We only support 'Kolmogorov' or 'geophysical'");
+    c.vvisc = vis; c.nnu = nnu;
+    std::vector<double> vh(c.h_k2l2.size());
+    for (size_t i = 0; i < vh.size(); ++i) vh[i] = (nnu == 1) ? vis * c.h_k2l2[i] : vis * std::pow(c.h_k2l2[i], nnu);
+    c.vhdis.upload(vh, c.stream);
+    c.diffusion_ready = true;
+    return vis;
+}
+
+static void do_finalise() {
+    if (!g_ctx) return;
+    Ctx* c = g_ctx;
+    ps_sync(c->stream);
+    DevBuf<double>* groups[] = {c->svor, c->vor, c->vel, c->svel, c->svorts, c->wa, c->wb};
+    for (auto* g : groups) for (int i = 0; i < 3; ++i) g[i].release();
+    for (int i = 0; i < 6; ++i) c->W[i].release();
+    DevBuf<double>* singles[] = {&c->stage, &c->kxl, &c->kyline, &c->kxd, &c->kyd, &c->k2l2, &c->k2l2i, &c->zm, &c->zp,
+                                 &c->rkz, &c->gamtop, &c->gambot, &c->filt2d, &c->filtz, &c->vhdis, &c->fac1, &c->fac2,
+                                 &c->wz, &c->ini_mean, &c->partial, &c->red};
+    for (auto* b : singles) b->release();
+    c->tw.release(); c->ro_phys_y.release(); c->ro_spec_y.release(); c->ro_x.release(); c->permy.release();
+#ifndef PS3D_EMU
+    if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+#else
+    free(c->h_red);
+#endif
+    delete c;
+    g_ctx = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// resident-mode operators
+// ---------------------------------------------------------------------------
+static void do_vor2vel(Ctx& c) {
+    V2VArgs a;
+    a.svor0 = c.svor[0].p; a.svor1 = c.svor[1].p; a.svor2 = c.svor[2].p;
+    a.wsem0 = c.W[0].p; a.wsem1 = c.W[1].p; a.wsem2 = c.W[2].p;
+    a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
+    launch_v2v(c, a);
+    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.W[i].p, c.vor[i].p, c.W[3].p, false, false);
+    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.svel[i].p, c.vel[i].p, c.W[3].p, false, false);
+}
+
+static void do_source(Ctx& c) {
+    const double fc[3] = {0.0, 0.0, 0.0};    // physics.f90 f_cor: zero for the configurations in scope
+    const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
+    const double *xi = c.vor[0].p, *eta = c.vor[1].p, *zeta = c.vor[2].p;
+    // r = u*eta - v*xi ; q = w*xi - u*zeta ; p = v*zeta - w*eta   (inversion.f90:327,336,350)
+    fft2d_fwd_cross(c, u, eta, fc[1], v, xi, fc[0], c.W[0].p, c.W[3].p);
+    fft2d_fwd_cross(c, w, xi, fc[0], u, zeta, fc[2], c.W[1].p, c.W[3].p);
+    fft2d_fwd_cross(c, v, zeta, fc[2], w, eta, fc[1], c.W[2].p, c.W[3].p);
+    SrcArgs a;
+    a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
+    a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
+    launch_src(c, a);
+}
+
+static void vor_mean(Ctx& c, int mode) {
+    if (c.rank != 0) return;
+    PS_LAUNCH((k_vor_mean), dim3(1), dim3(256), 256 * sizeof(double), c.stream, c.svor[0].p, c.svor[1].p,
+              (const double*)c.wz.p, c.nz, 1.0 / (double)c.nz, c.ini_mean.p, mode);
+    ++c.launches;
+}
+
+static FieldPtrs field_ptrs(Ctx& c) {
+    FieldPtrs f;
+    for (int i = 0; i < 3; ++i) { f.vor[i] = c.vor[i].p; f.vel[i] = c.vel[i].p; }
+    return f;
+}
+
+// reduces the physical fields into c.red[0..RQ_N)
+static void field_reduce(Ctx& c) {
+    const long long ncol = (long long)c.nxl * c.ny;
+    PS_LAUNCH((k_field_reduce), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              field_ptrs(c), ncol, c.nz, c.pz, c.partial.p);
+    PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              (const double*)c.partial.p, RED_BLOCKS, (int)RQ_N, RQ_OPMASK, c.red.p);
+    c.launches += 2;
+}
+
+static void do_set_diffusion(Ctx& c, double dt, double pref) {
+    if (!c.diffusion_ready) fail(PS3D_ERR_NOT_INITIALISED, "init_diffusion has not been called");
+    const long long ncol = (long long)c.nx * c.nyl;
+    if (c.stepper == PS3D_STEPPER_CN2) {
+        const double dfac = (c.nnu == 1) ? dt : pref * dt;          // cn2.f90:50-56
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 0, dfac, (const double*)c.vhdis.p,
+                  (const double*)c.filt2d.p, c.fac1.p, c.fac2.p, ncol);
+    } else {
+        const double dfac = 0.5 * pref * dt;                         // impl_rk4.f90:43
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 1, dfac, (const double*)c.vhdis.p,
+                  (const double*)c.filt2d.p, c.fac1.p, c.fac2.p, ncol);
+    }
+    ++c.launches;
+}
+
+static StepArgs step_args(Ctx& c) {
+    StepArgs a;
+    for (int i = 0; i < 3; ++i) { a.svor[i] = c.svor[i].p; a.svorts[i] = c.svorts[i].p; a.wa[i] = c.wa[i].p; a.wb[i] = c.wb[i].p; }
+    a.f2d = c.fac2.p; a.filtz = c.filtz.p; a.mq = c.fac1.p; a.pq = c.fac2.p; a.vd = c.fac1.p;
+    a.c1 = a.c2 = 0.0; a.stage = 0;
+    a.ncol = (long long)c.nx * c.nyl; a.nz = c.nz; a.pz = c.pz; a.has00 = (c.rank == 0);
+    return a;
+}
+
+static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype, int win, double* dt_out, double* diag);
+
+static void do_stepper_setup(Ctx& c, int stepper) {
+    if (stepper != PS3D_STEPPER_CN2 && stepper != PS3D_STEPPER_IMPL_RK4)
+        fail(PS3D_ERR_BAD_ARGUMENT, "unknown stepper id %d", stepper);
+    c.stepper = stepper;
+    for (int i = 0; i < 3; ++i) {
+        if (!c.wa[i].p) c.wa[i].alloc(c.nint);
+        if (stepper == PS3D_STEPPER_IMPL_RK4 && !c.wb[i].p) c.wb[i].alloc(c.nint);
+    }
+    c.stepper_ready = true;
+}
+
+static void cn2_update(Ctx& c, double dt2, int stage) {
+    StepArgs a = step_args(c);
+    a.c1 = dt2; a.stage = stage;
+    PS_LAUNCH((k_cn2_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, a);
+    ++c.launches;
+    vor_mean(c, 1);
+}
+
+static void rk4_update(Ctx& c, int stage, double c1, double c2, const double* pq) {
+    StepArgs a = step_args(c);
+    a.c1 = c1; a.c2 = c2; a.stage = stage; a.pq = pq;
+    PS_LAUNCH((k_rk4_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, a);
+    ++c.launches;
+}
+
+static void do_step(Ctx& c, double* t, double dt) {
+    if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
+    const long long ncol = (long long)c.nx * c.nyl;
+    if (c.stepper == PS3D_STEPPER_CN2) {
+        const double dt2 = 0.5 * dt;                       // cn2.f90:101
+        cn2_update(c, dt2, 0);                             // :120-137
+        for (int iter = 0; iter < 2; ++iter) {             // niter = 2 (:34, :143-177)
+            do_vor2vel(c);
+            do_source(c);
+            cn2_update(c, dt2, 1);
+        }
+        *t += dt;
+    } else {
+        const double dt2 = 0.5 * dt, dt3 = dt / 3.0, dt6 = dt / 6.0;   // impl_rk4.f90:82-84
+        // substep one filters the source with filt(0,:,:) (:227-229)
+        rk4_update(c, 1, dt2, dt6, c.filt2d.p);
+        do_vor2vel(c); do_source(c);
+        *t += dt2;
+        rk4_update(c, 2, dt2, dt3, c.fac2.p);
+        do_vor2vel(c); do_source(c);
+        *t += dt2;
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 2, 0.0, (const double*)nullptr,
+                  (const double*)nullptr, c.fac1.p, c.fac2.p, ncol);    // emq = emq**2 (:151)
+        ++c.launches;
+        rk4_update(c, 3, dt, dt3, c.fac2.p);
+        do_vor2vel(c); do_source(c);
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 3, 0.0, (const double*)nullptr,
+                  (const double*)nullptr, c.fac1.p, c.fac2.p, ncol);    // epq = epq**2 (:185)
+        ++c.launches;
+        rk4_update(c, 4, dt6, 0.0, c.fac2.p);
+        vor_mean(c, 1);                                    // :205
+    }
+}
+
+static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype, int win, double* dt_out, double* diag) {
+    const long long ncol = (long long)c.nxl * c.ny;
+    field_reduce(c);
+    // char vorticity needs vortrms = sqrt(<|omega|^2>) (advance.f90:180-183); computed on the host from the
+    // first reduction to keep the reference's evaluation order
+    ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    double r1[RQ_N];
+    for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
+    const double vortmax = std::sqrt(r1[RQ_MAXW2]);
+    const double vortrms = std::sqrt(r1[RQ_SUMW2] / (double)c.ncell);
+    PS_LAUNCH((k_char_vorticity), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              field_ptrs(c), ncol, c.nz, c.pz, vortrms, c.partial.p);
+    PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              (const double*)c.partial.p, RED_BLOCKS, 2, 0u, c.red.p);
+    c.launches += 2;
+    // velocity strain (advance.f90:199-217): derivative folded into the inverse sweeps
+    fft2d_inv(c, c.svel[0].p, c.W[0].p, c.W[5].p, true, false);    // du/dx
+    fft2d_inv(c, c.svel[0].p, c.W[1].p, c.W[5].p, false, true);    // du/dy
+    fft2d_inv(c, c.svel[2].p, c.W[2].p, c.W[5].p, true, false);    // dw/dx
+    fft2d_inv(c, c.svel[1].p, c.W[3].p, c.W[5].p, false, true);    // dv/dy
+    fft2d_inv(c, c.svel[2].p, c.W[4].p, c.W[5].p, false, true);    // dw/dy
+    StrainPtrs sp;
+    sp.dudx = c.W[0].p; sp.dudy = c.W[1].p; sp.dwdx = c.W[2].p; sp.dvdy = c.W[3].p; sp.dwdy = c.W[4].p;
+    for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
+    // k_strain writes partial[b*3..], after the char-vorticity final reduce has consumed partial (same stream)
+    PS_LAUNCH((k_strain), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream, sp, ncol, c.nz,
+              c.pz, c.partial.p);
+    PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              (const double*)c.partial.p, RED_BLOCKS, 3, 7u, c.red.p + 2);
+    c.launches += 2;
+    ps_d2h(c.h_red, c.red.p, 5 * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    const double small = 1.0e-12, cflmax = 0.8;                    // constants.f90:63-65
+    const double vorl1 = small + c.h_red[0], vorl2 = c.h_red[1];
+    const double vorch = vorl2 / vorl1;
+    const double bfmax = 0.0;
+    const double ggmax = std::max(2.220446049250313e-16, c.h_red[2]);   // ggmax = epsilon(ggmax) (advance.f90:222)
+    const double usggmax = std::max(0.0, c.h_red[3]), lsggmax = std::max(0.0, c.h_red[4]);
+    const double umax = r1[RQ_MAXU], vmax = r1[RQ_MAXV], wmax = r1[RQ_MAXWV];
+    const double dtcfl = cflmax * std::min(std::min(c.dx[0] / (umax + small), c.dx[1] / (vmax + small)),
+                                           c.dx[2] / (wmax + small));
+    const double dt = std::min(std::min(alpha / (ggmax + small), alpha / (bfmax + small)), std::min(dtcfl, t_limit - t));
+    c.rollmean.alloc(win);
+    const double rmv = c.rollmean.get_next(ggmax);
+    double pref;
+    switch (pretype) {                                             // advance.f90:385-408
+        case PS3D_PRE_CONSTANT: pref = 1.0; break;
+        case PS3D_PRE_VORCH: pref = vorch; break;
+        case PS3D_PRE_BFMAX: pref = bfmax; break;
+        case PS3D_PRE_ROLL_MEAN_MAX_STRAIN: pref = rmv; break;
+        case PS3D_PRE_MAX_STRAIN: pref = ggmax; break;
+        case PS3D_PRE_US_MAX_STRAIN: pref = usggmax; break;
+        default: fail(PS3D_ERR_BAD_ARGUMENT, "We only support 'constant', 'vorch', 'bfmax', 'roll-mean-max-strain', "
+                                             "'max-strain' and us-max-strain");
+    }
+    if (diag) {
+        const double ncelli = 1.0 / (double)c.ncell;
+        diag[PS3D_D_VORTMAX] = vortmax; diag[PS3D_D_VORTRMS] = vortrms; diag[PS3D_D_VORCH] = vorch;
+        diag[PS3D_D_VORMEAN_X] = r1[RQ_SUMW0] * ncelli; diag[PS3D_D_VORMEAN_Y] = r1[RQ_SUMW1] * ncelli;
+        diag[PS3D_D_VORMEAN_Z] = r1[RQ_SUMW2C] * ncelli;
+        diag[PS3D_D_BFMAX] = bfmax; diag[PS3D_D_GGMAX] = ggmax; diag[PS3D_D_UMAX] = umax; diag[PS3D_D_VMAX] = vmax;
+        diag[PS3D_D_WMAX] = wmax; diag[PS3D_D_USGGMAX] = usggmax; diag[PS3D_D_LSGGMAX] = lsggmax;
+        diag[PS3D_D_RMV] = rmv; diag[PS3D_D_DT] = dt; diag[PS3D_D_PREFACTOR] = pref;
+    }
+    *dt_out = dt;
+    if (c.stepper_ready && c.diffusion_ready) do_set_diffusion(c, dt, pref);     // advance.f90:375
+}
+
+static void do_upload_vorticity(Ctx& c, const double* vor_phys) {
+    // utils.f90:160-165
+    for (int i = 0; i < 3; ++i) {
+        to_device(c, vor_phys + (size_t)i * c.nnat, c.vor[i].p, false);
+        fft2d_fwd(c, c.vor[i].p, c.W[0].p, c.W[3].p);
+        launch_zop(c, ZOP_DECOMPOSE, c.W[0].p, c.svor[i].p);
+    }
+    vor_mean(c, 0);
+    ps_sync(c.stream);
+}
+
+// pressure (fields_derived.f90:67-157), lazily: needs the five strain fields
+static void do_pressure(Ctx& c, double* out_dev) { (void)c; (void)out_dev; fail(PS3D_ERR_UNSUPPORTED, "pressure download not implemented yet"); }
+
+}  // namespace ps3d
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+using namespace ps3d;
+
+#define PS_API_BEGIN try {
+#define PS_API_END                                                        \
+    return PS3D_OK;                                                       \
+    } catch (const StatusError& e) { return e.code; }                     \
+    catch (const DeviceError&) { return PS3D_ERR_DEVICE; }                \
+    catch (const std::exception& e) { set_error("%s", e.what()); return PS3D_ERR_DEVICE; }
+
+extern "C" {
+
+const char* ps3d_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int ps3d_cuda_init(int nx, int ny, int nz, const double lower[3], const double extent[3], int rank, int nranks,
+                   const void* nccl_id) {
+    PS_API_BEGIN
+    (void)nccl_id;
+    const bool fresh = (g_ctx == nullptr);
+    try { do_init(nx, ny, nz, lower, extent, rank, nranks); }
+    catch (...) { if (fresh && g_ctx) { try { do_finalise(); } catch (...) {} } throw; }
+    PS_API_END
+}
+
+int ps3d_cuda_init_inversion(int filtering_id) { PS_API_BEGIN do_init_inversion(filtering_id); PS_API_END }
+
+int ps3d_cuda_init_diffusion(int nnu, double prediss, int length_scale_id, double te, double en, double* nu_out) {
+    PS_API_BEGIN
+    const double v = do_init_diffusion(nnu, prediss, length_scale_id, te, en);
+    if (nu_out) *nu_out = v;
+    PS_API_END
+}
+
+int ps3d_cuda_finalise(void) { PS_API_BEGIN do_finalise(); PS_API_END }
+
+int ps3d_cuda_fftxyp2s(const double* fp, double* fs) {
+    PS_API_BEGIN
+    Ctx& c = ctx();
+    to_device(c, fp, c.W[0].p, false);
+    fft2d_fwd(c, c.W[0].p, c.W[1].p, c.W[2].p);
+    to_host(c, c.W[1].p, fs, true);
+    PS_API_END
+}
+
+int ps3d_cuda_fftxys2p(const double* fs, double* fp) {
+    PS_API_BEGIN
+    Ctx& c = ctx();
+    to_device(c, fs, c.W[0].p, true);
+    fft2d_inv(c, c.W[0].p, c.W[1].p, c.W[2].p, false, false);
+    to_host(c, c.W[1].p, fp, false);
+    PS_API_END
+}
+
+static void zop_host(int op, const double* in, double* out) {
+    Ctx& c = ready();
+    to_device(c, in, c.W[0].p, true);
+    launch_zop(c, op, c.W[0].p, c.W[1].p);
+    to_host(c, c.W[1].p, out, true);
+}
+
+int ps3d_cuda_fftsine(double* fs) { PS_API_BEGIN zop_host(ZOP_SINE, fs, fs); PS_API_END }
+int ps3d_cuda_fftcosine(double* fs) { PS_API_BEGIN zop_host(ZOP_COSINE, fs, fs); PS_API_END }
+int ps3d_cuda_diffx(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFX, fs, ds); PS_API_END }
+int ps3d_cuda_diffy(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFY, fs, ds); PS_API_END }
+int ps3d_cuda_central_diffz(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFZ, fs, ds); PS_API_END }
+int ps3d_cuda_field_combine_semi_spectral(double* sf) { PS_API_BEGIN zop_host(ZOP_COMBINE, sf, sf); PS_API_END }
+int ps3d_cuda_field_decompose_semi_spectral(double* sfc) { PS_API_BEGIN zop_host(ZOP_DECOMPOSE, sfc, sfc); PS_API_END }
+
+int ps3d_cuda_field_combine_physical(const double* sf, double* fc) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    to_device(c, sf, c.W[0].p, true);
+    launch_zop(c, ZOP_COMBINE, c.W[0].p, c.W[1].p);
+    fft2d_inv(c, c.W[1].p, c.W[0].p, c.W[2].p, false, false);
+    to_host(c, c.W[0].p, fc, false);
+    PS_API_END
+}
+
+int ps3d_cuda_field_decompose_physical(const double* fc, double* sf) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    to_device(c, fc, c.W[0].p, false);
+    fft2d_fwd(c, c.W[0].p, c.W[1].p, c.W[2].p);
+    launch_zop(c, ZOP_DECOMPOSE, c.W[1].p, c.W[0].p);
+    to_host(c, c.W[0].p, sf, true);
+    PS_API_END
+}
+
+int ps3d_cuda_upload_vorticity(const double* vor_phys) { PS_API_BEGIN do_upload_vorticity(ready(), vor_phys); PS_API_END }
+int ps3d_cuda_vor2vel(void) { PS_API_BEGIN Ctx& c = ready(); do_vor2vel(c); ps_sync(c.stream); PS_API_END }
+int ps3d_cuda_source(void) { PS_API_BEGIN Ctx& c = ready(); do_source(c); ps_sync(c.stream); PS_API_END }
+
+int ps3d_cuda_adapt(double t, double t_limit, double alpha, int pretype_id, int win, double* dt, double diag_out[16]) {
+    PS_API_BEGIN
+    if (!dt) fail(PS3D_ERR_BAD_ARGUMENT, "dt is null");
+    if (win < 1) fail(PS3D_ERR_BAD_ARGUMENT, "roll_mean_win_size must be >= 1");
+    do_adapt(ready(), t, t_limit, alpha, pretype_id, win, dt, diag_out);
+    PS_API_END
+}
+
+int ps3d_cuda_stepper_setup(int stepper_id) { PS_API_BEGIN do_stepper_setup(ready(), stepper_id); PS_API_END }
+int ps3d_cuda_set_diffusion(double dt, double pref) { PS_API_BEGIN Ctx& c = ready(); do_set_diffusion(c, dt, pref); ps_sync(c.stream); PS_API_END }
+int ps3d_cuda_step(double* t, double dt) { PS_API_BEGIN Ctx& c = ready(); if (!t) fail(PS3D_ERR_BAD_ARGUMENT, "t is null"); do_step(c, t, dt); ps_sync(c.stream); PS_API_END }
+
+int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, int win, double* dt_out, double diag_out[16]) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!t) fail(PS3D_ERR_BAD_ARGUMENT, "t is null");
+    if (win < 1) fail(PS3D_ERR_BAD_ARGUMENT, "roll_mean_win_size must be >= 1");
+    if (!c.stepper_ready || !c.diffusion_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup / init_diffusion missing");
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaEventRecord(c.ev0, c.stream));
+#endif
+    double dt = 0.0;
+    do_vor2vel(c);                                     // advance.f90:85
+    do_adapt(c, *t, t_limit, alpha, pretype_id, win, &dt, diag_out);   // :88
+    do_source(c);                                      // :95
+    do_step(c, t, dt);                                 // :102
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaEventRecord(c.ev1, c.stream));
+    PS_CUDA_TRY(cudaEventSynchronize(c.ev1));
+    float ms = 0.f;
+    PS_CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    c.last_advance_ms = ms;
+#else
+    ps_sync(c.stream);
+#endif
+    if (dt_out) *dt_out = dt;
+    PS_API_END
+}
+
+static DevBuf<double>* field_by_id(Ctx& c, int id, bool& spectral) {
+    switch (id) {
+        case PS3D_F_SVOR: spectral = true; return c.svor;
+        case PS3D_F_VOR: spectral = false; return c.vor;
+        case PS3D_F_VEL: spectral = false; return c.vel;
+        case PS3D_F_SVEL: spectral = true; return c.svel;
+        case PS3D_F_SVORTS: spectral = true; return c.svorts;
+        default: return nullptr;
+    }
+}
+
+int ps3d_cuda_download(int field_id, int comp, double* host) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!host) fail(PS3D_ERR_BAD_ARGUMENT, "host pointer is null");
+    if (field_id == PS3D_F_PRES || field_id == PS3D_F_DELTA) {
+        if (field_id == PS3D_F_DELTA) {
+            // horizontal_divergence (fields_derived.f90:161-182): delta = u_x + v_y
+            fft2d_inv(c, c.svel[0].p, c.W[0].p, c.W[5].p, true, false);
+            fft2d_inv(c, c.svel[1].p, c.W[1].p, c.W[5].p, false, true);
+            fail(PS3D_ERR_UNSUPPORTED, "delta download not implemented yet");
+        }
+        do_pressure(c, c.W[0].p);
+    }
+    bool spectral = false;
+    DevBuf<double>* f = field_by_id(c, field_id, spectral);
+    if (!f || comp < 0 || comp > 2) fail(PS3D_ERR_BAD_ARGUMENT, "bad field id %d / component %d", field_id, comp);
+    to_host(c, f[comp].p, host, spectral);
+    PS_API_END
+}
+
+int ps3d_cuda_upload(int field_id, int comp, const double* host) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    bool spectral = false;
+    DevBuf<double>* f = field_by_id(c, field_id, spectral);
+    if (!f || comp < 0 || comp > 2 || !host) fail(PS3D_ERR_BAD_ARGUMENT, "bad field id %d / component %d", field_id, comp);
+    to_device(c, host, f[comp].p, spectral);
+    ps_sync(c.stream);
+    PS_API_END
+}
+
+int ps3d_cuda_diagnostics(double out[8]) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!out) fail(PS3D_ERR_BAD_ARGUMENT, "out is null");
+    field_reduce(c);
+    ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    const double ncelli = 1.0 / (double)c.ncell;
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    out[0] = 0.5 * c.h_red[RQ_SUMU2] * ncelli;      // field_diagnostics.f90:93-103
+    out[1] = 0.5 * c.h_red[RQ_SUMW2] * ncelli;      // :177-187
+    out[2] = c.h_red[RQ_SUMUW] * ncelli;            // plotting/plot_vor_vel_he_evolution.py:62-65
+    PS_API_END
+}
+
+long long ps3d_cuda_kernel_launches(void) { return g_ctx ? g_ctx->launches : 0; }
+double ps3d_cuda_last_advance_ms(void) { return g_ctx ? g_ctx->last_advance_ms : 0.0; }
+
+int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!ms_per_launch || reps < 1 || which < 0 || which > 5) fail(PS3D_ERR_BAD_ARGUMENT, "bad time_kernel arguments");
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaEventRecord(c.ev0, c.stream));
+#endif
+    for (int r = 0; r < reps; ++r) {
+        switch (which) {
+            case 0: { Sweep s{1, false, PRO_PLAIN, {c.vor[0].p, nullptr, nullptr, nullptr}, 0, 0, c.W[3].p}; run_sweep(c, s); break; }
+            case 1: { Sweep s{0, false, PRO_PLAIN, {c.W[3].p, nullptr, nullptr, nullptr}, 0, 0, c.W[4].p}; run_sweep(c, s); break; }
+            case 2: { Sweep s{0, true, PRO_PLAIN, {c.svel[0].p, nullptr, nullptr, nullptr}, 0, 0, c.W[3].p}; run_sweep(c, s); break; }
+            case 3: { Sweep s{1, true, PRO_PLAIN, {c.W[3].p, nullptr, nullptr, nullptr}, 0, 0, c.W[4].p}; run_sweep(c, s); break; }
+            case 4: {
+                V2VArgs a;
+                // writes go to scratch so that the resident state is not disturbed
+                a.svor0 = c.W[0].p; a.svor1 = c.W[1].p; a.svor2 = c.svor[2].p;
+                a.wsem0 = c.W[2].p; a.wsem1 = c.W[3].p; a.wsem2 = c.W[4].p;
+                a.svel0 = c.W[5].p; a.svel1 = c.W[5].p; a.svel2 = c.W[5].p;
+                if (r == 0) { ps_d2d(c.W[0].p, c.svor[0].p, c.nint * sizeof(double), c.stream); ps_d2d(c.W[1].p, c.svor[1].p, c.nint * sizeof(double), c.stream); }
+                launch_v2v(c, a);
+                break;
+            }
+            case 5: {
+                SrcArgs a;
+                a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
+                a.s0 = c.W[3].p; a.s1 = c.W[4].p; a.s2 = c.W[5].p;
+                launch_src(c, a);
+                break;
+            }
+        }
+    }
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaEventRecord(c.ev1, c.stream));
+    PS_CUDA_TRY(cudaEventSynchronize(c.ev1));
+    float ms = 0.f;
+    PS_CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    *ms_per_launch = (double)ms / reps;
+#else
+    ps_sync(c.stream);
+    *ms_per_launch = 0.0;
+#endif
+    PS_API_END
+}
+
+}  // extern "C"
