@@ -1,0 +1,89 @@
+"""Kernel index arithmetic on the CPU block emulator (tests/_emu, test-only build of the
+same .cu sources with g++) against the oracle.  Small grids only; the parity tests proper
+are the -m gpu ones."""
+import math
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as G
+from oracle import ps3d_oracle as O
+from ps3d_b200.lib import PS3DLib, PS3DError
+
+TOL = 5e-14
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = PS3DLib(G.build_emu())
+    yield lib
+
+
+@pytest.fixture
+def grid(emu):
+    nx, ny, nz = 16, 32, 16
+    lower = np.array([-0.5 * math.pi, -0.5 * math.pi, 0.0])
+    extent = np.array([math.pi, 2 * math.pi, 1.5])
+    emu.init(nx, ny, nz, lower, extent)
+    emu.init_inversion("Hou & Li")
+    yield emu, O.PS3D(nx, ny, nz, lower, extent), np.random.default_rng(1234)
+    emu.finalise()
+
+
+def test_operators(grid):
+    lib, s, rng = grid
+    f = rng.uniform(-1, 1, (s.nx, s.ny, s.nz + 1))
+    fs = lib.fftxyp2s(f)
+    assert rel(fs, s.fftxyp2s(f)) < TOL
+    assert rel(lib.fftxys2p(fs), f) < TOL
+    assert rel(lib.fftsine(f), s.fftsine(f)) < TOL
+    assert rel(lib.fftcosine(f), s.fftcosine(f)) < TOL
+    assert rel(lib.diffx(f), s.diffx(f)) < TOL
+    assert rel(lib.diffy(f), s.diffy(f)) < TOL
+    assert rel(lib.central_diffz(f), s.central_diffz(f)) < TOL
+    assert rel(lib.field_combine_semi_spectral(f), s.field_combine_semi_spectral(f)) < TOL
+    assert rel(lib.field_decompose_semi_spectral(f), s.field_decompose_semi_spectral(f)) < TOL
+    assert rel(lib.field_combine_physical(f), s.field_combine_physical(f)) < TOL
+    assert rel(lib.field_decompose_physical(f), s.field_decompose_physical(f)) < TOL
+
+
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_time_step(grid, stepper):
+    lib, s, rng = grid
+    vor = rng.uniform(-1, 1, (3, s.nx, s.ny, s.nz + 1))
+    s.set_vorticity(vor)
+    lib.upload_vorticity(vor)
+    lib.vor2vel()
+    for name in ("svor", "vor", "svel", "vel"):
+        assert rel(lib.download3(name), getattr(s, name)) < TOL, name
+    d = lib.diagnostics()
+    assert d["ke"] == pytest.approx(s.get_kinetic_energy(), rel=1e-13)
+    assert d["en"] == pytest.approx(s.get_enstrophy(), rel=1e-13)
+    assert d["helicity"] == pytest.approx(s.get_helicity(), rel=1e-11, abs=1e-16)
+    lib.source()
+    s.source()
+    assert rel(lib.download3("svorts"), s.svorts) < TOL
+    lib.init_diffusion(d["ke"], d["en"])
+    lib.stepper_setup(stepper)
+    t, dt, diag = lib.advance(0.0, 100.0)
+    to, dto = s.advance(0.0, 100.0, stepper, literal=True)
+    assert dt == pytest.approx(dto, rel=1e-13) and t == pytest.approx(to, rel=1e-13)
+    for k in ("vortmax", "vortrms", "vorch", "ggmax", "umax", "vmax", "wmax", "usggmax", "lsggmax"):
+        assert diag[k] == pytest.approx(s.diag[k], rel=1e-12), k
+    assert rel(lib.download3("svor"), s.svor) < TOL
+
+
+def test_error_paths(emu):
+    with pytest.raises(PS3DError) as e:
+        emu.vor2vel()
+    assert e.value.status == 1
+    with pytest.raises(PS3DError) as e:
+        emu.init(24, 32, 32, np.zeros(3), np.ones(3))       # stafft.f90:87-95 analogue
+    assert e.value.status == 3
+    with pytest.raises(PS3DError) as e:
+        emu.init(32, 32, 32, np.zeros(3), np.array([1.0, 0.0, 1.0]))   # sta2dfft.f90:67-74
+    assert e.value.status == 2

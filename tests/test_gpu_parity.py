@@ -1,0 +1,192 @@
+"""Parity tests proper: the CUDA path through the C ABI against the oracle on the same inputs
+(bar from BASELINE.json north_star: per-step fields <= 1e-12 relative to the field max-norm,
+energy / enstrophy / helicity <= 1e-10 relative after 100 steps), the reference's own analytic
+known-answer tests through the C ABI, and size-independent properties at full size."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ps3d_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PI = math.pi
+FIELD_TOL = 1e-12      # north_star: per-step fields, relative (max-norm)
+DIAG_TOL = 1e-10       # north_star: KE / enstrophy / helicity after 100 steps
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    import ps3d_b200
+    return ps3d_b200.load()
+
+
+def open_grid(lib, nx, ny, nz, lower, extent, filtering="Hou & Li"):
+    lib.init(nx, ny, nz, np.asarray(lower, float), np.asarray(extent, float))
+    lib.init_inversion(filtering)
+    return O.PS3D(nx, ny, nz, lower, extent, filtering)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (16, 32, 8), (128, 64, 32), (8, 8, 8)])
+def test_operators_white_noise(lib, shape):
+    """isolated transforms on a white-noise field (all modes populated)."""
+    nx, ny, nz = shape
+    s = open_grid(lib, nx, ny, nz, [-PI, -0.5 * PI, 0.0], [2 * PI, PI, 1.7])
+    try:
+        f = np.random.default_rng(1234).uniform(-1, 1, (nx, ny, nz + 1))
+        fs = lib.fftxyp2s(f)
+        assert rel(fs, s.fftxyp2s(f)) < FIELD_TOL
+        assert rel(lib.fftxys2p(fs), f) < FIELD_TOL
+        assert rel(lib.fftsine(f), s.fftsine(f)) < FIELD_TOL
+        assert rel(lib.fftcosine(f), s.fftcosine(f)) < FIELD_TOL
+        assert rel(lib.diffx(f), s.diffx(f)) < FIELD_TOL
+        assert rel(lib.diffy(f), s.diffy(f)) < FIELD_TOL
+        assert rel(lib.central_diffz(f), s.central_diffz(f)) < FIELD_TOL
+        assert rel(lib.field_combine_semi_spectral(f), s.field_combine_semi_spectral(f)) < FIELD_TOL
+        assert rel(lib.field_decompose_semi_spectral(f), s.field_decompose_semi_spectral(f)) < FIELD_TOL
+        assert rel(lib.field_combine_physical(f), s.field_combine_physical(f)) < FIELD_TOL
+        assert rel(lib.field_decompose_physical(f), s.field_decompose_physical(f)) < FIELD_TOL
+        # 2/3 rule shares everything but the filter tables
+    finally:
+        lib.finalise()
+
+
+def test_vor2vel_1_known_answer(lib):
+    """unit-tests/test_vor2vel_1.f90:99: Beltrami 32^3, velocity vs analytic, atol 1e-14."""
+    s = open_grid(lib, 32, 32, 32, -0.5 * PI * np.ones(3), PI * np.ones(3))
+    try:
+        x = (s.lower[0] + s.dx[0] * np.arange(32))[:, None, None]
+        y = (s.lower[1] + s.dx[1] * np.arange(32))[None, :, None]
+        z = (s.lower[2] + s.dx[2] * np.arange(33))[None, None, :]
+        k, l, m = 2.0, 2.0, 1.0
+        alpha = math.sqrt(k * k + l * l + m * m)
+        f = 1.0 / (k * k + l * l)
+        ref = np.empty((3, 32, 32, 33))
+        ref[0] = f * (k * m * np.sin(m * z) - l * alpha * np.cos(m * z)) * np.sin(k * x + l * y)
+        ref[1] = f * (l * m * np.sin(m * z) + k * alpha * np.cos(m * z)) * np.sin(k * x + l * y)
+        ref[2] = np.cos(m * z) * np.cos(k * x + l * y)
+        lib.upload_vorticity(alpha * ref)
+        lib.vor2vel()
+        assert np.max(np.abs(lib.download3("vel") - ref)) < 1e-14
+    finally:
+        lib.finalise()
+
+
+def test_vor2vel_mean_flow_known_answers(lib):
+    """unit-tests/test_vor2vel_3.f90:82 (eta = 1 -> u = z - zc, 1e-15) and _4 (eta = 2z)."""
+    s = open_grid(lib, 32, 32, 32, [-0.5, -0.5, 0.0], [1.0, 1.0, 1.0])
+    try:
+        z = (s.lower[2] + s.dx[2] * np.arange(33))[None, None, :] + np.zeros((32, 32, 1))
+        vor = np.zeros((3, 32, 32, 33))
+        vor[1] = 1.0
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        vel = lib.download3("vel")
+        assert np.max(np.abs(vel[0] - (z - 0.5))) < 2e-15 and np.max(np.abs(vel[1:])) < 2e-15
+        vor[1] = 2 * z
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        vel = lib.download3("vel")
+        assert np.max(np.abs(vel[0] - (z ** 2 - 1.0 / 3.0))) < 2e-15
+    finally:
+        lib.finalise()
+
+
+def test_diffx_diffy_known_answer(lib):
+    """unit-tests/test_diffx.f90:59-75 / test_diffy.f90: cos 4x -> -4 sin 4x, 1e-12."""
+    s = open_grid(lib, 64, 128, 64, -PI * np.ones(3), 2 * PI * np.ones(3))
+    try:
+        x = (s.lower[0] + s.dx[0] * np.arange(64))[:, None, None] + np.zeros((1, 128, 65))
+        out = lib.fftxys2p(lib.diffx(lib.fftxyp2s(np.cos(4 * x))))
+        assert np.max(np.abs(out + 4 * np.sin(4 * x))) < 1e-12
+        y = (s.lower[1] + s.dx[1] * np.arange(128))[None, :, None] + np.zeros((64, 1, 65))
+        out = lib.fftxys2p(lib.diffy(lib.fftxyp2s(np.cos(4 * y))))
+        assert np.max(np.abs(out + 4 * np.sin(4 * y))) < 1e-12
+    finally:
+        lib.finalise()
+
+
+@pytest.mark.parametrize("filtering", ["Hou & Li", "2/3-rule"])
+def test_vor2vel_source_white_noise_64(lib, filtering):
+    s = open_grid(lib, 64, 64, 64, -0.5 * PI * np.ones(3), PI * np.ones(3), filtering)
+    try:
+        vor = np.random.default_rng(7).uniform(-1, 1, (3, 64, 64, 65))
+        s.set_vorticity(vor)
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        for name in ("svor", "vor", "svel", "vel"):
+            assert rel(lib.download3(name), getattr(s, name)) < FIELD_TOL, name
+        lib.source()
+        s.source()
+        assert rel(lib.download3("svorts"), s.svorts) < FIELD_TOL
+        d = lib.diagnostics()
+        assert d["ke"] == pytest.approx(s.get_kinetic_energy(), rel=1e-13)
+        assert d["en"] == pytest.approx(s.get_enstrophy(), rel=1e-13)
+    finally:
+        lib.finalise()
+
+
+@pytest.mark.parametrize("stepper,n,nsteps", [("cn2", 32, 100), ("impl-diff-rk4", 32, 100), ("cn2", 64, 10)])
+def test_beltrami_trajectory(lib, stepper, n, nsteps):
+    """fields every step to 1e-12, dt sequence, and
+    KE / enstrophy / helicity after the last step to 1e-10 (the oracle runs the *literal*
+    combine -> multiply -> decompose steppers of the reference)."""
+    from ps3d_b200 import host
+    ref = O.beltrami_setup(n)
+    s = host.beltrami_solver(lib, n, stepper=stepper)
+    try:
+        t = 0.0
+        for i in range(nsteps):
+            dt, diag = s.advance()
+            t, dto = ref.advance(t, 100.0, stepper, literal=True)
+            assert dt == pytest.approx(dto, rel=1e-11), i
+            for k in ("vortmax", "vortrms", "vorch", "ggmax", "umax", "vmax", "wmax", "usggmax", "lsggmax"):
+                assert diag[k] == pytest.approx(ref.diag[k], rel=1e-10), (i, k)
+            if i % 10 == 9 or i < 3:
+                assert rel(lib.download3("svor"), ref.svor) < FIELD_TOL, i
+        assert s.t == pytest.approx(t, rel=1e-11)
+        lib.vor2vel()
+        ref.vor2vel()
+        for name in ("vor", "vel"):
+            assert rel(lib.download3(name), getattr(ref, name)) < FIELD_TOL, name
+        d = lib.diagnostics()
+        assert d["ke"] == pytest.approx(ref.get_kinetic_energy(), rel=DIAG_TOL)
+        assert d["en"] == pytest.approx(ref.get_enstrophy(), rel=DIAG_TOL)
+        assert d["helicity"] == pytest.approx(ref.get_helicity(), rel=DIAG_TOL)
+    finally:
+        s.close()
+
+
+def test_full_size_properties_256(lib):
+    """Properties that need no oracle at 256^3: inverse(forward) = identity, DST/DCT are
+    self-inverse, linearity, combine/decompose are mutual inverses, Parseval for the packed FFT."""
+    n = 256
+    lib.init(n, n, n, -0.5 * PI * np.ones(3), PI * np.ones(3))
+    lib.init_inversion("Hou & Li")
+    try:
+        rng = np.random.default_rng(3)
+        f = rng.uniform(-1, 1, (n, n, n + 1))
+        g = rng.uniform(-1, 1, (n, n, n + 1))
+        fs = lib.fftxyp2s(f)
+        assert rel(lib.fftxys2p(fs), f) < FIELD_TOL
+        gs = lib.fftxyp2s(g)
+        assert rel(lib.fftxyp2s(2.0 * f - 3.0 * g), 2.0 * fs - 3.0 * gs) < FIELD_TOL
+        # Parseval: sum f^2 = sum_k w_k |packed|^2 with weight 2 except DC/Nyquist rows, per axis
+        w = np.full(n, 2.0); w[0] = 1.0; w[n // 2] = 1.0
+        lhs = np.sum(f[..., 5] ** 2)
+        rhs = np.sum(w[:, None] * w[None, :] * fs[..., 5] ** 2)
+        assert lhs == pytest.approx(rhs, rel=1e-12)
+        d = lib.fftsine(f)
+        dd = lib.fftsine(d)
+        assert rel(dd[..., 1:n], f[..., 1:n]) < FIELD_TOL and np.all(dd[..., n] == 0.0)
+        assert rel(lib.fftcosine(lib.fftcosine(f)), f) < FIELD_TOL
+        assert rel(lib.field_decompose_semi_spectral(lib.field_combine_semi_spectral(f)), f) < FIELD_TOL
+    finally:
+        lib.finalise()
