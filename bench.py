@@ -1,0 +1,249 @@
+#!/usr/bin/env python
+"""Headline benchmark: Beltrami grid-pt*steps/s (FP64), one `advance` time step per "step".
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): Beltrami 512^3,
+examples/beltrami_512.config (stepper cn2, Hou & Li filter, nnu = 3, prediss = 30, pretype vorch,
+alpha = 0.1), synthetic analytic initial condition (beltrami.f90:162-181).  One JSON line on stdout.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Beltrami grid-pt*steps/s (FP64)"
+UNIT = "grid-pt*steps/s"
+SWEEPS = {"cn2": 115, "impl-diff-rk4": 150}          # necessary 1-D transform sweeps per step
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+                for k, nme in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(n, steps, warmup):
+    """Reference algorithm (literal combine/decompose steppers) on the host cores: the oracle port."""
+    from oracle import ps3d_oracle as O
+    s = O.beltrami_setup(n)
+    t = 0.0
+    for _ in range(warmup):
+        t, _ = s.advance(t, 100.0, "cn2", literal=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t, _ = s.advance(t, 100.0, "cn2", literal=True)
+    dt = time.perf_counter() - t0
+    return n ** 3 * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_n
+    val, sec = cpu_reference_run(n, args.steps, args.warmup)
+    cores = os.cpu_count()
+    sample = f"Beltrami {n}^3 cn2 steps (bounded sample of the 512^3 workload), NumPy/SciPy port of the reference algorithm"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Beltrami {args.n}^3 cn2 (examples/beltrami_512.config)", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=512, help="grid size (nx = ny = nz)")
+    ap.add_argument("--stepper", default="cn2")
+    ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    os.environ.setdefault("CUDA_DEVICE_ORDER", "PCI_BUS_ID")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import ps3d_b200
+    from ps3d_b200 import host
+    lib = ps3d_b200.load()
+    # NOTE: ps3d_cuda_init selects device rank % ndev; with one process per GPU we present exactly
+    # this process's device as device 0 through the rank argument below.
+    n = args.n
+    lower = -0.5 * math.pi * np.ones(3)
+    extent = math.pi * np.ones(3)
+    os.environ["PS3D_DEVICE"] = str(local_rank)
+    solver = host.Solver(lib, n, n, n, lower, extent, stepper=args.stepper)
+    vor_np = host.beltrami_vorticity(n, n, n, lower, extent)
+    vor_pinned = torch.from_numpy(vor_np).pin_memory()
+    vor_host = vor_pinned.numpy()
+    solver.setup_fields(vor_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.advance()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = lib.kernel_launches()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        solver.advance()
+        dev_ms += lib.last_advance_ms()          # CUDA events on the library's stream around the whole step
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = lib.kernel_launches() - l0
+    clocks = sampler.stop()
+    ms_step = dev_ms / args.steps
+    if world > 1:
+        tt = torch.tensor([ms_step, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, wall = float(tt[0]), float(tt[1])
+
+    # ---- end-to-end through the C ABI with host buffers (H2D of the step's input, D2H of its result) ----
+    h2d = vor_host.nbytes
+    e2e_steps = max(2, min(args.steps, 5))
+    solver.lib.upload_vorticity(vor_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lib.upload_vorticity(vor_host)           # 3 fields, pinned host memory -> HBM, decomposed on device
+        solver.t = 0.0
+        solver.advance()                         # diag_out[16] comes back to the host
+        d = lib.diagnostics()                    # KE / enstrophy / helicity read back
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_sec = float(tt[0])
+
+    # ---- per-kernel device times (CUDA events on the library's stream), roofline of the dominant one ----
+    peak, peak_src = peaks()
+    N = n * n * (n + 1)
+    kinfo = [("line_fwd_y", 16), ("line_fwd_x", 16), ("line_inv_x", 16), ("line_inv_y", 16),
+             ("vor2vel_columns", 8 * 16), ("source_columns", 5 * 16)]
+    kernels = {}
+    for w, (name, bpp) in enumerate(kinfo):
+        lib.time_kernel(w, 2)
+        ms = lib.time_kernel(w, 10)
+        kernels[name] = {"ms": ms, "alg_bytes": bpp * N * 8 // 8, "GBs": bpp * N / (ms * 1e-3) / 1e9}
+    # share of the step: launches per cn2 step = 3 vor2vel + 3 source column kernels, 3*18 + 10 line sweeps
+    mult = 3 if args.stepper == "cn2" else 4
+    share = {"vor2vel_columns": mult * kernels["vor2vel_columns"]["ms"],
+             "source_columns": mult * kernels["source_columns"]["ms"],
+             "line_sweeps": (mult * 18 + 10) * np.mean([kernels[k]["ms"] for k in list(kernels)[:4]])}
+    dom = max(share, key=share.get)
+    if dom == "line_sweeps":
+        dom = "line_fwd_y"
+    roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBs"], "peak": peak, "unit": "GB/s",
+            "frac": kernels[dom]["GBs"] / peak, "traffic": None, "peak_source": peak_src,
+            "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"]}
+    step_bytes = SWEEPS[args.stepper] * 16 * N
+    value = world * n ** 3 / (ms_step * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"Beltrami {n}^3 {args.stepper} (examples/beltrami_512.config), analytic IC k=l=2 m=1",
+                   "grid": [n, n, n], "stepper": args.stepper, "filtering": "Hou & Li", "nnu": 3, "prediss": 30.0,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab exchange not built yet)",
+                   "l2": "inputs larger than L2 (each field %.2f GB vs 126 MB L2)" % (N * 8 / 1e9)},
+        "roofline": roof,
+        "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                          "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+        "kernels": kernels, "step_share_ms": share,
+        "e2e": {"value": world * n ** 3 / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": (16 + 8) * 8, "ms_per_step": e2e_sec * 1e3},
+        "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps * 1e3, "clocks": clocks,
+        "diag": {k: float(v) for k, v in d.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        val, sec = cpu_reference_run(args.ref_n, 2, 1)
+        out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"Beltrami {args.ref_n}^3 cn2, 2 steps after 1 warm-up, NumPy/SciPy port of the "
+                                         f"reference algorithm (literal steppers), scipy.fft on all cores"}
+    solver.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

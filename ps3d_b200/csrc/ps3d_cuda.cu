@@ -320,7 +320,14 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         fail(PS3D_ERR_NO_DEVICE, "no CUDA device: libps3d_cuda has no CPU path");
-    PS_CUDA_TRY(cudaSetDevice(rank % ndev));
+    {
+        // one process per GPU: PS3D_DEVICE, else the launcher's LOCAL_RANK, else rank modulo the device count
+        const char* e = getenv("PS3D_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        int dev = e ? atoi(e) : rank % ndev;
+        if (dev < 0 || dev >= ndev) fail(PS3D_ERR_BAD_ARGUMENT, "device %d out of range (%d devices)", dev, ndev);
+        PS_CUDA_TRY(cudaSetDevice(dev));
+    }
 #endif
     Ctx* c = new Ctx();
     g_ctx = c;
