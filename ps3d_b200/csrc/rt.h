@@ -64,7 +64,15 @@ typedef cudaStream_t ps_stream_t;
     } while (0)
 #define PS_SMEM(type, name) extern __shared__ __align__(16) unsigned char _ps_smem_raw[]; \
     type* name = reinterpret_cast<type*>(_ps_smem_raw)
-inline void* ps_malloc(size_t bytes) { void* p = nullptr; PS_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 1)); PS_CUDA_TRY(cudaMemset(p, 0, bytes ? bytes : 1)); return p; }
+inline void* ps_malloc(size_t bytes) {
+    void* p = nullptr;
+    PS_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 1));
+    PS_CUDA_TRY(cudaMemset(p, 0, bytes ? bytes : 1));
+    // the memset runs on the legacy default stream, which the library's non-blocking stream does not
+    // synchronise with: finish it before the buffer can be used
+    PS_CUDA_TRY(cudaDeviceSynchronize());
+    return p;
+}
 inline void ps_free(void* p) { if (p) cudaFree(p); }
 inline void ps_h2d(void* d, const void* h, size_t n, ps_stream_t s) { PS_CUDA_TRY(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
 inline void ps_d2h(void* h, const void* d, size_t n, ps_stream_t s) { PS_CUDA_TRY(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
