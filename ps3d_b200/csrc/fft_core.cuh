@@ -19,9 +19,24 @@
 
 namespace ps3d {
 
-// scratch index padding: one extra slot per 8 (stride-8 scatter -> stride 9)
-__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
-__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3) + 1; }
+// Scratch index policies (bank-conflict-free for the stride-R Stockham scatter AND the unit-stride gather;
+// shared memory has 32 4-byte banks, a half-warp of 8-byte accesses must hit 16 distinct 8-byte columns):
+//  IxSwz  : one FFT per scratch line, lanes of a warp are consecutive butterflies u.  XOR swizzle
+//           b0^=i4, b1^=i5, b2^=i6, b3^=i6: the bits that vary across a half-warp in pass 1 (i3..i6),
+//           pass 2 (i0..i2,i6) and pass 3 (i0..i3) always map onto 16 distinct columns.  No padding.
+//  IxIlv  : NF FFTs interleaved (element i of FFT f at NF*sigma(i) + f), lanes = f fastest then u.  sigma
+//           XORs bit 3 (NF = 8) or bits 3,4 (NF = 4) into the low bits so that the 16/NF butterflies of a
+//           half-warp land on distinct columns in both the stride-8 scatter and the unit-stride gather.
+struct IxSwz {
+    __device__ __forceinline__ int operator()(int i) const { return i ^ (((i >> 4) & 7) | (((i >> 6) & 1) << 3)); }
+};
+template <int NF>
+struct IxIlv {
+    int f;
+    __device__ __forceinline__ int operator()(int i) const {
+        return NF * (i ^ ((i >> 3) & (16 / NF - 1))) + f;
+    }
+};
 
 template <bool INV>
 __device__ __forceinline__ void radix4(double& r0, double& i0, double& r1, double& i1,
@@ -113,9 +128,9 @@ __device__ __forceinline__ void fft_pass(double (&vr)[8], double (&vi)[8], int u
     }
 }
 
-template <int N, int R>
+template <int N, int R, class IX>
 __device__ __forceinline__ void fft_scatter(const double (&vr)[8], const double (&vi)[8], int u, int s,
-                                            double* __restrict__ sre, double* __restrict__ sim) {
+                                            double* __restrict__ sre, double* __restrict__ sim, const IX& ix) {
     constexpr int G = 8 / R;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -124,19 +139,19 @@ __device__ __forceinline__ void fft_scatter(const double (&vr)[8], const double 
         const int q = b - p * s;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int idx = padi(q + s * (R * p + j));
+            const int idx = ix(q + s * (R * p + j));
             sre[idx] = vr[g + j * G];
             sim[idx] = vi[g + j * G];
         }
     }
 }
 
-template <int N>
+template <int N, class IX>
 __device__ __forceinline__ void fft_gather(double (&vr)[8], double (&vi)[8], int u,
-                                           const double* __restrict__ sre, const double* __restrict__ sim) {
+                                           const double* __restrict__ sre, const double* __restrict__ sim, const IX& ix) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int idx = padi(u + e * (N / 8));
+        const int idx = ix(u + e * (N / 8));
         vr[e] = sre[idx];
         vi[e] = sim[idx];
     }
@@ -150,11 +165,11 @@ __host__ __device__ constexpr bool is_pow2(int n) { return n > 0 && (n & (n - 1)
 // Full transform.  All N/8 threads of the FFT must call this together (it
 // contains __syncthreads(), so every thread of the BLOCK must take part, with
 // `active` false for threads that own no FFT).  sre/sim: this FFT's scratch
-// line (padded_len(N) doubles each).  The scratch must not be in use by other
+// line (N doubles each for IxSwz).  The scratch must not be in use by other
 // threads when the call is entered.
-template <int N, bool INV>
+template <int N, bool INV, class IX>
 __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int u, bool active,
-                                           double* __restrict__ sre, double* __restrict__ sim,
+                                           double* __restrict__ sre, double* __restrict__ sim, const IX& ix,
                                            const double2* __restrict__ tw, int twscale) {
     static_assert(is_pow2(N) && N >= 8, "power-of-two lengths >= 8 only");
     int s = 1;
@@ -170,9 +185,9 @@ __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int
         const bool last = (pass == N8 - 1) && (TAIL == 1);
         if (!last) {
             if (pass > 0) __syncthreads();               // WAR: everyone has gathered
-            if (active) fft_scatter<N, 8>(vr, vi, u, s, sre, sim);
+            if (active) fft_scatter<N, 8>(vr, vi, u, s, sre, sim, ix);
             __syncthreads();
-            if (active) fft_gather<N>(vr, vi, u, sre, sim);
+            if (active) fft_gather<N>(vr, vi, u, sre, sim, ix);
         }
         s *= 8;
     }

@@ -4,11 +4,12 @@
 // strided, z-coalesced tile access, and diffx/diffy (sta3dfft.f90:304-377) or
 // the u x omega products (inversion.f90:327-350) folded into the load.
 //
-// Tile = 8 consecutive z (one 64-byte segment per row) x N rows.  The 8 real
-// lines are transformed as 4 complex FFTs (two real lines per complex FFT:
-// c = a + i b, separated afterwards by Hermitian symmetry), each by N/8
-// threads: block = N/2 threads, lane = (f = t&3, u = t>>2) so that one warp
-// load instruction covers 8 rows x 64 B.
+// Tile = 16 consecutive z (one full 128-byte line per row) x N rows.  The 16
+// real lines are transformed as 8 complex FFTs (two real lines per complex
+// FFT: c = a + i b, separated afterwards by Hermitian symmetry), each by N/8
+// threads: block = N threads, lane = (f = t&7, u = t>>3) so that one warp
+// load instruction covers 4 rows x 128 B (the minimum number of L1 wavefronts).
+// The 8 FFTs are interleaved in the shared-memory scratch (IxIlv<8>).
 //
 // Output packing is the reference's (stafft.f90:55-58): row k holds Re X_k,
 // row N-k holds Im X_k (k = 1..N/2-1), rows 0 and N/2 the real DC/Nyquist
@@ -20,6 +21,8 @@
 namespace ps3d {
 
 enum { PRO_PLAIN = 0, PRO_DIFF = 1, PRO_CROSS = 2 };
+constexpr int LINE_ZC = 16;            // z values per tile row (pz is a multiple of this)
+constexpr int LINE_NF = LINE_ZC / 2;   // complex FFTs per tile
 
 struct LineArgs {
     const double* in0;        // PLAIN/DIFF: the field.  CROSS: a
@@ -31,7 +34,7 @@ struct LineArgs {
     long long in_os, out_os;  // stride between consecutive outer lines (doubles)
     const long long* in_rowoff;   // [N] offset of row k from the tile base (doubles)
     const long long* out_rowoff;  // [N]
-    int nzc;                  // z-chunks per line (pz / 8)
+    int nzc;                  // z-chunks per line (pz / 16)
     const double* kdiff;      // DIFF: wavenumber per k = 0..N/2 (0 at k = 0 and N/2)
     double scale;             // 1/sqrt(N)
     const double2* tw;
@@ -42,12 +45,11 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 __device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
 
 template <int N, int PRO>
-__global__ void __launch_bounds__(N / 2) k_line_fwd(LineArgs a) {
+__global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_fwd(LineArgs a) {
     PS_SMEM(double, sm);
-    constexpr int PL = padded_len(N);
-    const int t = threadIdx.x, f = t & 3, u = t >> 2;
+    const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
     const int o = blockIdx.x / a.nzc, zc = blockIdx.x - o * a.nzc;
-    const long long ibase = (long long)o * a.in_os + zc * 8 + 2 * f;
+    const long long ibase = (long long)o * a.in_os + zc * LINE_ZC + 2 * f;
     double vr[8], vi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -62,27 +64,29 @@ __global__ void __launch_bounds__(N / 2) k_line_fwd(LineArgs a) {
             vr[e] = x.x; vi[e] = x.y;
         }
     }
-    double* sre = sm + f * 2 * PL;
-    double* sim = sre + PL;
-    block_cfft<N, false>(vr, vi, u, true, sre, sim, a.tw, a.twscale);
+    double* sre = sm;
+    double* sim = sm + LINE_NF * N;
+    const IxIlv<LINE_NF> ix{f};
+    block_cfft<N, false>(vr, vi, u, true, sre, sim, ix, a.tw, a.twscale);
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int idx = padi(u + e * (N / 8));
+        const int idx = ix(u + e * (N / 8));
         sre[idx] = vr[e]; sim[idx] = vi[e];
     }
     __syncthreads();
-    const long long obase = (long long)o * a.out_os + zc * 8 + 2 * f;
+    const long long obase = (long long)o * a.out_os + zc * LINE_ZC + 2 * f;
     const double sc = a.scale, hs = 0.5 * a.scale;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int k = u + e * (N / 8);
         if (k == 0) {
-            st2(a.out + obase + __ldg(&a.out_rowoff[0]), sre[0] * sc, sim[0] * sc);
-            const int ih = padi(N / 2);
+            const int i0 = ix(0);
+            st2(a.out + obase + __ldg(&a.out_rowoff[0]), sre[i0] * sc, sim[i0] * sc);
+            const int ih = ix(N / 2);
             st2(a.out + obase + __ldg(&a.out_rowoff[N / 2]), sre[ih] * sc, sim[ih] * sc);
         } else {
-            const int ik = padi(k), im = padi(N - k);
+            const int ik = ix(k), im = ix(N - k);
             const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
             // A_k = (C_k + conj C_{N-k})/2, B_k = (C_k - conj C_{N-k})/(2i)
             st2(a.out + obase + __ldg(&a.out_rowoff[k]), (p + r) * hs, (q + s) * hs);       // Re A, Re B
@@ -92,14 +96,14 @@ __global__ void __launch_bounds__(N / 2) k_line_fwd(LineArgs a) {
 }
 
 template <int N, int PRO>
-__global__ void __launch_bounds__(N / 2) k_line_inv(LineArgs a) {
+__global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_inv(LineArgs a) {
     PS_SMEM(double, sm);
-    constexpr int PL = padded_len(N);
-    const int t = threadIdx.x, f = t & 3, u = t >> 2;
+    const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
     const int o = blockIdx.x / a.nzc, zc = blockIdx.x - o * a.nzc;
-    const long long ibase = (long long)o * a.in_os + zc * 8 + 2 * f;
-    double* sre = sm + f * 2 * PL;
-    double* sim = sre + PL;
+    const long long ibase = (long long)o * a.in_os + zc * LINE_ZC + 2 * f;
+    double* sre = sm;
+    double* sim = sm + LINE_NF * N;
+    const IxIlv<LINE_NF> ix{f};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int k = u + e * (N / 8);
@@ -107,8 +111,9 @@ __global__ void __launch_bounds__(N / 2) k_line_inv(LineArgs a) {
             double2 x0 = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[0]));
             double2 xh = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[N / 2]));
             if (PRO == PRO_DIFF) { x0.x = x0.y = 0.0; xh.x = xh.y = 0.0; }
-            sre[0] = x0.x; sim[0] = x0.y;
-            const int ih = padi(N / 2);
+            const int i0 = ix(0);
+            sre[i0] = x0.x; sim[i0] = x0.y;
+            const int ih = ix(N / 2);
             sre[ih] = xh.x; sim[ih] = xh.y;
         } else {
             const double2 xk = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[k]));
@@ -120,17 +125,17 @@ __global__ void __launch_bounds__(N / 2) k_line_inv(LineArgs a) {
                 const double ar = -kap * Ai, ai = kap * Ar, br = -kap * Bi, bi = kap * Br;
                 Ar = ar; Ai = ai; Br = br; Bi = bi;
             }
-            const int ik = padi(k), im = padi(N - k);
+            const int ik = ix(k), im = ix(N - k);
             sre[ik] = Ar - Bi; sim[ik] = Ai + Br;     // C_k     = A + i B
             sre[im] = Ar + Bi; sim[im] = Br - Ai;     // C_{N-k} = conj(A) + i conj(B)
         }
     }
     __syncthreads();
     double vr[8], vi[8];
-    fft_gather<N>(vr, vi, u, sre, sim);
+    fft_gather<N>(vr, vi, u, sre, sim, ix);
     __syncthreads();
-    block_cfft<N, true>(vr, vi, u, true, sre, sim, a.tw, a.twscale);
-    const long long obase = (long long)o * a.out_os + zc * 8 + 2 * f;
+    block_cfft<N, true>(vr, vi, u, true, sre, sim, ix, a.tw, a.twscale);
+    const long long obase = (long long)o * a.out_os + zc * LINE_ZC + 2 * f;
     const double sc = a.scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
@@ -138,6 +143,6 @@ __global__ void __launch_bounds__(N / 2) k_line_inv(LineArgs a) {
 }
 
 template <int N>
-constexpr size_t line_smem_bytes() { return (size_t)4 * 2 * padded_len(N) * sizeof(double); }
+constexpr size_t line_smem_bytes() { return (size_t)LINE_NF * 2 * N * sizeof(double); }
 
 }  // namespace ps3d

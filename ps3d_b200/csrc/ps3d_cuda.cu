@@ -155,7 +155,7 @@ static void allow_smem(K, size_t) {}
 template <int N>
 static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles) {
     const size_t sm = line_smem_bytes<N>();
-    const dim3 grid(ntiles), block(N / 2);
+    const dim3 grid(ntiles), block(N);
     if (!inv) {
         if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS>), grid, block, sm, c.stream, a); }
         else { allow_smem(k_line_fwd<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN>), grid, block, sm, c.stream, a); }
@@ -183,7 +183,7 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.in0 = s.in[0]; a.in1 = s.in[1]; a.in2 = s.in[2]; a.in3 = s.in[3];
     a.add1 = s.add1; a.add3 = s.add3;
     a.out = s.out;
-    a.nzc = c.pz / 8;
+    a.nzc = c.pz / LINE_ZC;
     a.tw = c.tw.p;
     int n, nouter;
     if (s.axis == 1) {
@@ -332,7 +332,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     Ctx* c = new Ctx();
     g_ctx = c;
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
-    c->pz = (c->nzp + 7) / 8 * 8;
+    c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
     c->nxl = nx / nranks; c->nyl = ny / nranks;
     for (int i = 0; i < 3; ++i) {

@@ -3,20 +3,26 @@
 //   { (b, a), (b, ny-a), (nx-b, a), (nx-b, ny-a) }
 // so that diffx/diffy (which couple Hermitian slot k with slot n-k,
 // reference sta3dfft.f90:304-377, via mpi_reverse.f90:332-398) are local
-// register/shared-memory operations and no mirrored data is ever re-read from
-// HBM.  One block owns one group: the 4 columns (nz+1 doubles each, contiguous
-// in memory) are staged in shared memory, all z transforms and pointwise
-// operators run there, results are written back once.
+// register operations and no mirrored data is ever re-read from HBM.  One
+// block owns one group: the 4 columns (nz+1 doubles each, contiguous in
+// memory) are staged in shared memory, all z transforms and pointwise operators
+// run there, results are written back once.
 //
 // Spectral arrays are [kx][kyl][pz] with kyl the rank-local index of the
 // *paired* ky order  ky' = 0, ny/2, 1, ny-1, 2, ny-2, ...  (kyl = 2a'+sy), so
 // the y-mirror of a column is its neighbour kyl^1 and a slab of ky' is closed
 // under mirroring (replaces mpi_reverse entirely).
 //
-// DST-I / DCT-I of length nz (reference stafft.f90:410-550 conventions) are
-// done two columns at a time as one complex FFT of length 2 nz over the odd /
-// even extensions: accurate (no post-processing recurrence) and built on the
-// same block_cfft as the x/y passes.
+// Work split inside a block (NT = nz/2 threads):
+//  * pointwise stages are "z-owner": thread t owns rows z = t, t + NT (and
+//    thread 0 also row nz) of ALL four slots, so every x/y mirror coupling is a
+//    register operation and the hyperbolic functions of a row are evaluated once
+//    and kept in registers for the whole kernel;
+//  * DST-I / DCT-I of length nz (reference stafft.f90:410-550 conventions) are
+//    done two columns at a time as one complex FFT of length 2 nz over the odd /
+//    even extensions: accurate (no post-processing recurrence) and built on the
+//    same block_cfft as the x/y passes; the two pair-FFTs of a field run
+//    concurrently on the two halves of the block.
 //
 // The N-sized tables of the reference (phim, phip, thetam, thetap, dthetam,
 // dthetap, green, filt: inversion_utils.f90:281-369,484-542) are never
@@ -48,11 +54,11 @@ template <int NZ>
 struct ZCfg {
     static constexpr int M = 2 * NZ;              // pair-FFT length
     static constexpr int TPF = M / 8;             // threads per pair FFT
-    static constexpr int NT = 2 * TPF;            // 2 pair FFTs = 4 slots of one field
+    static constexpr int NT = 2 * TPF;            // 2 pair FFTs = 4 slots of one field  (= NZ/2)
     static constexpr int LC = NZ + 2;             // column buffer stride (rows 0..NZ used)
-    static constexpr int PL = padded_len(M);
-    static constexpr int SCR = 2 * 2 * PL;        // doubles of FFT scratch
+    static constexpr int SCR = 2 * 2 * M;         // doubles of FFT scratch (2 FFTs x re/im x M)
     static constexpr int BUF = 4 * LC;            // doubles per 4-slot field buffer
+    static constexpr int ZI = 3;                  // rows per thread: t, t+NT, and NZ (thread 0 only)
 };
 
 // ---- group bookkeeping -----------------------------------------------------
@@ -86,43 +92,65 @@ __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
     return r;
 }
 
-__device__ __forceinline__ bool slot_active(const Grp& r, int s) { return !(r.dupx && s >= 2); }
+// number of active slots: 2 when the x-mirror is the column itself
+__device__ __forceinline__ int nslots(const Grp& r) { return r.dupx ? 2 : 4; }
 
+// ---- z-owner helpers ----------------------------------------------------------
+// row owned by this thread in iteration `it` (-1: none)
 template <int NZ>
-__device__ __forceinline__ void col_load(double* buf, const double* __restrict__ src, const Grp& r) {
-    constexpr int LC = ZCfg<NZ>::LC;
-    for (int i = threadIdx.x; i < 4 * LC; i += blockDim.x) {
-        const int s = i / LC, z = i - s * LC;
-        buf[i] = (z <= NZ && slot_active(r, s)) ? src[r.off[s] + z] : 0.0;
-    }
+__device__ __forceinline__ int my_row(int it) {
+    constexpr int NT = ZCfg<NZ>::NT;
+    const int t = threadIdx.x;
+    if (it < 2) return t + it * NT;
+    return (t == 0) ? NZ : -1;
 }
 
+// Four-slot register tile of one row.
+struct Row4 { double v[4]; };
+
 template <int NZ>
-__device__ __forceinline__ void col_store(double* __restrict__ dst, const double* buf, const Grp& r) {
+__device__ __forceinline__ Row4 row_load_g(const double* __restrict__ src, const Grp& r, int z) {
+    Row4 x;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) x.v[s] = (s < 2 || !r.dupx) ? src[r.off[s] + z] : 0.0;
+    return x;
+}
+template <int NZ>
+__device__ __forceinline__ void row_store_g(double* __restrict__ dst, const Grp& r, int z, const Row4& x) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (s < 2 || !r.dupx) dst[r.off[s] + z] = x.v[s];
+}
+template <int NZ>
+__device__ __forceinline__ Row4 row_load_s(const double* buf, int z) {
     constexpr int LC = ZCfg<NZ>::LC;
-    for (int i = threadIdx.x; i < 4 * LC; i += blockDim.x) {
-        const int s = i / LC, z = i - s * LC;
-        if (z <= NZ && slot_active(r, s)) dst[r.off[s] + z] = buf[i];
-    }
+    Row4 x;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) x.v[s] = buf[s * LC + z];
+    return x;
+}
+template <int NZ>
+__device__ __forceinline__ void row_store_s(double* buf, int z, const Row4& x) {
+    constexpr int LC = ZCfg<NZ>::LC;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) buf[s * LC + z] = x.v[s];
+}
+
+// d/dx, d/dy of a row (sta3dfft.f90:325-329): slot s = 2*sx + sy,
+//   sx = 0 (kx = b):  ds = -kx f(nx-b);   sx = 1 (kx = nx-b): ds = +kx f(b);   same in y with sy.
+__device__ __forceinline__ Row4 ddx(const Row4& f, const Grp& r) {
+    Row4 d;
+    d.v[0] = -r.kx * f.v[2]; d.v[1] = -r.kx * f.v[3]; d.v[2] = r.kx * f.v[0]; d.v[3] = r.kx * f.v[1];
+    return d;
+}
+__device__ __forceinline__ Row4 ddy(const Row4& f, const Grp& r) {
+    Row4 d;
+    d.v[0] = -r.ky * f.v[1]; d.v[1] = r.ky * f.v[0]; d.v[2] = -r.ky * f.v[3]; d.v[3] = r.ky * f.v[2];
+    return d;
 }
 
 // ---- harmonic (Laplace) functions on the fly -------------------------------
-// EP/EM[sy][i] = exp(-kl zp_i), exp(-kl zm_i)   (inversion_utils.f90:505-509)
-template <int NZ>
-__device__ __forceinline__ void hyp_tables(double* EP, double* EM, const SpecGeom& g, const Grp& r) {
-    constexpr int LC = ZCfg<NZ>::LC;
-    for (int i = threadIdx.x; i < 2 * LC; i += blockDim.x) {
-        const int sy = i / LC, z = i - sy * LC;
-        double ep = 0.0, em = 0.0;
-        if (z <= NZ) {
-            const double kl = sqrt(r.k2[sy]);
-            ep = exp(-(kl * __ldg(&g.zp[z])));
-            em = exp(-(kl * __ldg(&g.zm[z])));
-        }
-        EP[i] = ep; EM[i] = em;
-    }
-}
-
+// block constants per sy (inversion_utils.f90:494-503, 529-530)
 struct Hyp { double kl, ef, div, k2if, Q, R; bool lin; };
 
 __device__ __forceinline__ Hyp make_hyp(const SpecGeom& g, const Grp& r, int sy) {
@@ -137,25 +165,50 @@ __device__ __forceinline__ Hyp make_hyp(const SpecGeom& g, const Grp& r, int sy)
     return h;
 }
 
-__device__ __forceinline__ void hyp_phi(const Hyp& h, const SpecGeom& g, double ep, double em, int z,
-                                        double& phim, double& phip) {
-    if (h.lin) {
-        phim = __ldg(&g.zm[z]) / g.Lz;
-        phip = __ldg(&g.zp[z]) / g.Lz;
-    } else {
-        phim = h.div * (ep - h.ef * em);
-        phip = h.div * (em - h.ef * ep);
+// per-thread table for the rows this thread owns: phim, phip for sy = 0, 1 (inversion_utils.f90:505-519)
+template <int NZ>
+struct HypRows {
+    double zm[3], zp[3];
+    double ep[3][2], em[3][2];
+    double phim[3][2], phip[3][2];
+};
+
+template <int NZ>
+__device__ __forceinline__ void hyp_rows(HypRows<NZ>& T, const Hyp (&h)[2], const SpecGeom& g, const Grp& r) {
+    const bool same = (r.k2[0] == r.k2[1]) && !r.g00;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        T.zm[it] = __ldg(&g.zm[z]);
+        T.zp[it] = __ldg(&g.zp[z]);
+#pragma unroll
+        for (int sy = 0; sy < 2; ++sy) {
+            if (sy == 1 && same) {
+                T.ep[it][1] = T.ep[it][0]; T.em[it][1] = T.em[it][0];
+                T.phim[it][1] = T.phim[it][0]; T.phip[it][1] = T.phip[it][0];
+                continue;
+            }
+            const double ep = exp(-(h[sy].kl * T.zp[it]));
+            const double em = exp(-(h[sy].kl * T.zm[it]));
+            T.ep[it][sy] = ep; T.em[it][sy] = em;
+            if (h[sy].lin) {
+                T.phim[it][sy] = T.zm[it] / g.Lz;
+                T.phip[it][sy] = T.zp[it] / g.Lz;
+            } else {
+                T.phim[it][sy] = h[sy].div * (ep - h[sy].ef * em);
+                T.phip[it][sy] = h[sy].div * (em - h[sy].ef * ep);
+            }
+        }
     }
 }
 
-// thetam, thetap, dthetam, dthetap (inversion_utils.f90:518-541)
-__device__ __forceinline__ void hyp_theta(const Hyp& h, const SpecGeom& g, double ep, double em, int z,
-                                          double& thm, double& thp, double& dthm, double& dthp) {
+// thetam, thetap, dthetam, dthetap of one row (inversion_utils.f90:518-541)
+__device__ __forceinline__ void hyp_theta(const Hyp& h, double ep, double em, double zm, double zp, double phim,
+                                          double phip, double& thm, double& thp, double& dthm, double& dthp) {
     if (h.lin) { thm = thp = dthm = dthp = 0.0; return; }
-    const double Lm = h.kl * __ldg(&g.zm[z]);
-    const double Lp = h.kl * __ldg(&g.zp[z]);
-    const double phim = h.div * (ep - h.ef * em);
-    const double phip = h.div * (em - h.ef * ep);
+    const double Lm = h.kl * zm;
+    const double Lp = h.kl * zp;
     const double dphim = -h.kl * h.div * (ep + h.ef * em);
     const double dphip = h.kl * h.div * (em + h.ef * ep);
     thm = h.k2if * (h.R * Lm * phip - h.Q * Lp * phim);
@@ -166,38 +219,32 @@ __device__ __forceinline__ void hyp_theta(const Hyp& h, const SpecGeom& g, doubl
 
 // ---- z transforms on a 4-slot shared-memory field ---------------------------
 // DST-I of rows 1..NZ-1 of each slot (scaled sqrt(2/NZ)); rows 0 and NZ are
-// neither read nor written (stafft.f90:509-513).  Ends with a barrier.
+// neither read nor written (stafft.f90:509-513).  Ends with a barrier; the
+// caller must have a barrier between its last write of X and this call.
 template <int NZ>
 __device__ __forceinline__ void dst4(double* X, double* scr, const SpecGeom& g) {
-    constexpr int M = ZCfg<NZ>::M, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC, PL = ZCfg<NZ>::PL;
+    constexpr int M = ZCfg<NZ>::M, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
     const int t = threadIdx.x;
     const int f = t / TPF, u = t - f * TPF;
-    const bool active = f < 2;
-    const double* x0 = X + (2 * f) * LC;
-    const double* x1 = x0 + LC;
+    double* x0 = X + (2 * f) * LC;
+    double* x1 = x0 + LC;
     double vr[8], vi[8];
-    if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = u + e * (M / 8);
-            double a = 0.0, c = 0.0;
-            if (j > 0 && j < NZ) { a = x0[j]; c = x1[j]; }
-            else if (j > NZ) { a = -x0[M - j]; c = -x1[M - j]; }
-            vr[e] = a; vi[e] = c;
-        }
+    for (int e = 0; e < 8; ++e) {
+        const int j = u + e * (M / 8);
+        double a = 0.0, c = 0.0;
+        if (j > 0 && j < NZ) { a = x0[j]; c = x1[j]; }
+        else if (j > NZ) { a = -x0[M - j]; c = -x1[M - j]; }
+        vr[e] = a; vi[e] = c;
     }
-    double* sre = scr + (active ? f : 0) * 2 * PL;
-    double* sim = sre + PL;
-    block_cfft<M, false>(vr, vi, u, active, sre, sim, g.tw, g.ntw / M);
+    double* sre = scr + f * 2 * M;
+    double* sim = sre + M;
+    block_cfft<M, false>(vr, vi, u, true, sre, sim, IxSwz(), g.tw, g.ntw / M);
     const double sc = rsqrt((double)M);     // 1/sqrt(2 nz)
-    if (active) {
-        double* y0 = X + (2 * f) * LC;
-        double* y1 = y0 + LC;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = u + e * (M / 8);
-            if (k >= 1 && k < NZ) { y0[k] = -vi[e] * sc; y1[k] = vr[e] * sc; }
-        }
+    for (int e = 0; e < 4; ++e) {
+        const int k = u + e * (M / 8);
+        if (k >= 1) { x0[k] = -vi[e] * sc; x1[k] = vr[e] * sc; }     // k < NZ always for e < 4
     }
     __syncthreads();
 }
@@ -205,95 +252,28 @@ __device__ __forceinline__ void dst4(double* X, double* scr, const SpecGeom& g) 
 // DCT-I of rows 0..NZ of each slot (scaled sqrt(2/NZ)).  Ends with a barrier.
 template <int NZ>
 __device__ __forceinline__ void dct4(double* X, double* scr, const SpecGeom& g) {
-    constexpr int M = ZCfg<NZ>::M, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC, PL = ZCfg<NZ>::PL;
+    constexpr int M = ZCfg<NZ>::M, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
     const int t = threadIdx.x;
     const int f = t / TPF, u = t - f * TPF;
-    const bool active = f < 2;
-    const double* x0 = X + (2 * f) * LC;
-    const double* x1 = x0 + LC;
+    double* x0 = X + (2 * f) * LC;
+    double* x1 = x0 + LC;
     double vr[8], vi[8];
-    if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = u + e * (M / 8);
-            const int jj = (j <= NZ) ? j : M - j;
-            vr[e] = x0[jj]; vi[e] = x1[jj];
-        }
+    for (int e = 0; e < 8; ++e) {
+        const int j = u + e * (M / 8);
+        const int jj = (j <= NZ) ? j : M - j;
+        vr[e] = x0[jj]; vi[e] = x1[jj];
     }
-    double* sre = scr + (active ? f : 0) * 2 * PL;
-    double* sim = sre + PL;
-    block_cfft<M, false>(vr, vi, u, active, sre, sim, g.tw, g.ntw / M);
+    double* sre = scr + f * 2 * M;
+    double* sim = sre + M;
+    block_cfft<M, false>(vr, vi, u, true, sre, sim, IxSwz(), g.tw, g.ntw / M);
     const double sc = rsqrt((double)M);
-    if (active) {
-        double* y0 = X + (2 * f) * LC;
-        double* y1 = y0 + LC;
 #pragma unroll
-        for (int e = 0; e < 5; ++e) {
-            const int k = u + e * (M / 8);
-            if (k <= NZ) { y0[k] = vr[e] * sc; y1[k] = vi[e] * sc; }
-        }
+    for (int e = 0; e < 5; ++e) {
+        const int k = u + e * (M / 8);
+        if (k <= NZ) { x0[k] = vr[e] * sc; x1[k] = vi[e] * sc; }
     }
     __syncthreads();
-}
-
-// X(1..NZ-1) += / -= X(0) phim + X(NZ) phip   (inversion_utils.f90:571, 643)
-template <int NZ, int SIGN>
-__device__ __forceinline__ void harmonic(double* X, const double* EP, const double* EM,
-                                         const SpecGeom& g, const Grp& r) {
-    constexpr int LC = ZCfg<NZ>::LC;
-    const Hyp h0 = make_hyp(g, r, 0), h1 = make_hyp(g, r, 1);
-    for (int i = threadIdx.x; i < 4 * LC; i += blockDim.x) {
-        const int s = i / LC, z = i - s * LC, sy = s & 1;
-        if (z >= 1 && z < NZ) {
-            double phim, phip;
-            hyp_phi(sy ? h1 : h0, g, EP[sy * LC + z], EM[sy * LC + z], z, phim, phip);
-            const double hpart = X[s * LC] * phim + X[s * LC + NZ] * phip;
-            X[i] = (SIGN > 0) ? X[i] + hpart : X[i] - hpart;
-        }
-    }
-    __syncthreads();
-}
-
-// field_combine_semi_spectral in place (inversion_utils.f90:617-647)
-template <int NZ>
-__device__ __forceinline__ void combine4(double* X, double* scr, const double* EP, const double* EM,
-                                         const SpecGeom& g, const Grp& r) {
-    dst4<NZ>(X, scr, g);
-    harmonic<NZ, +1>(X, EP, EM, g, r);
-}
-
-// field_decompose_semi_spectral in place (inversion_utils.f90:563-592)
-template <int NZ>
-__device__ __forceinline__ void decompose4(double* X, double* scr, const double* EP, const double* EM,
-                                           const SpecGeom& g, const Grp& r) {
-    harmonic<NZ, -1>(X, EP, EM, g, r);
-    dst4<NZ>(X, scr, g);
-}
-
-// D = central_diffz(S)  (inversion_utils.f90:653-673).  Ends with a barrier.
-template <int NZ>
-__device__ __forceinline__ void diffz4(double* D, const double* S, const SpecGeom& g) {
-    constexpr int LC = ZCfg<NZ>::LC;
-    for (int i = threadIdx.x; i < 4 * LC; i += blockDim.x) {
-        const int s = i / LC, z = i - s * LC;
-        if (z == 0) D[i] = g.dzi * (S[i + 1] - S[i]);
-        else if (z == NZ) D[i] = g.dzi * (S[i] - S[i - 1]);
-        else if (z < NZ) D[i] = (S[i + 1] - S[i - 1]) * g.hdzi;
-    }
-    __syncthreads();
-}
-
-// d/dx and d/dy of a 4-slot field at element i = s*LC + z (sta3dfft.f90:325-329):
-//   slot sx = 0 (kx = b):    ds = -kx * f(nx-b) ;  slot sx = 1 (kx = nx-b): ds = +kx * f(b)
-template <int NZ>
-__device__ __forceinline__ double ddx(const double* F, int i, int s, const Grp& r) {
-    constexpr int LC = ZCfg<NZ>::LC;
-    return (s & 2) ? r.kx * F[i - 2 * LC] : -r.kx * F[i + 2 * LC];
-}
-template <int NZ>
-__device__ __forceinline__ double ddy(const double* F, int i, int s, const Grp& r) {
-    constexpr int LC = ZCfg<NZ>::LC;
-    return (s & 1) ? r.ky * F[i - LC] : -r.ky * F[i + LC];
 }
 
 // ---------------------------------------------------------------------------
@@ -304,7 +284,7 @@ __device__ __forceinline__ double ddy(const double* F, int i, int s, const Grp& 
 enum { ZOP_SINE = 0, ZOP_COSINE, ZOP_COMBINE, ZOP_DECOMPOSE, ZOP_DIFFZ, ZOP_DIFFX, ZOP_DIFFY };
 
 template <int NZ>
-constexpr size_t zop_smem_bytes() { return (size_t)(3 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
+constexpr size_t zop_smem_bytes() { return (size_t)(ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
 template <int NZ>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const double* __restrict__ in,
@@ -312,38 +292,67 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
     PS_SMEM(double, sm);
     constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
     double* X = sm;
-    double* Y = X + BUF;
-    double* EP = Y + BUF;
-    double* EM = EP + 2 * LC;
-    double* scr = EP + BUF;
+    double* scr = X + BUF;
     const Grp r = make_grp(g, blockIdx.x);
-    col_load<NZ>(X, in, r);
-    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE) hyp_tables<NZ>(EP, EM, g, r);
-    __syncthreads();
-    if (op == ZOP_SINE) {
-        dst4<NZ>(X, scr, g);
-        for (int s = threadIdx.x; s < 4; s += blockDim.x) X[s * LC + NZ] = 0.0;   // stafft.f90:546-549
-        __syncthreads();
-        col_store<NZ>(out, X, r);
-    } else if (op == ZOP_COSINE) {
-        dct4<NZ>(X, scr, g);
-        col_store<NZ>(out, X, r);
-    } else if (op == ZOP_COMBINE) {
-        combine4<NZ>(X, scr, EP, EM, g, r);
-        col_store<NZ>(out, X, r);
-    } else if (op == ZOP_DECOMPOSE) {
-        decompose4<NZ>(X, scr, EP, EM, g, r);
-        col_store<NZ>(out, X, r);
-    } else if (op == ZOP_DIFFZ) {
-        diffz4<NZ>(Y, X, g);
-        col_store<NZ>(out, Y, r);
-    } else {
-        for (int i = threadIdx.x; i < 4 * LC; i += blockDim.x) {
-            const int s = i / LC;
-            Y[i] = (op == ZOP_DIFFX) ? ddx<NZ>(X, i, s, r) : ddy<NZ>(X, i, s, r);
+    Hyp h[2];
+    HypRows<NZ> T;
+    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE) {
+        h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
+        hyp_rows<NZ>(T, h, g, r);
+    }
+    if (op == ZOP_DIFFX || op == ZOP_DIFFY) {
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            const Row4 x = row_load_g<NZ>(in, r, z);
+            row_store_g<NZ>(out, r, z, op == ZOP_DIFFX ? ddx(x, r) : ddy(x, r));
         }
-        __syncthreads();
-        col_store<NZ>(out, Y, r);
+        return;
+    }
+    // stage the columns
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 x = row_load_g<NZ>(in, r, z);
+        if (op == ZOP_DECOMPOSE && z >= 1 && z < NZ) {
+            // subtract the harmonic part (inversion_utils.f90:571); boundary rows straight from memory
+            const Row4 x0 = row_load_g<NZ>(in, r, 0), xn = row_load_g<NZ>(in, r, NZ);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x.v[s] -= x0.v[s] * T.phim[it][s & 1] + xn.v[s] * T.phip[it][s & 1];
+        }
+        row_store_s<NZ>(X, z, x);
+    }
+    __syncthreads();
+    if (op == ZOP_DIFFZ) {
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            Row4 d;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double* c = X + s * LC;
+                d.v[s] = (z == 0) ? g.dzi * (c[1] - c[0]) : (z == NZ) ? g.dzi * (c[NZ] - c[NZ - 1]) : (c[z + 1] - c[z - 1]) * g.hdzi;
+            }
+            row_store_g<NZ>(out, r, z, d);
+        }
+        return;
+    }
+    if (op == ZOP_COSINE) dct4<NZ>(X, scr, g);
+    else dst4<NZ>(X, scr, g);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 x = row_load_s<NZ>(X, z);
+        if (op == ZOP_SINE && z == NZ) { x.v[0] = x.v[1] = x.v[2] = x.v[3] = 0.0; }     // stafft.f90:546-549
+        if (op == ZOP_COMBINE && z >= 1 && z < NZ) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x.v[s] += X[s * LC] * T.phim[it][s & 1] + X[s * LC + NZ] * T.phip[it][s & 1];
+        }
+        row_store_g<NZ>(out, r, z, x);
     }
 }
 
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
 // the inverse x/y passes that give `vor`), svel.
 // ---------------------------------------------------------------------------
 template <int NZ>
-constexpr size_t v2v_smem_bytes() { return (size_t)(6 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR + 16) * sizeof(double); }
+constexpr size_t v2v_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
 struct V2VArgs {
     double* svor0; double* svor1; const double* svor2;   // in/out, in/out, in
@@ -362,126 +371,203 @@ struct V2VArgs {
 };
 
 template <int NZ>
-__global__ void __launch_bounds__(ZCfg<NZ>::NT) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
+__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ >= 512) ? 2 : 1) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
     PS_SMEM(double, sm);
     constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
     double* A = sm;
     double* B = A + BUF;
     double* C = B + BUF;
-    double* D = C + BUF;
-    double* E = D + BUF;
-    double* EP = E + BUF;
-    double* EM = EP + 2 * LC;
-    double* scr = EP + BUF;
-    double* bnd = scr + ZCfg<NZ>::SCR;       // [8] D(0), D(nz) per slot
-    const int tid = threadIdx.x, nt = blockDim.x;
+    double* E = C + BUF;
+    double* scr = E + BUF;
     const Grp r = make_grp(g, blockIdx.x);
+    Hyp h[2];
+    h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
+    HypRows<NZ> T;
+    hyp_rows<NZ>(T, h, g, r);
 
-    col_load<NZ>(A, a.svor0, r);
-    col_load<NZ>(B, a.svor1, r);
-    col_load<NZ>(C, a.svor2, r);
-    hyp_tables<NZ>(EP, EM, g, r);
-    __syncthreads();
-
-    // D = B_x - A_y   (inversion.f90:39-42)
-    for (int i = tid; i < 4 * LC; i += nt) {
-        const int s = i / LC;
-        D[i] = ddx<NZ>(B, i, s, r) - ddy<NZ>(A, i, s, r);
-    }
-    // C -> semi-spectral zeta (inversion.f90:45); E = C_z, decomposed (:46-47)
-    combine4<NZ>(C, scr, EP, EM, g, r);
-    diffz4<NZ>(E, C, g);
-    decompose4<NZ>(E, scr, EP, EM, g, r);
-
-    // A = k2l2i (E_x + D_y), B = k2l2i (E_y - D_x); (0,0) column keeps its mean (:55-76)
-    for (int i = tid; i < 4 * LC; i += nt) {
-        const int s = i / LC;
-        if (r.g00 && s == 0) continue;
-        const double k2i = r.k2i[s & 1];
-        A[i] = k2i * (ddx<NZ>(E, i, s, r) + ddy<NZ>(D, i, s, r));
-        B[i] = k2i * (ddy<NZ>(E, i, s, r) - ddx<NZ>(D, i, s, r));
+    // stage svor
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        row_store_s<NZ>(A, z, row_load_g<NZ>(a.svor0, r, z));
+        row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
+        row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
     }
     __syncthreads();
-    col_store<NZ>(a.svor0, A, r);
-    col_store<NZ>(a.svor1, B, r);
 
-    // source of the w inversion: D = A_y - B_x (mixed spectral) (:86-90)
-    for (int i = tid; i < 4 * LC; i += nt) {
-        const int s = i / LC;
-        D[i] = ddy<NZ>(A, i, s, r) - ddx<NZ>(B, i, s, r);
+    // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; also the
+    // semi-spectral zeta that feeds the inverse x/y passes (:81)
+    dst4<NZ>(C, scr, g);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 c = row_load_s<NZ>(C, z);
+        if (z >= 1 && z < NZ) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) c.v[s] += C[s * LC] * T.phim[it][s & 1] + C[s * LC + NZ] * T.phip[it][s & 1];
+            row_store_s<NZ>(C, z, c);
+        }
+        row_store_g<NZ>(a.wsem2, r, z, c);
     }
-    // horizontally averaged flow from the (0,0) column (:150-165) -> E slots 0 (ubar), 1 (vbar)
-    if (r.g00) {
-        for (int i = tid; i < 4 * LC; i += nt) {
-            const int s = i / LC, z = i - s * LC;
-            double v = 0.0;
-            if (z >= 1 && z < NZ) {
-                const double rkzi = 1.0 / __ldg(&g.rkz[z]);
-                if (s == 0) v = -rkzi * B[z];
-                else if (s == 1) v = rkzi * A[z];
+    __syncthreads();
+    // E = decompose(central_diffz(C)) (:46-47): FD, harmonic part removed, then DST
+    {
+        double e0[4], en[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const double* c = C + s * LC;
+            e0[s] = g.dzi * (c[1] - c[0]);
+            en[s] = g.dzi * (c[NZ] - c[NZ - 1]);
+        }
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            Row4 e;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double* c = C + s * LC;
+                if (z == 0) e.v[s] = e0[s];
+                else if (z == NZ) e.v[s] = en[s];
+                else e.v[s] = (c[z + 1] - c[z - 1]) * g.hdzi - (e0[s] * T.phim[it][s & 1] + en[s] * T.phip[it][s & 1]);
             }
-            E[i] = v;
-        }
-        __syncthreads();
-        dct4<NZ>(E, scr, g);
-        for (int z = tid; z <= NZ; z += nt) {
-            const double gt = __ldg(&g.gamtop[z]), gb = __ldg(&g.gambot[z]);
-            E[z] = E[z] + B[NZ] * gt - B[0] * gb;            // ubar
-            E[LC + z] = E[LC + z] - A[NZ] * gt + A[0] * gb;  // vbar
+            row_store_s<NZ>(E, z, e);
         }
     }
     __syncthreads();
+    dst4<NZ>(E, scr, g);
+
+    // D = B_x - A_y (:39-42); A = k2l2i (E_x + D_y), B = k2l2i (E_y - D_x), (0,0) keeps its mean (:55-76);
+    // then the source of the w inversion D2 = A_y - B_x (:86-90) -> E buffer
+    double ub[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};     // (0,0) group: ubar/vbar sources of my rows
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 fa = row_load_s<NZ>(A, z), fb = row_load_s<NZ>(B, z);
+        const Row4 fe = row_load_s<NZ>(E, z);
+        const Row4 bx = ddx(fb, r), ay = ddy(fa, r);
+        Row4 d;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) d.v[s] = bx.v[s] - ay.v[s];
+        const Row4 ex = ddx(fe, r), ey = ddy(fe, r), dx_ = ddx(d, r), dy_ = ddy(d, r);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (r.g00 && s == 0) continue;
+            fa.v[s] = r.k2i[s & 1] * (ex.v[s] + dy_.v[s]);
+            fb.v[s] = r.k2i[s & 1] * (ey.v[s] - dx_.v[s]);
+        }
+        row_store_g<NZ>(a.svor0, r, z, fa);
+        row_store_g<NZ>(a.svor1, r, z, fb);
+        row_store_s<NZ>(A, z, fa);
+        row_store_s<NZ>(B, z, fb);
+        const Row4 ay2 = ddy(fa, r), bx2 = ddx(fb, r);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) d.v[s] = ay2.v[s] - bx2.v[s];
+        row_store_s<NZ>(E, z, d);
+        if (r.g00 && z >= 1 && z < NZ) {                     // :153-154
+            const double rkzi = 1.0 / __ldg(&g.rkz[z]);
+            ub[it] = -rkzi * fb.v[0];
+            vb[it] = rkzi * fa.v[0];
+        }
+    }
+    __syncthreads();
+    // boundary values of D2 (:96-104) and of the mean vorticity (:163-164), before anything is overwritten
+    double d0[4], dn[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { d0[s] = E[s * LC]; dn[s] = E[s * LC + NZ]; }
+    const double a00 = A[0], a0n = A[NZ], b00 = B[0], b0n = B[NZ];
 
     // vorticity to semi-spectral space for the inverse x/y passes (:80-82)
-    combine4<NZ>(A, scr, EP, EM, g, r);
-    combine4<NZ>(B, scr, EP, EM, g, r);
-    col_store<NZ>(a.wsem0, A, r);
-    col_store<NZ>(a.wsem1, B, r);
-    col_store<NZ>(a.wsem2, C, r);
-    for (int s = tid; s < 4; s += nt) { bnd[s] = D[s * LC]; bnd[4 + s] = D[s * LC + NZ]; }
+    dst4<NZ>(A, scr, g);
+    dst4<NZ>(B, scr, g);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 fa = row_load_s<NZ>(A, z), fb = row_load_s<NZ>(B, z);
+        if (z >= 1 && z < NZ) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                fa.v[s] += A[s * LC] * T.phim[it][s & 1] + A[s * LC + NZ] * T.phip[it][s & 1];
+                fb.v[s] += B[s * LC] * T.phim[it][s & 1] + B[s * LC + NZ] * T.phip[it][s & 1];
+            }
+        }
+        row_store_g<NZ>(a.wsem0, r, z, fa);
+        row_store_g<NZ>(a.wsem1, r, z, fb);
+    }
     __syncthreads();
 
-    // invert Laplacian (:108-122): D <- green * D (rows 1..nz-1), A <- rkz * D
-    for (int i = tid; i < 4 * LC; i += nt) {
-        const int s = i / LC, z = i - s * LC;
-        double as = 0.0;
+    // invert Laplacian (:108-122): E <- green * D2 (rows 1..nz-1), A <- rkz * E (cosine series of dw/dz)
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 as, ds = row_load_s<NZ>(E, z);
         if (z >= 1 && z < NZ) {
             const double rk = __ldg(&g.rkz[z]);
-            const double green = -1.0 / (r.k2[s & 1] + rk * rk);
-            const double d = green * D[i];
-            D[i] = d;
-            as = rk * d;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double green = -1.0 / (r.k2[s & 1] + rk * rk);
+                ds.v[s] = green * ds.v[s];
+                as.v[s] = rk * ds.v[s];
+            }
+            row_store_s<NZ>(E, z, ds);
+        } else {
+            as.v[0] = as.v[1] = as.v[2] = as.v[3] = 0.0;
         }
-        A[i] = as;
+        row_store_s<NZ>(A, z, as);
+    }
+    // horizontally averaged flow from the (0,0) column (:150-165): cosine transform in B slots 0, 1
+    if (r.g00) {
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            Row4 m;
+            m.v[0] = ub[it]; m.v[1] = vb[it]; m.v[2] = 0.0; m.v[3] = 0.0;
+            row_store_s<NZ>(B, z, m);
+        }
     }
     __syncthreads();
     dct4<NZ>(A, scr, g);     // (:128)
-    dst4<NZ>(D, scr, g);     // (:129)
-    // w = D + boundary part, dw/dz = es + as  (:96-104, :136-139); B <- dw/dz
-    {
-        const Hyp h0 = make_hyp(g, r, 0), h1 = make_hyp(g, r, 1);
-        for (int i = tid; i < 4 * LC; i += nt) {
-            const int s = i / LC, z = i - s * LC, sy = s & 1;
-            if (z > NZ) continue;
-            double thm, thp, dthm, dthp;
-            hyp_theta(sy ? h1 : h0, g, EP[sy * LC + z], EM[sy * LC + z], z, thm, thp, dthm, dthp);
-            const double d0 = bnd[s], dn = bnd[4 + s];
-            B[i] = d0 * dthm + dn * dthp + A[i];
-            D[i] = (z == 0 || z == NZ) ? 0.0 : D[i] + d0 * thm + dn * thp;
-        }
-    }
-    __syncthreads();
+    dst4<NZ>(E, scr, g);     // (:129)
+    if (r.g00) dct4<NZ>(B, scr, g);
+
+    // w = E + boundary part, dw/dz = es + as (:96-104, :136-139);
     // u = k2l2i (es_x + cs_y), v = k2l2i (es_y - cs_x), (0,0) <- ubar, vbar (:169-213)
-    for (int i = tid; i < 4 * LC; i += nt) {
-        const int s = i / LC, z = i - s * LC;
-        if (z > NZ || !slot_active(r, s)) continue;
-        const double k2i = r.k2i[s & 1];
-        double u = k2i * (ddx<NZ>(B, i, s, r) + ddy<NZ>(C, i, s, r));
-        double v = k2i * (ddy<NZ>(B, i, s, r) - ddx<NZ>(C, i, s, r));
-        if (r.g00 && s == 0) { u = E[z]; v = E[LC + z]; }
-        a.svel0[r.off[s] + z] = u;
-        a.svel1[r.off[s] + z] = v;
-        a.svel2[r.off[s] + z] = D[i];
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        const Row4 as = row_load_s<NZ>(A, z), ds = row_load_s<NZ>(E, z), cs = row_load_s<NZ>(C, z);
+        Row4 es, w;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int sy = s & 1;
+            double thm, thp, dthm, dthp;
+            hyp_theta(h[sy], T.ep[it][sy], T.em[it][sy], T.zm[it], T.zp[it], T.phim[it][sy], T.phip[it][sy],
+                      thm, thp, dthm, dthp);
+            es.v[s] = d0[s] * dthm + dn[s] * dthp + as.v[s];
+            w.v[s] = (z == 0 || z == NZ) ? 0.0 : ds.v[s] + d0[s] * thm + dn[s] * thp;
+        }
+        const Row4 ex = ddx(es, r), ey = ddy(es, r), cx = ddx(cs, r), cy = ddy(cs, r);
+        Row4 u, v;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            u.v[s] = r.k2i[s & 1] * (ex.v[s] + cy.v[s]);
+            v.v[s] = r.k2i[s & 1] * (ey.v[s] - cx.v[s]);
+        }
+        if (r.g00) {
+            const double gt = __ldg(&g.gamtop[z]), gb = __ldg(&g.gambot[z]);
+            u.v[0] = B[z] + b0n * gt - b00 * gb;               // ubar (:163)
+            v.v[0] = B[LC + z] - a0n * gt + a00 * gb;          // vbar (:164)
+        }
+        row_store_g<NZ>(a.svel0, r, z, u);
+        row_store_g<NZ>(a.svel1, r, z, v);
+        row_store_g<NZ>(a.svel2, r, z, w);
     }
 }
 
@@ -492,45 +578,111 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_vor2vel_spec(SpecGeom g, V2VAr
 // are formed here instead of through two more 2-D FFTs.
 // ---------------------------------------------------------------------------
 template <int NZ>
-constexpr size_t src_smem_bytes() { return (size_t)(6 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
+constexpr size_t src_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
 struct SrcArgs {
     const double* r; const double* q; const double* p;   // semi-spectral fluxes
     double* s0; double* s1; double* s2;                  // svorts (mixed spectral)
 };
 
+// stage a semi-spectral field F (global) with its harmonic part removed -> buffer X (rows 0, NZ kept),
+// and optionally the same for central_diffz(F) -> buffer DX.
 template <int NZ>
-__global__ void __launch_bounds__(ZCfg<NZ>::NT) k_source_spec(SpecGeom g, SrcArgs a) {
+__device__ __forceinline__ void stage_decomposed(double* X, const double* __restrict__ F, const HypRows<NZ>& T,
+                                                 const Grp& r) {
+    const Row4 x0 = row_load_g<NZ>(F, r, 0), xn = row_load_g<NZ>(F, r, NZ);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 x = row_load_g<NZ>(F, r, z);
+        if (z >= 1 && z < NZ) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x.v[s] -= x0.v[s] * T.phim[it][s & 1] + xn.v[s] * T.phip[it][s & 1];
+        }
+        row_store_s<NZ>(X, z, x);
+    }
+}
+
+template <int NZ>
+__device__ __forceinline__ void stage_diffz_decomposed(double* DX, const double* __restrict__ F, const SpecGeom& g,
+                                                       const HypRows<NZ>& T, const Grp& r) {
+    const Row4 f0 = row_load_g<NZ>(F, r, 0), f1 = row_load_g<NZ>(F, r, 1);
+    const Row4 fn = row_load_g<NZ>(F, r, NZ), fm = row_load_g<NZ>(F, r, NZ - 1);
+    Row4 e0, en;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { e0.v[s] = g.dzi * (f1.v[s] - f0.v[s]); en.v[s] = g.dzi * (fn.v[s] - fm.v[s]); }
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 d;
+        if (z == 0) d = e0;
+        else if (z == NZ) d = en;
+        else {
+            const Row4 up = row_load_g<NZ>(F, r, z + 1), dn = row_load_g<NZ>(F, r, z - 1);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                d.v[s] = (up.v[s] - dn.v[s]) * g.hdzi - (e0.v[s] * T.phim[it][s & 1] + en.v[s] * T.phip[it][s & 1]);
+        }
+        row_store_s<NZ>(DX, z, d);
+    }
+}
+
+template <int NZ>
+__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ >= 512) ? 2 : 1) k_source_spec(SpecGeom g, SrcArgs a) {
     PS_SMEM(double, sm);
-    constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
+    constexpr int BUF = ZCfg<NZ>::BUF;
     double* R = sm;
-    double* Q = R + BUF;
-    double* P = Q + BUF;
-    double* DQ = P + BUF;
-    double* DP = DQ + BUF;
-    double* EP = DP + BUF;
-    double* EM = EP + 2 * LC;
-    double* scr = EP + BUF;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    double* X = R + BUF;
+    double* Y = X + BUF;
+    double* W = Y + BUF;
+    double* scr = W + BUF;
     const Grp r = make_grp(g, blockIdx.x);
-    col_load<NZ>(R, a.r, r);
-    col_load<NZ>(Q, a.q, r);
-    col_load<NZ>(P, a.p, r);
-    hyp_tables<NZ>(EP, EM, g, r);
+    Hyp h[2];
+    h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
+    HypRows<NZ> T;
+    hyp_rows<NZ>(T, h, g, r);
+
+    // R = decompose(r), X = decompose(dq/dz), Y = decompose(dp/dz), W = decompose(q)
+    stage_decomposed<NZ>(R, a.r, T, r);
+    stage_diffz_decomposed<NZ>(X, a.q, g, T, r);
+    stage_diffz_decomposed<NZ>(Y, a.p, g, T, r);
+    stage_decomposed<NZ>(W, a.q, T, r);
     __syncthreads();
-    diffz4<NZ>(DQ, Q, g);
-    diffz4<NZ>(DP, P, g);
-    decompose4<NZ>(R, scr, EP, EM, g, r);
-    decompose4<NZ>(Q, scr, EP, EM, g, r);
-    decompose4<NZ>(P, scr, EP, EM, g, r);
-    decompose4<NZ>(DQ, scr, EP, EM, g, r);
-    decompose4<NZ>(DP, scr, EP, EM, g, r);
-    for (int i = tid; i < 4 * LC; i += nt) {
-        const int s = i / LC, z = i - s * LC;
-        if (z > NZ || !slot_active(r, s)) continue;
-        a.s0[r.off[s] + z] = ddy<NZ>(R, i, s, r) - DQ[i];                      // dr/dy - dq/dz
-        a.s1[r.off[s] + z] = DP[i] - ddx<NZ>(R, i, s, r);                      // dp/dz - dr/dx
-        a.s2[r.off[s] + z] = ddx<NZ>(Q, i, s, r) - ddy<NZ>(P, i, s, r);        // dq/dx - dp/dy
+    dst4<NZ>(R, scr, g);
+    dst4<NZ>(X, scr, g);
+    dst4<NZ>(Y, scr, g);
+    dst4<NZ>(W, scr, g);
+    // xi, eta tendencies (inversion.f90:341-359); keep d(q)/dx of my rows for the zeta tendency
+    Row4 qx[3];
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        const Row4 fr = row_load_s<NZ>(R, z), dq = row_load_s<NZ>(X, z), dp = row_load_s<NZ>(Y, z);
+        const Row4 ry = ddy(fr, r), rx = ddx(fr, r);
+        Row4 s0, s1;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { s0.v[s] = ry.v[s] - dq.v[s]; s1.v[s] = dp.v[s] - rx.v[s]; }
+        row_store_g<NZ>(a.s0, r, z, s0);       // dr/dy - dq/dz
+        row_store_g<NZ>(a.s1, r, z, s1);       // dp/dz - dr/dx
+        qx[it] = ddx(row_load_s<NZ>(W, z), r);
+    }
+    __syncthreads();
+    // zeta tendency dq/dx - dp/dy (:363-367)
+    stage_decomposed<NZ>(R, a.p, T, r);
+    __syncthreads();
+    dst4<NZ>(R, scr, g);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        const Row4 py = ddy(row_load_s<NZ>(R, z), r);
+        Row4 s2;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) s2.v[s] = qx[it].v[s] - py.v[s];
+        row_store_g<NZ>(a.s2, r, z, s2);
     }
 }
 
