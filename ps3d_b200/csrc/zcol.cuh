@@ -179,7 +179,14 @@ __device__ __forceinline__ void hyp_rows(HypRows<NZ>& T, const Hyp (&h)[2], cons
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
-        if (z < 0) continue;
+        if (z < 0) {
+            // never read, but keep every register defined on every path: ptxas 12.9 was seen to emit spill
+            // loads without the matching stores for values that are undefined on some lanes
+            T.zm[it] = T.zp[it] = 0.0;
+            T.ep[it][0] = T.ep[it][1] = T.em[it][0] = T.em[it][1] = 0.0;
+            T.phim[it][0] = T.phim[it][1] = T.phip[it][0] = T.phip[it][1] = 0.0;
+            continue;
+        }
         T.zm[it] = __ldg(&g.zm[z]);
         T.zp[it] = __ldg(&g.zp[z]);
 #pragma unroll
@@ -368,6 +375,7 @@ struct V2VArgs {
     double* svor0; double* svor1; const double* svor2;   // in/out, in/out, in
     double* wsem0; double* wsem1; double* wsem2;         // semi-spectral vorticity (out)
     double* svel0; double* svel1; double* svel2;         // semi-spectral velocity (out)
+    int dbg;
 };
 
 template <int NZ>
@@ -565,6 +573,41 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ >= 512) ? 2 : 1) k_vor2vel_s
             u.v[0] = B[z] + b0n * gt - b00 * gb;               // ubar (:163)
             v.v[0] = B[LC + z] - a0n * gt + a00 * gb;          // vbar (:164)
         }
+        if (a.dbg == 1) {
+            Row4 t1, t2;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                double thm, thp, dthm, dthp;
+                hyp_theta(h[s & 1], T.ep[it][s & 1], T.em[it][s & 1], T.zm[it], T.zp[it], T.phim[it][s & 1], T.phip[it][s & 1],
+                          thm, thp, dthm, dthp);
+                t1.v[s] = dthm; t2.v[s] = dthp;
+            }
+            if (a.dbg == 1) { u = es; v = as; w = t1; }
+            (void)t2;
+        }
+        if (a.dbg == 4) {
+            Row4 t1, t2, t3;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                double thm, thp, dthm, dthp;
+                hyp_theta(h[s & 1], T.ep[it][s & 1], T.em[it][s & 1], T.zm[it], T.zp[it], T.phim[it][s & 1], T.phip[it][s & 1],
+                          thm, thp, dthm, dthp);
+                t1.v[s] = dthm; t2.v[s] = dthp; t3.v[s] = (s & 2) ? thp : thm;
+            }
+            u = t1; v = t2; w = t3;
+        }
+        if (a.dbg == 3) {
+            Row4 t1, t2, t3;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { t1.v[s] = (s & 2) ? T.zm[it] : T.ep[it][s & 1]; t2.v[s] = (s & 2) ? T.zp[it] : T.em[it][s & 1]; t3.v[s] = (s & 2) ? T.phip[it][s & 1] : T.phim[it][s & 1]; }
+            u = t1; v = t2; w = t3;
+        }
+        if (a.dbg == 2) {
+            Row4 t1, t2;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { t1.v[s] = d0[s]; t2.v[s] = dn[s]; }
+            u = t1; v = t2; w = ds;
+        }
         row_store_g<NZ>(a.svel0, r, z, u);
         row_store_g<NZ>(a.svel1, r, z, v);
         row_store_g<NZ>(a.svel2, r, z, w);
@@ -655,7 +698,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ >= 512) ? 2 : 1) k_source_sp
     dst4<NZ>(Y, scr, g);
     dst4<NZ>(W, scr, g);
     // xi, eta tendencies (inversion.f90:341-359); keep d(q)/dx of my rows for the zeta tendency
-    Row4 qx[3];
+    Row4 qx[3] = {};
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
