@@ -100,9 +100,19 @@ __device__ __forceinline__ void radix(double* xr, double* xi) {
 //   v[g + j*(8/R)]) and belong at x'[q + s*(R*p + j)], p = b / s, q = b % s.
 // `s` is the product of the radices of the previous passes.
 // tw[m] = (cos(2 pi m / NTW), sin(2 pi m / NTW)), twscale = NTW / N.
+// twiddles of one radix-8 butterfly: W^m1, W^2m1, W^4m1 (loaded ahead of the exchange that precedes the pass)
+struct Tw3 { double2 w1, w2, w4; };
+template <int N>
+__device__ __forceinline__ Tw3 tw_load8(int u, int s, const double2* __restrict__ tw, int twscale) {
+    const int m1 = s * (u / s) * twscale;
+    Tw3 t;
+    t.w1 = __ldg(&tw[m1]); t.w2 = __ldg(&tw[2 * m1]); t.w4 = __ldg(&tw[4 * m1]);
+    return t;
+}
+
 template <int N, int R, bool INV>
 __device__ __forceinline__ void fft_pass(double (&vr)[8], double (&vi)[8], int u, int s,
-                                         const double2* __restrict__ tw, int twscale) {
+                                         const double2* __restrict__ tw, int twscale, const Tw3* pre = nullptr) {
     constexpr int G = 8 / R;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -114,12 +124,29 @@ __device__ __forceinline__ void fft_pass(double (&vr)[8], double (&vi)[8], int u
             const int b = u + g * (N / 8);
             const int p = b / s;
             const int m1 = s * p * twscale;
+            // W^m1, W^2m1, W^4m1 from the table (correctly rounded), the other powers as single products:
+            // 3 table loads per butterfly instead of 7, at most one extra rounding per twiddle
+            double wr[R], wi[R];
+            {
+                const double2 w1 = (R == 8 && pre) ? pre->w1 : __ldg(&tw[m1]);
+                wr[1] = w1.x; wi[1] = INV ? w1.y : -w1.y;
+                if (R > 2) {
+                    const double2 w2 = (R == 8 && pre) ? pre->w2 : __ldg(&tw[2 * m1]);
+                    wr[2] = w2.x; wi[2] = INV ? w2.y : -w2.y;
+                    wr[3] = wr[1] * wr[2] - wi[1] * wi[2]; wi[3] = wr[1] * wi[2] + wi[1] * wr[2];
+                }
+                if (R > 4) {
+                    const double2 w4 = (R == 8 && pre) ? pre->w4 : __ldg(&tw[4 * m1]);
+                    wr[4] = w4.x; wi[4] = INV ? w4.y : -w4.y;
+                    wr[5] = wr[1] * wr[4] - wi[1] * wi[4]; wi[5] = wr[1] * wi[4] + wi[1] * wr[4];
+                    wr[6] = wr[2] * wr[4] - wi[2] * wi[4]; wi[6] = wr[2] * wi[4] + wi[2] * wr[4];
+                    wr[7] = wr[3] * wr[4] - wi[3] * wi[4]; wi[7] = wr[3] * wi[4] + wi[3] * wr[4];
+                }
+            }
 #pragma unroll
             for (int j = 1; j < R; ++j) {
-                const double2 w = __ldg(&tw[m1 * j]);
-                const double wr = w.x, wi = INV ? w.y : -w.y;
-                const double tr = xr[j] * wr - xi[j] * wi;
-                const double ti = xr[j] * wi + xi[j] * wr;
+                const double tr = xr[j] * wr[j] - xi[j] * wi[j];
+                const double ti = xr[j] * wi[j] + xi[j] * wr[j];
                 xr[j] = tr; xi[j] = ti;
             }
         }
@@ -179,11 +206,14 @@ __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int
     static_assert(L > 0, "unsupported FFT length");
     constexpr int N8 = L / 3;            // number of radix-8 passes
     constexpr int TAIL = 1 << (L % 3);   // 1, 2 or 4
+    Tw3 t = tw_load8<N>(u, 1, tw, twscale);
 #pragma unroll
     for (int pass = 0; pass < N8; ++pass) {
-        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale);
+        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale, &t);
         const bool last = (pass == N8 - 1) && (TAIL == 1);
         if (!last) {
+            // twiddles of the next radix-8 pass travel with the exchange (hides their L1/L2 latency)
+            if (pass + 1 < N8 && s * 64 < N) t = tw_load8<N>(u, s * 8, tw, twscale);
             if (pass > 0) __syncthreads();               // WAR: everyone has gathered
             if (active) fft_scatter<N, 8>(vr, vi, u, s, sre, sim, ix);
             __syncthreads();

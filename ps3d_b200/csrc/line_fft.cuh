@@ -24,6 +24,23 @@ enum { PRO_PLAIN = 0, PRO_DIFF = 1, PRO_CROSS = 2 };
 constexpr int LINE_ZC = 16;            // z values per tile row (pz is a multiple of this)
 constexpr int LINE_NF = LINE_ZC / 2;   // complex FFTs per tile
 
+// Row k of a line -> offset (doubles) from the tile base, computed arithmetically (no table loads):
+//  paired == 0: k * stride                         (x lines; physical side of y lines)
+//  paired == 1: spectral side of y lines in the paired ky order ky' = 0, n/2, 1, n-1, 2, n-2, ...;
+//               ky' = d * nyl + kyl is owned by rank d at local row kyl: ((d * dstride) + kyl) * stride
+struct RowMap {
+    long long stride;
+    long long dstride;
+    int paired, n, lognyl;
+};
+__device__ __forceinline__ long long row_off(const RowMap& m, int k) {
+    if (!m.paired) return (long long)k * m.stride;
+    const int h = m.n >> 1;
+    const int kp = (k == 0) ? 0 : (k == h) ? 1 : (k < h) ? 2 * k : 2 * (m.n - k) + 1;
+    const int d = kp >> m.lognyl, kl = kp & ((1 << m.lognyl) - 1);
+    return ((long long)d * m.dstride + kl) * m.stride;
+}
+
 struct LineArgs {
     const double* in0;        // PLAIN/DIFF: the field.  CROSS: a
     const double* in1;        // CROSS: b      (value = a*b - c*d)
@@ -32,8 +49,7 @@ struct LineArgs {
     double add1, add3;        // CROSS: constants added to b and d (f_cor)
     double* out;
     long long in_os, out_os;  // stride between consecutive outer lines (doubles)
-    const long long* in_rowoff;   // [N] offset of row k from the tile base (doubles)
-    const long long* out_rowoff;  // [N]
+    RowMap in_map, out_map;   // offset of row k from the tile base
     int nzc;                  // z-chunks per line (pz / 16)
     const double* kdiff;      // DIFF: wavenumber per k = 0..N/2 (0 at k = 0 and N/2)
     double scale;             // 1/sqrt(N)
@@ -53,7 +69,7 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     double vr[8], vi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const long long off = ibase + __ldg(&a.in_rowoff[u + e * (N / 8)]);
+        const long long off = ibase + row_off(a.in_map, u + e * (N / 8));
         if (PRO == PRO_CROSS) {
             const double2 x0 = ld2(a.in0 + off), x1 = ld2(a.in1 + off);
             const double2 x2 = ld2(a.in2 + off), x3 = ld2(a.in3 + off);
@@ -82,15 +98,15 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
         const int k = u + e * (N / 8);
         if (k == 0) {
             const int i0 = ix(0);
-            st2(a.out + obase + __ldg(&a.out_rowoff[0]), sre[i0] * sc, sim[i0] * sc);
+            st2(a.out + obase + row_off(a.out_map, 0), sre[i0] * sc, sim[i0] * sc);
             const int ih = ix(N / 2);
-            st2(a.out + obase + __ldg(&a.out_rowoff[N / 2]), sre[ih] * sc, sim[ih] * sc);
+            st2(a.out + obase + row_off(a.out_map, N / 2), sre[ih] * sc, sim[ih] * sc);
         } else {
             const int ik = ix(k), im = ix(N - k);
             const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
             // A_k = (C_k + conj C_{N-k})/2, B_k = (C_k - conj C_{N-k})/(2i)
-            st2(a.out + obase + __ldg(&a.out_rowoff[k]), (p + r) * hs, (q + s) * hs);       // Re A, Re B
-            st2(a.out + obase + __ldg(&a.out_rowoff[N - k]), (q - s) * hs, (r - p) * hs);   // Im A, Im B
+            st2(a.out + obase + row_off(a.out_map, k), (p + r) * hs, (q + s) * hs);       // Re A, Re B
+            st2(a.out + obase + row_off(a.out_map, N - k), (q - s) * hs, (r - p) * hs);   // Im A, Im B
         }
     }
 }
@@ -108,16 +124,16 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     for (int e = 0; e < 4; ++e) {
         const int k = u + e * (N / 8);
         if (k == 0) {
-            double2 x0 = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[0]));
-            double2 xh = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[N / 2]));
+            double2 x0 = ld2(a.in0 + ibase + row_off(a.in_map, 0));
+            double2 xh = ld2(a.in0 + ibase + row_off(a.in_map, N / 2));
             if (PRO == PRO_DIFF) { x0.x = x0.y = 0.0; xh.x = xh.y = 0.0; }
             const int i0 = ix(0);
             sre[i0] = x0.x; sim[i0] = x0.y;
             const int ih = ix(N / 2);
             sre[ih] = xh.x; sim[ih] = xh.y;
         } else {
-            const double2 xk = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[k]));
-            const double2 xm = ld2(a.in0 + ibase + __ldg(&a.in_rowoff[N - k]));
+            const double2 xk = ld2(a.in0 + ibase + row_off(a.in_map, k));
+            const double2 xm = ld2(a.in0 + ibase + row_off(a.in_map, N - k));
             double Ar = xk.x, Ai = xm.x, Br = xk.y, Bi = xm.y;
             if (PRO == PRO_DIFF) {
                 // d/dx: X_k -> i kappa X_k  (sta3dfft.f90:325-329)
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     const double sc = a.scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-        st2(a.out + obase + __ldg(&a.out_rowoff[u + e * (N / 8)]), vr[e] * sc, vi[e] * sc);
+        st2(a.out + obase + row_off(a.out_map, u + e * (N / 8)), vr[e] * sc, vi[e] * sc);
 }
 
 template <int N>

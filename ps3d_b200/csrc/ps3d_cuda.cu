@@ -191,13 +191,18 @@ static void run_sweep(Ctx& c, const Sweep& s) {
         n = c.ny; nouter = c.nxl;
         // physical side [xl][y][pz]; spectral side [xl][ky'][pz] (== [kx][kyl][pz] for one rank)
         a.in_os = (long long)c.ny * c.pz; a.out_os = (long long)c.ny * c.pz;
-        a.in_rowoff = s.inv ? c.ro_spec_y.p : c.ro_phys_y.p;
-        a.out_rowoff = s.inv ? c.ro_phys_y.p : c.ro_spec_y.p;
+        int lognyl = 0;
+        while ((1 << lognyl) < c.nyl) ++lognyl;
+        const RowMap phys{(long long)c.pz, 0, 0, n, 0};
+        const RowMap spec{(long long)c.pz, (long long)c.nxl * c.nyl, 1, n, lognyl};
+        a.in_map = s.inv ? spec : phys;
+        a.out_map = s.inv ? phys : spec;
         a.kdiff = c.kyline.p;
     } else {
         n = c.nx; nouter = c.nyl;
         a.in_os = c.pz; a.out_os = c.pz;
-        a.in_rowoff = c.ro_x.p; a.out_rowoff = c.ro_x.p;
+        const RowMap xm{(long long)c.nyl * c.pz, 0, 0, n, 0};
+        a.in_map = xm; a.out_map = xm;
         a.kdiff = c.kxl.p;
     }
     a.scale = 1.0 / std::sqrt((double)n);
