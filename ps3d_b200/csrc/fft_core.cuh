@@ -206,14 +206,22 @@ __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int
     static_assert(L > 0, "unsupported FFT length");
     constexpr int N8 = L / 3;            // number of radix-8 passes
     constexpr int TAIL = 1 << (L % 3);   // 1, 2 or 4
+#ifdef PS3D_TW_PREFETCH
     Tw3 t = tw_load8<N>(u, 1, tw, twscale);
+#endif
 #pragma unroll
     for (int pass = 0; pass < N8; ++pass) {
-        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale, &t);
+#ifdef PS3D_TW_PREFETCH
+        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale, (pass == 0 || s * 8 < N) ? &t : nullptr);
+#else
+        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale);
+#endif
         const bool last = (pass == N8 - 1) && (TAIL == 1);
         if (!last) {
             // twiddles of the next radix-8 pass travel with the exchange (hides their L1/L2 latency)
+#ifdef PS3D_TW_PREFETCH
             if (pass + 1 < N8 && s * 64 < N) t = tw_load8<N>(u, s * 8, tw, twscale);
+#endif
             if (pass > 0) __syncthreads();               // WAR: everyone has gathered
             if (active) fft_scatter<N, 8>(vr, vi, u, s, sre, sim, ix);
             __syncthreads();

@@ -33,10 +33,14 @@ struct RowMap {
     long long dstride;
     int paired, n, lognyl;
 };
+// branch-free (selects only) so that the unrolled global loads of a tile can all be issued back to back;
+// for paired == 0 the host sets lognyl = 30, dstride = 0, i.e. d = 0 and kl = k
 __device__ __forceinline__ long long row_off(const RowMap& m, int k) {
-    if (!m.paired) return (long long)k * m.stride;
     const int h = m.n >> 1;
-    const int kp = (k == 0) ? 0 : (k == h) ? 1 : (k < h) ? 2 * k : 2 * (m.n - k) + 1;
+    int kq = (k < h) ? 2 * k : 2 * (m.n - k) + 1;
+    kq = (k == 0) ? 0 : kq;
+    kq = (k == h) ? 1 : kq;
+    const int kp = m.paired ? kq : k;
     const int d = kp >> m.lognyl, kl = kp & ((1 << m.lognyl) - 1);
     return ((long long)d * m.dstride + kl) * m.stride;
 }
@@ -120,31 +124,38 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     double* sre = sm;
     double* sim = sm + LINE_NF * N;
     const IxIlv<LINE_NF> ix{f};
+    // rows k and N-k (k = 0: rows 0 and N/2); all eight loads are issued before the first use
+    double2 xa[4], xb[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int k = u + e * (N / 8);
-        if (k == 0) {
-            double2 x0 = ld2(a.in0 + ibase + row_off(a.in_map, 0));
-            double2 xh = ld2(a.in0 + ibase + row_off(a.in_map, N / 2));
-            if (PRO == PRO_DIFF) { x0.x = x0.y = 0.0; xh.x = xh.y = 0.0; }
-            const int i0 = ix(0);
-            sre[i0] = x0.x; sim[i0] = x0.y;
-            const int ih = ix(N / 2);
-            sre[ih] = xh.x; sim[ih] = xh.y;
-        } else {
-            const double2 xk = ld2(a.in0 + ibase + row_off(a.in_map, k));
-            const double2 xm = ld2(a.in0 + ibase + row_off(a.in_map, N - k));
-            double Ar = xk.x, Ai = xm.x, Br = xk.y, Bi = xm.y;
-            if (PRO == PRO_DIFF) {
-                // d/dx: X_k -> i kappa X_k  (sta3dfft.f90:325-329)
-                const double kap = __ldg(&a.kdiff[k]);
-                const double ar = -kap * Ai, ai = kap * Ar, br = -kap * Bi, bi = kap * Br;
-                Ar = ar; Ai = ai; Br = br; Bi = bi;
-            }
-            const int ik = ix(k), im = ix(N - k);
-            sre[ik] = Ar - Bi; sim[ik] = Ai + Br;     // C_k     = A + i B
-            sre[im] = Ar + Bi; sim[im] = Br - Ai;     // C_{N-k} = conj(A) + i conj(B)
+        const int kb = (k == 0) ? N / 2 : N - k;
+        xa[e] = ld2(a.in0 + ibase + row_off(a.in_map, k));
+        xb[e] = ld2(a.in0 + ibase + row_off(a.in_map, kb));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int k = u + e * (N / 8);
+        const bool k0 = (k == 0);
+        const int kb = k0 ? N / 2 : N - k;
+        double Ar = xa[e].x, Ai = xb[e].x, Br = xa[e].y, Bi = xb[e].y;
+        if (PRO == PRO_DIFF) {
+            // d/dx: X_k -> i kappa X_k  (sta3dfft.f90:325-329); kappa = 0 at k = 0 and N/2 (:321-335)
+            const double kap = __ldg(&a.kdiff[k]);
+            const double ar = -kap * Ai, ai = kap * Ar, br = -kap * Bi, bi = kap * Br;
+            Ar = ar; Ai = ai; Br = br; Bi = bi;
         }
+        // generic k: C_k = A + i B, C_{N-k} = conj(A) + i conj(B);  k = 0: the two rows are the real DC and
+        // Nyquist terms of both lines, C_0 = a_0 + i b_0, C_{N/2} = a_{N/2} + i b_{N/2}
+        double rk = Ar - Bi, qk = Ai + Br, rm = Ar + Bi, qm = Br - Ai;
+        if (k0) {
+            const bool z = (PRO == PRO_DIFF);
+            rk = z ? 0.0 : xa[e].x; qk = z ? 0.0 : xa[e].y;
+            rm = z ? 0.0 : xb[e].x; qm = z ? 0.0 : xb[e].y;
+        }
+        const int ik = ix(k), im = ix(kb);
+        sre[ik] = rk; sim[ik] = qk;
+        sre[im] = rm; sim[im] = qm;
     }
     __syncthreads();
     double vr[8], vi[8];

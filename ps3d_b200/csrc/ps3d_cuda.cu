@@ -193,7 +193,7 @@ static void run_sweep(Ctx& c, const Sweep& s) {
         a.in_os = (long long)c.ny * c.pz; a.out_os = (long long)c.ny * c.pz;
         int lognyl = 0;
         while ((1 << lognyl) < c.nyl) ++lognyl;
-        const RowMap phys{(long long)c.pz, 0, 0, n, 0};
+        const RowMap phys{(long long)c.pz, 0, 0, n, 30};
         const RowMap spec{(long long)c.pz, (long long)c.nxl * c.nyl, 1, n, lognyl};
         a.in_map = s.inv ? spec : phys;
         a.out_map = s.inv ? phys : spec;
@@ -201,7 +201,7 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     } else {
         n = c.nx; nouter = c.nyl;
         a.in_os = c.pz; a.out_os = c.pz;
-        const RowMap xm{(long long)c.nyl * c.pz, 0, 0, n, 0};
+        const RowMap xm{(long long)c.nyl * c.pz, 0, 0, n, 30};
         a.in_map = xm; a.out_map = xm;
         a.kdiff = c.kxl.p;
     }

@@ -5,9 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ps3d_b200
 from ps3d_b200 import host
 
-lib = ps3d_b200.load()
+from ps3d_b200.lib import PS3DLib, LIB_PATH
+lib = PS3DLib(os.environ.get('PS3D_PROBE_LIB', LIB_PATH))
 for n in [int(v) for v in sys.argv[1:]] or [256, 512]:
-    for stepper in ("cn2", "impl-diff-rk4"):
+    for stepper in ("cn2",):
         s = host.beltrami_solver(lib, n, stepper=stepper)
         for _ in range(2):
             s.advance()
