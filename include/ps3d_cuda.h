@@ -21,6 +21,8 @@
 #ifndef PS3D_CUDA_H
 #define PS3D_CUDA_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -102,6 +104,21 @@ int ps3d_cuda_upload(int field_id, int comp, const double* host);
 /* out[0..2] = kinetic energy, enstrophy (field_diagnostics.f90:85,172), helicity
  * (plotting/nc_reader.py:94-101 trapezoid mean of u.omega); out[3..7] reserved */
 int ps3d_cuda_diagnostics(double out[8]);
+
+/* ---- multi-rank transport ----
+ * Slab decomposition over `nranks` GPUs of one box: physical fields are split in x (rank r owns planes
+ * r*nx/P .. (r+1)*nx/P - 1), spectral fields in ky (rank r owns rows r*ny/P .. of the paired order
+ * ky' = 0, ny/2, 1, ny-1, 2, ny-2, ...), one all-to-all of P equal contiguous blocks per 2-D FFT
+ * (replaces transpose_to_pencil, fft_pencil.f90:283-330, and reverse_x/y, mpi_reverse.f90:332-398).
+ * Default transport: NCCL (nccl_id given to ps3d_cuda_init).  Alternatively the host supplies its own
+ * collectives, e.g. CUDA-aware MPI_Alltoall / MPI_Allreduce on the reference's communicators
+ * (mpi_layout.f90:34-36): `alltoall` gets device pointers (block d of `send` goes to rank d and must land
+ * as block <sender> of `recv`), `allreduce` a host buffer (op 0 = sum, 1 = max); both return 0 on success. */
+typedef int (*ps3d_alltoall_fn)(const void* send, void* recv, size_t bytes_per_rank, void* user);
+typedef int (*ps3d_allreduce_fn)(double* buf, int n, int op, void* user);
+int ps3d_cuda_set_transport(ps3d_alltoall_fn alltoall, ps3d_allreduce_fn allreduce, void* user);
+/* number of all-to-alls issued and bytes this rank sent to other ranks since init */
+int ps3d_cuda_comm_stats(long long* n_alltoall, double* bytes_sent);
 
 /* ---- introspection for benchmarks ---- */
 /* number of kernels this library has launched since init */

@@ -17,6 +17,7 @@
 #include "line_fft.cuh"
 #include "zcol.cuh"
 #include "pointwise.cuh"
+#include "transport.h"
 
 namespace ps3d {
 
@@ -99,12 +100,13 @@ struct Ctx {
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
 
-    DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[6];
+    DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[8];
+    Transport tr;
+    DevBuf<double> redS, redM;            // all-reduce landing buffers (sum / max)
     DevBuf<double> stage;                 // natural-layout staging for the host boundary
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
     DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
     DevBuf<double2> tw;
-    DevBuf<long long> ro_phys_y, ro_spec_y, ro_x;
     DevBuf<int> permy;
     int ntw = 0;
     std::vector<double> h_rkx, h_rky, h_rkz, h_k2l2, h_filt2d;   // host copies ([kx][kyl] local order)
@@ -190,7 +192,8 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     if (s.axis == 1) {
         n = c.ny; nouter = c.nxl;
         // physical side [xl][y][pz]; spectral side [xl][ky'][pz] (== [kx][kyl][pz] for one rank)
-        a.in_os = (long long)c.ny * c.pz; a.out_os = (long long)c.ny * c.pz;
+        const long long pos = (long long)c.ny * c.pz, sos = (long long)c.nyl * c.pz;
+        a.in_os = s.inv ? sos : pos; a.out_os = s.inv ? pos : sos;
         int lognyl = 0;
         while ((1 << lognyl) < c.nyl) ++lognyl;
         const RowMap phys{(long long)c.pz, 0, 0, n, 30};
@@ -210,35 +213,93 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     launch_line(c, n, s.inv, s.pro, a, nouter * a.nzc);
 }
 
-static void require_single_rank(Ctx& c) {
-    if (c.nranks != 1) fail(PS3D_ERR_UNSUPPORTED, "multi-rank slab exchange is not available in this build");
+// ---- slab exchange: P equal contiguous blocks, block d of `send` goes to rank d and lands as block
+// `rank` of its `recv` (replaces the four transpose_to_pencil calls per 2-D FFT of the reference) ----
+static void exchange(Ctx& c, const double* send, double* recv) {
+    Transport& t = c.tr;
+    const size_t nb = (size_t)c.nxl * c.nyl * c.pz;         // doubles per block
+    ++t.n_alltoall;
+    t.bytes_sent += (double)nb * 8.0 * (t.nranks - 1);
+    if (t.a2a_cb) {
+        ps_sync(c.stream);
+        if (t.a2a_cb(send, recv, nb * sizeof(double), t.user) != 0) fail(PS3D_ERR_DEVICE, "all-to-all callback failed");
+        return;
+    }
+#ifndef PS3D_EMU
+    if (t.have_nccl()) {
+        int rc = t.nccl.GroupStart();
+        for (int d = 0; d < t.nranks && rc == 0; ++d) {
+            rc = t.nccl.Send(send + (size_t)d * nb, nb, NcclApi::kFloat64, d, t.comm, (void*)c.stream);
+            if (rc == 0) rc = t.nccl.Recv(recv + (size_t)d * nb, nb, NcclApi::kFloat64, d, t.comm, (void*)c.stream);
+        }
+        const int rc2 = t.nccl.GroupEnd();
+        if (rc != 0 || rc2 != 0) fail(PS3D_ERR_DEVICE, "NCCL all-to-all failed: %s", t.nccl.GetErrorString(rc ? rc : rc2));
+        return;
+    }
+#endif
+    fail(PS3D_ERR_NOT_INITIALISED, "nranks > 1 but neither an NCCL id nor a transport callback was given");
 }
 
-// fftxyp2s on internal layouts: physical [x][y][pz] -> semi-spectral [kx][ky'][pz]
-static void fft2d_fwd(Ctx& c, const double* in, double* out, double* tmp) {
-    require_single_rank(c);
-    Sweep sy{1, false, PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, tmp};
+// small all-reduce of host values: vals[i] <- sum or max over ranks according to bit i of opmask
+static void allreduce_host(Ctx& c, double* vals, int n, unsigned opmask) {
+    Transport& t = c.tr;
+    if (t.nranks == 1) return;
+    double s[64], m[64];
+    for (int i = 0; i < n; ++i) { s[i] = vals[i]; m[i] = vals[i]; }
+    if (t.ar_cb) {
+        if (t.ar_cb(s, n, 0, t.user) != 0 || t.ar_cb(m, n, 1, t.user) != 0) fail(PS3D_ERR_DEVICE, "all-reduce callback failed");
+    } else {
+#ifndef PS3D_EMU
+        if (!t.have_nccl()) fail(PS3D_ERR_NOT_INITIALISED, "no transport for the all-reduce");
+        ps_h2d(c.redS.p, s, n * sizeof(double), c.stream);
+        ps_h2d(c.redM.p, m, n * sizeof(double), c.stream);
+        int rc = t.nccl.AllReduce(c.redS.p, c.redS.p, n, NcclApi::kFloat64, NcclApi::kSum, t.comm, (void*)c.stream);
+        if (rc == 0) rc = t.nccl.AllReduce(c.redM.p, c.redM.p, n, NcclApi::kFloat64, NcclApi::kMax, t.comm, (void*)c.stream);
+        if (rc != 0) fail(PS3D_ERR_DEVICE, "NCCL all-reduce failed: %s", t.nccl.GetErrorString(rc));
+        ps_d2h(s, c.redS.p, n * sizeof(double), c.stream);
+        ps_d2h(m, c.redM.p, n * sizeof(double), c.stream);
+        ps_sync(c.stream);
+#else
+        fail(PS3D_ERR_NOT_INITIALISED, "no transport for the all-reduce");
+#endif
+    }
+    for (int i = 0; i < n; ++i) vals[i] = ((opmask >> i) & 1) ? m[i] : s[i];
+}
+
+// fftxyp2s on internal layouts: physical [xl][y][pz] -> semi-spectral [kx][kyl][pz]
+//   one rank : y sweep -> tmp -> x sweep -> out
+//   P ranks  : y sweep -> tmp ([d][xl][kyl][pz]) -> all-to-all -> tmp2 (= [kx][kyl][pz]) -> x sweep -> out
+static void fft2d_fwd_impl(Ctx& c, const Sweep& sy_in, double* out) {
+    double* t1 = c.W[5].p;
+    Sweep sy = sy_in;
+    sy.out = t1;
     run_sweep(c, sy);
-    Sweep sx{0, false, PRO_PLAIN, {tmp, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
+    const double* xin = t1;
+    if (c.nranks > 1) { exchange(c, t1, c.W[6].p); xin = c.W[6].p; }
+    Sweep sx{0, false, PRO_PLAIN, {xin, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
     run_sweep(c, sx);
+}
+
+static void fft2d_fwd(Ctx& c, const double* in, double* out) {
+    Sweep sy{1, false, PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, nullptr};
+    fft2d_fwd_impl(c, sy, out);
 }
 
 // a*(b+add1) - c*(d+add3) -> forward 2-D FFT
 static void fft2d_fwd_cross(Ctx& c, const double* a, const double* b, double add1, const double* cc, const double* d,
-                            double add3, double* out, double* tmp) {
-    require_single_rank(c);
-    Sweep sy{1, false, PRO_CROSS, {a, b, cc, d}, add1, add3, tmp};
-    run_sweep(c, sy);
-    Sweep sx{0, false, PRO_PLAIN, {tmp, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
-    run_sweep(c, sx);
+                            double add3, double* out) {
+    Sweep sy{1, false, PRO_CROSS, {a, b, cc, d}, add1, add3, nullptr};
+    fft2d_fwd_impl(c, sy, out);
 }
 
-// fftxys2p (optionally of d/dx or d/dy of the input): [kx][ky'][pz] -> [x][y][pz]
-static void fft2d_inv(Ctx& c, const double* in, double* out, double* tmp, bool dx, bool dy) {
-    require_single_rank(c);
-    Sweep sx{0, true, dx ? PRO_DIFF : PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, tmp};
+// fftxys2p (optionally of d/dx or d/dy of the input): [kx][kyl][pz] -> [xl][y][pz]
+static void fft2d_inv(Ctx& c, const double* in, double* out, bool dx, bool dy) {
+    double* t1 = c.W[5].p;
+    Sweep sx{0, true, dx ? PRO_DIFF : PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, t1};
     run_sweep(c, sx);
-    Sweep sy{1, true, dy ? PRO_DIFF : PRO_PLAIN, {tmp, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
+    const double* yin = t1;
+    if (c.nranks > 1) { exchange(c, t1, c.W[6].p); yin = c.W[6].p; }
+    Sweep sy{1, true, dy ? PRO_DIFF : PRO_PLAIN, {yin, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
     run_sweep(c, sy);
 }
 
@@ -295,15 +356,21 @@ static int stream_blocks(size_t n) { return (int)std::min<size_t>((n + 255) / 25
 // ---------------------------------------------------------------------------
 // host boundary: natural Fortran layout <-> internal layouts
 // ---------------------------------------------------------------------------
+// Host layouts: physical fields f(0:nz, 0:ny-1, x-slab of this rank); spectral fields f(0:nz, ky, 0:nx-1) with ky in
+// natural order on one rank, and on P > 1 ranks the rank's slab of the paired order ky' (0, ny/2, 1, ny-1, ...).
 static void to_device(Ctx& c, const double* host, double* dev, bool spectral) {
+    const bool slab = spectral && c.nranks > 1;
+    const int d0 = slab ? c.nx : c.nxl, d1 = slab ? c.nyl : c.ny;
     ps_h2d(c.stage.p, host, c.nnat * sizeof(double), c.stream);
-    PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.stage.p, dev, c.nxl,
-              c.ny, c.nzp, c.pz, spectral ? (const int*)c.permy.p : (const int*)nullptr);
+    PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.stage.p, dev, d0,
+              d1, c.nzp, c.pz, (spectral && !slab) ? (const int*)c.permy.p : (const int*)nullptr);
     ++c.launches;
 }
 static void to_host(Ctx& c, const double* dev, double* host, bool spectral) {
-    PS_LAUNCH((k_repack_out), dim3(stream_blocks(c.nnat)), dim3(256), 0, c.stream, dev, c.stage.p, c.nxl, c.ny, c.nzp,
-              c.pz, spectral ? (const int*)c.permy.p : (const int*)nullptr);
+    const bool slab = spectral && c.nranks > 1;
+    const int d0 = slab ? c.nx : c.nxl, d1 = slab ? c.nyl : c.ny;
+    PS_LAUNCH((k_repack_out), dim3(stream_blocks(c.nnat)), dim3(256), 0, c.stream, dev, c.stage.p, d0, d1, c.nzp,
+              c.pz, (spectral && !slab) ? (const int*)c.permy.p : (const int*)nullptr);
     ++c.launches;
     ps_d2h(host, c.stage.p, c.nnat * sizeof(double), c.stream);
     ps_sync(c.stream);
@@ -312,7 +379,8 @@ static void to_host(Ctx& c, const double* dev, double* host, bool spectral) {
 // ---------------------------------------------------------------------------
 // init
 // ---------------------------------------------------------------------------
-static void do_init(int nx, int ny, int nz, const double* lower, const double* extent, int rank, int nranks) {
+static void do_init(int nx, int ny, int nz, const double* lower, const double* extent, int rank, int nranks,
+                    const void* nccl_id) {
     if (g_ctx) fail(PS3D_ERR_BAD_ARGUMENT, "ps3d_cuda_init called twice without ps3d_cuda_finalise");
     if (!lower || !extent) fail(PS3D_ERR_BAD_ARGUMENT, "null lower/extent");
     if (!pow2(nx) || !pow2(ny) || !pow2(nz) || nx < 8 || ny < 8 || nz < 8 || nx > 1024 || ny > 1024 || nz > 512)
@@ -357,6 +425,18 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     PS_CUDA_TRY(cudaMallocHost((void**)&c->h_red, 64 * sizeof(double)));
 #else
     c->h_red = (double*)calloc(64, sizeof(double));
+#endif
+    c->tr.rank = rank; c->tr.nranks = nranks;
+#ifndef PS3D_EMU
+    if (nranks > 1 && nccl_id) {
+        if (!c->tr.nccl.load()) throw StatusError{PS3D_ERR_DEVICE};
+        NcclApi::UniqueId id;
+        memcpy(id.internal, nccl_id, sizeof id.internal);
+        const int rc = c->tr.nccl.CommInitRank(&c->tr.comm, nranks, id, rank);
+        if (rc != 0) fail(PS3D_ERR_DEVICE, "ncclCommInitRank failed: %s", c->tr.nccl.GetErrorString(rc));
+    }
+#else
+    (void)nccl_id;
 #endif
     ps_stream_t s = c->stream;
 
@@ -407,18 +487,10 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
             kyd[ap] = (a == 0) ? 0.0 : c->h_rky[a];
         }
         c->kyd.upload(kyd, s);
-        std::vector<long long> rp(ny), rs(ny), rx(nx);
-        for (int k = 0; k < ny; ++k) {
-            rp[k] = (long long)k * c->pz;
-            const int kp = perm[k];
-            const int d = kp / c->nyl, kl = kp % c->nyl;
-            rs[k] = ((long long)d * c->nxl * c->nyl + kl) * c->pz;
-        }
-        for (int k = 0; k < nx; ++k) rx[k] = (long long)k * c->nyl * c->pz;
-        c->ro_phys_y.upload(rp, s); c->ro_spec_y.upload(rs, s); c->ro_x.upload(rx, s);
     }
     c->stage.alloc(c->nnat);
-    for (int i = 0; i < 6; ++i) c->W[i].alloc(c->nint);
+    for (int i = 0; i < (nranks > 1 ? 8 : 6); ++i) c->W[i].alloc(c->nint);
+    c->redS.alloc(64); c->redM.alloc(64);
     c->partial.alloc((size_t)RED_BLOCKS * 16);
     c->red.alloc(64);
 }
@@ -532,12 +604,16 @@ static void do_finalise() {
     ps_sync(c->stream);
     DevBuf<double>* groups[] = {c->svor, c->vor, c->vel, c->svel, c->svorts, c->wa, c->wb};
     for (auto* g : groups) for (int i = 0; i < 3; ++i) g[i].release();
-    for (int i = 0; i < 6; ++i) c->W[i].release();
+    for (int i = 0; i < 8; ++i) c->W[i].release();
+    c->redS.release(); c->redM.release();
+#ifndef PS3D_EMU
+    if (c->tr.comm) c->tr.nccl.CommDestroy(c->tr.comm);
+#endif
     DevBuf<double>* singles[] = {&c->stage, &c->kxl, &c->kyline, &c->kxd, &c->kyd, &c->k2l2, &c->k2l2i, &c->zm, &c->zp,
                                  &c->rkz, &c->gamtop, &c->gambot, &c->filt2d, &c->filtz, &c->vhdis, &c->fac1, &c->fac2,
                                  &c->wz, &c->ini_mean, &c->partial, &c->red};
     for (auto* b : singles) b->release();
-    c->tw.release(); c->ro_phys_y.release(); c->ro_spec_y.release(); c->ro_x.release(); c->permy.release();
+    c->tw.release(); c->permy.release();
 #ifndef PS3D_EMU
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -560,8 +636,8 @@ static void do_vor2vel(Ctx& c) {
     a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
     a.dbg = getenv("PS3D_DBG") ? atoi(getenv("PS3D_DBG")) : 0;
     launch_v2v(c, a);
-    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.W[i].p, c.vor[i].p, c.W[3].p, false, false);
-    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.svel[i].p, c.vel[i].p, c.W[3].p, false, false);
+    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.W[i].p, c.vor[i].p, false, false);
+    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.svel[i].p, c.vel[i].p, false, false);
 }
 
 static void do_source(Ctx& c) {
@@ -569,9 +645,9 @@ static void do_source(Ctx& c) {
     const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
     const double *xi = c.vor[0].p, *eta = c.vor[1].p, *zeta = c.vor[2].p;
     // r = u*eta - v*xi ; q = w*xi - u*zeta ; p = v*zeta - w*eta   (inversion.f90:327,336,350)
-    fft2d_fwd_cross(c, u, eta, fc[1], v, xi, fc[0], c.W[0].p, c.W[3].p);
-    fft2d_fwd_cross(c, w, xi, fc[0], u, zeta, fc[2], c.W[1].p, c.W[3].p);
-    fft2d_fwd_cross(c, v, zeta, fc[2], w, eta, fc[1], c.W[2].p, c.W[3].p);
+    fft2d_fwd_cross(c, u, eta, fc[1], v, xi, fc[0], c.W[0].p);
+    fft2d_fwd_cross(c, w, xi, fc[0], u, zeta, fc[2], c.W[1].p);
+    fft2d_fwd_cross(c, v, zeta, fc[2], w, eta, fc[1], c.W[2].p);
     SrcArgs a;
     a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
     a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
@@ -696,6 +772,7 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     ps_sync(c.stream);
     double r1[RQ_N];
     for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
+    allreduce_host(c, r1, RQ_N, RQ_OPMASK);             // advance.f90:299-305, field_diagnostics.f90:418-424
     const double vortmax = std::sqrt(r1[RQ_MAXW2]);
     const double vortrms = std::sqrt(r1[RQ_SUMW2] / (double)c.ncell);
     PS_LAUNCH((k_char_vorticity), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
@@ -704,11 +781,11 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
               (const double*)c.partial.p, RED_BLOCKS, 2, 0u, c.red.p);
     c.launches += 2;
     // velocity strain (advance.f90:199-217): derivative folded into the inverse sweeps
-    fft2d_inv(c, c.svel[0].p, c.W[0].p, c.W[5].p, true, false);    // du/dx
-    fft2d_inv(c, c.svel[0].p, c.W[1].p, c.W[5].p, false, true);    // du/dy
-    fft2d_inv(c, c.svel[2].p, c.W[2].p, c.W[5].p, true, false);    // dw/dx
-    fft2d_inv(c, c.svel[1].p, c.W[3].p, c.W[5].p, false, true);    // dv/dy
-    fft2d_inv(c, c.svel[2].p, c.W[4].p, c.W[5].p, false, true);    // dw/dy
+    fft2d_inv(c, c.svel[0].p, c.W[0].p, true, false);    // du/dx
+    fft2d_inv(c, c.svel[0].p, c.W[1].p, false, true);    // du/dy
+    fft2d_inv(c, c.svel[2].p, c.W[2].p, true, false);    // dw/dx
+    fft2d_inv(c, c.svel[1].p, c.W[3].p, false, true);    // dv/dy
+    fft2d_inv(c, c.svel[2].p, c.W[4].p, false, true);    // dw/dy
     StrainPtrs sp;
     sp.dudx = c.W[0].p; sp.dudy = c.W[1].p; sp.dwdx = c.W[2].p; sp.dvdy = c.W[3].p; sp.dwdy = c.W[4].p;
     for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
@@ -720,8 +797,10 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     c.launches += 2;
     ps_d2h(c.h_red, c.red.p, 5 * sizeof(double), c.stream);
     ps_sync(c.stream);
+    allreduce_host(c, c.h_red, 5, 0x1cu);                // sums: vorl1, vorl2 (field_diagnostics.f90:529-535); max: strain
     const double small = 1.0e-12, cflmax = 0.8;                    // constants.f90:63-65
-    const double vorl1 = small + c.h_red[0], vorl2 = c.h_red[1];
+    // vorl1 starts from `small` on every rank before the reduction (field_diagnostics.f90:509,529-535)
+    const double vorl1 = small * (double)c.nranks + c.h_red[0], vorl2 = c.h_red[1];
     const double vorch = vorl2 / vorl1;
     const double bfmax = 0.0;
     const double ggmax = std::max(2.220446049250313e-16, c.h_red[2]);   // ggmax = epsilon(ggmax) (advance.f90:222)
@@ -760,7 +839,7 @@ static void do_upload_vorticity(Ctx& c, const double* vor_phys) {
     // utils.f90:160-165
     for (int i = 0; i < 3; ++i) {
         to_device(c, vor_phys + (size_t)i * c.nnat, c.vor[i].p, false);
-        fft2d_fwd(c, c.vor[i].p, c.W[0].p, c.W[3].p);
+        fft2d_fwd(c, c.vor[i].p, c.W[0].p);
         launch_zop(c, ZOP_DECOMPOSE, c.W[0].p, c.svor[i].p);
     }
     vor_mean(c, 0);
@@ -791,9 +870,8 @@ const char* ps3d_cuda_last_error(void) { return g_last_error.c_str(); }
 int ps3d_cuda_init(int nx, int ny, int nz, const double lower[3], const double extent[3], int rank, int nranks,
                    const void* nccl_id) {
     PS_API_BEGIN
-    (void)nccl_id;
     const bool fresh = (g_ctx == nullptr);
-    try { do_init(nx, ny, nz, lower, extent, rank, nranks); }
+    try { do_init(nx, ny, nz, lower, extent, rank, nranks, nccl_id); }
     catch (...) { if (fresh && g_ctx) { try { do_finalise(); } catch (...) {} } throw; }
     PS_API_END
 }
@@ -813,7 +891,7 @@ int ps3d_cuda_fftxyp2s(const double* fp, double* fs) {
     PS_API_BEGIN
     Ctx& c = ctx();
     to_device(c, fp, c.W[0].p, false);
-    fft2d_fwd(c, c.W[0].p, c.W[1].p, c.W[2].p);
+    fft2d_fwd(c, c.W[0].p, c.W[1].p);
     to_host(c, c.W[1].p, fs, true);
     PS_API_END
 }
@@ -822,7 +900,7 @@ int ps3d_cuda_fftxys2p(const double* fs, double* fp) {
     PS_API_BEGIN
     Ctx& c = ctx();
     to_device(c, fs, c.W[0].p, true);
-    fft2d_inv(c, c.W[0].p, c.W[1].p, c.W[2].p, false, false);
+    fft2d_inv(c, c.W[0].p, c.W[1].p, false, false);
     to_host(c, c.W[1].p, fp, false);
     PS_API_END
 }
@@ -847,7 +925,7 @@ int ps3d_cuda_field_combine_physical(const double* sf, double* fc) {
     Ctx& c = ready();
     to_device(c, sf, c.W[0].p, true);
     launch_zop(c, ZOP_COMBINE, c.W[0].p, c.W[1].p);
-    fft2d_inv(c, c.W[1].p, c.W[0].p, c.W[2].p, false, false);
+    fft2d_inv(c, c.W[1].p, c.W[0].p, false, false);
     to_host(c, c.W[0].p, fc, false);
     PS_API_END
 }
@@ -856,7 +934,7 @@ int ps3d_cuda_field_decompose_physical(const double* fc, double* sf) {
     PS_API_BEGIN
     Ctx& c = ready();
     to_device(c, fc, c.W[0].p, false);
-    fft2d_fwd(c, c.W[0].p, c.W[1].p, c.W[2].p);
+    fft2d_fwd(c, c.W[0].p, c.W[1].p);
     launch_zop(c, ZOP_DECOMPOSE, c.W[1].p, c.W[0].p);
     to_host(c, c.W[0].p, sf, true);
     PS_API_END
@@ -923,8 +1001,8 @@ int ps3d_cuda_download(int field_id, int comp, double* host) {
     if (field_id == PS3D_F_PRES || field_id == PS3D_F_DELTA) {
         if (field_id == PS3D_F_DELTA) {
             // horizontal_divergence (fields_derived.f90:161-182): delta = u_x + v_y
-            fft2d_inv(c, c.svel[0].p, c.W[0].p, c.W[5].p, true, false);
-            fft2d_inv(c, c.svel[1].p, c.W[1].p, c.W[5].p, false, true);
+            fft2d_inv(c, c.svel[0].p, c.W[0].p, true, false);
+            fft2d_inv(c, c.svel[1].p, c.W[1].p, false, true);
             fail(PS3D_ERR_UNSUPPORTED, "delta download not implemented yet");
         }
         do_pressure(c, c.W[0].p);
@@ -954,11 +1032,27 @@ int ps3d_cuda_diagnostics(double out[8]) {
     field_reduce(c);
     ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
     ps_sync(c.stream);
+    allreduce_host(c, c.h_red, RQ_N, RQ_OPMASK);
     const double ncelli = 1.0 / (double)c.ncell;
     for (int i = 0; i < 8; ++i) out[i] = 0.0;
     out[0] = 0.5 * c.h_red[RQ_SUMU2] * ncelli;      // field_diagnostics.f90:93-103
     out[1] = 0.5 * c.h_red[RQ_SUMW2] * ncelli;      // :177-187
     out[2] = c.h_red[RQ_SUMUW] * ncelli;            // plotting/plot_vor_vel_he_evolution.py:62-65
+    PS_API_END
+}
+
+int ps3d_cuda_set_transport(ps3d_alltoall_fn alltoall, ps3d_allreduce_fn allreduce, void* user) {
+    PS_API_BEGIN
+    Ctx& c = ctx();
+    c.tr.a2a_cb = alltoall; c.tr.ar_cb = allreduce; c.tr.user = user;
+    PS_API_END
+}
+
+int ps3d_cuda_comm_stats(long long* n_alltoall, double* bytes_sent) {
+    PS_API_BEGIN
+    Ctx& c = ctx();
+    if (n_alltoall) *n_alltoall = c.tr.n_alltoall;
+    if (bytes_sent) *bytes_sent = c.tr.bytes_sent;
     PS_API_END
 }
 

@@ -47,7 +47,12 @@ _SIGNATURES = {
     "ps3d_cuda_upload": [C.c_int, C.c_int, _dp],
     "ps3d_cuda_diagnostics": [_dp],
     "ps3d_cuda_time_kernel": [C.c_int, C.c_int, _dp],
+    "ps3d_cuda_set_transport": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "ps3d_cuda_comm_stats": [C.POINTER(C.c_longlong), _dp],
 }
+ALLTOALL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _dp, C.c_int, C.c_int, C.c_void_p)
+SPECTRAL_FIELDS = ("svor", "svel", "svorts")
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ps3d_cuda_last_error", "ps3d_cuda_kernel_launches",
                                                "ps3d_cuda_last_advance_ms"])
 
@@ -83,7 +88,7 @@ class PS3DLib:
         self.dll.ps3d_cuda_last_error.restype = C.c_char_p
         self.dll.ps3d_cuda_kernel_launches.restype = C.c_longlong
         self.dll.ps3d_cuda_last_advance_ms.restype = C.c_double
-        self.shape = None
+        self.shape = self.spec_shape = None
 
     def _call(self, name, *args):
         st = getattr(self.dll, name)(*args)
@@ -95,7 +100,10 @@ class PS3DLib:
         lo = _in(lower)
         ex = _in(extent)
         self._call("ps3d_cuda_init", nx, ny, nz, _ptr(lo), _ptr(ex), rank, nranks, nccl_id)
-        self.shape = (nx // nranks, ny, nz + 1)
+        self.shape = (nx // nranks, ny, nz + 1)                      # physical fields: x-slab
+        # spectral fields: all kx, natural ky on one rank / this rank's slab of the paired ky order otherwise
+        self.spec_shape = (nx, ny // nranks, nz + 1) if nranks > 1 else self.shape
+        self.nranks, self.rank = nranks, rank
 
     def init_inversion(self, filtering="Hou & Li"):
         self._call("ps3d_cuda_init_inversion", FILTER[filtering])
@@ -163,8 +171,28 @@ class PS3DLib:
         self._call("ps3d_cuda_advance", C.byref(tt), t_limit, alpha, PRETYPE[pretype], win, C.byref(dt), _ptr(diag))
         return tt.value, dt.value, dict(zip(DIAG, diag))
 
+    def set_transport(self, alltoall, allreduce):
+        """Plug host collectives (ctypes callbacks built with ALLTOALL_FN / ALLREDUCE_FN); keep them alive."""
+        self._cb = (alltoall, allreduce)
+        self._call("ps3d_cuda_set_transport", C.cast(alltoall, C.c_void_p), C.cast(allreduce, C.c_void_p), None)
+
+    def comm_stats(self):
+        n = C.c_longlong(0)
+        b = C.c_double(0.0)
+        self._call("ps3d_cuda_comm_stats", C.byref(n), C.byref(b))
+        return n.value, b.value
+
+    @staticmethod
+    def paired_ky(ny):
+        """ky of each row of the paired order ky' = 0, ny/2, 1, ny-1, 2, ny-2, ..."""
+        out = np.empty(ny, dtype=np.int64)
+        out[0], out[1] = 0, ny // 2
+        for a in range(1, ny // 2):
+            out[2 * a], out[2 * a + 1] = a, ny - a
+        return out
+
     def download(self, field, comp=0):
-        out = np.empty(self.shape)
+        out = np.empty(self.spec_shape if field in SPECTRAL_FIELDS else self.shape)
         self._call("ps3d_cuda_download", FIELD[field], comp, _ptr(out))
         return out
 

@@ -1,0 +1,22 @@
+"""N > 1 path on CPU: two ranks of the x-slab / ky-slab decomposition run the emulated kernels, exchanging
+through torch.distributed (gloo) via ps3d_cuda_set_transport, and must reproduce the one-rank oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import __graft_entry__ as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_two_rank_slab_decomposition_matches_oracle(stepper):
+    emu = G.build_emu()
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(ROOT, "tests", "multirank_worker.py"), emu, stepper]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("worst") == 2
