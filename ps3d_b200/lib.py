@@ -99,7 +99,11 @@ class PS3DLib:
     def init(self, nx, ny, nz, lower, extent, rank=0, nranks=1, nccl_id=None):
         lo = _in(lower)
         ex = _in(extent)
-        self._call("ps3d_cuda_init", nx, ny, nz, _ptr(lo), _ptr(ex), rank, nranks, nccl_id)
+        idbuf = None
+        if nccl_id is not None:
+            assert len(nccl_id) == 128, "ncclUniqueId is 128 bytes"
+            idbuf = C.cast(C.create_string_buffer(bytes(nccl_id), 128), C.c_void_p)
+        self._call("ps3d_cuda_init", nx, ny, nz, _ptr(lo), _ptr(ex), rank, nranks, idbuf)
         self.shape = (nx // nranks, ny, nz + 1)                      # physical fields: x-slab
         # spectral fields: all kx, natural ky on one rank / this rank's slab of the paired ky order otherwise
         self.spec_shape = (nx, ny // nranks, nz + 1) if nranks > 1 else self.shape

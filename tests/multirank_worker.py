@@ -24,11 +24,22 @@ def main():
     stepper = sys.argv[2]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    nx, ny, nz = 16, 16, 16
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    nx, ny, nz = n, n, n
     lower = np.array([-0.5 * math.pi] * 3)
     extent = np.array([math.pi] * 3)
-    lib = PS3DLib(emu)
-    lib.init(nx, ny, nz, lower, extent, rank, world)
+    use_cuda = (emu == "cuda")
+    if use_cuda:
+        # product library, NCCL transport inside the library (its own communicator)
+        import ps3d_b200
+        os.environ["PS3D_DEVICE"] = os.environ.get("LOCAL_RANK", "0")
+        lib = ps3d_b200.load()
+        box = [torch.cuda.nccl.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        lib.init(nx, ny, nz, lower, extent, rank, world, box[0])
+    else:
+        lib = PS3DLib(emu)
+        lib.init(nx, ny, nz, lower, extent, rank, world)
 
     def alltoall(send, recv, nbytes, user):
         n = nbytes // 8
@@ -55,7 +66,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op else dist.ReduceOp.SUM)
         return 0
 
-    lib.set_transport(ALLTOALL_FN(alltoall), ALLREDUCE_FN(allreduce))
+    if not use_cuda:
+        lib.set_transport(ALLTOALL_FN(alltoall), ALLREDUCE_FN(allreduce))
     lib.init_inversion("Hou & Li")
     ref = O.PS3D(nx, ny, nz, lower, extent)
     vor = np.random.default_rng(5).uniform(-1, 1, (3, nx, ny, nz + 1))

@@ -225,3 +225,20 @@ def test_full_size_properties_256(lib):
         assert rel(lib.field_decompose_semi_spectral(lib.field_combine_semi_spectral(f)), f) < FIELD_TOL
     finally:
         lib.finalise()
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_multi_gpu_slab_matches_oracle(nranks):
+    """P-GPU slab decomposition with NCCL all-to-alls against the one-rank oracle (needs P GPUs)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr",
+           "127.0.0.1", "--master-port", "29621", os.path.join(root, "tests", "multirank_worker.py"), "cuda", "cn2", "64"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("worst") == nranks
