@@ -100,8 +100,12 @@ struct Ctx {
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
 
-    DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[8];
+    DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[9];
     Transport tr;
+    ps_stream_t comm_stream = 0;          // NCCL all-to-alls run here, overlapped with the sweeps of other fields
+#ifndef PS3D_EMU
+    cudaEvent_t ev_first[8] = {}, ev_a2a[8] = {}, ev_second[8] = {};
+#endif
     DevBuf<double> redS, redM;            // all-reduce landing buffers (sum / max)
     DevBuf<double> stage;                 // natural-layout staging for the host boundary
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
@@ -215,13 +219,13 @@ static void run_sweep(Ctx& c, const Sweep& s) {
 
 // ---- slab exchange: P equal contiguous blocks, block d of `send` goes to rank d and lands as block
 // `rank` of its `recv` (replaces the four transpose_to_pencil calls per 2-D FFT of the reference) ----
-static void exchange(Ctx& c, const double* send, double* recv) {
+static void exchange(Ctx& c, const double* send, double* recv, ps_stream_t stream) {
     Transport& t = c.tr;
     const size_t nb = (size_t)c.nxl * c.nyl * c.pz;         // doubles per block
     ++t.n_alltoall;
     t.bytes_sent += (double)nb * 8.0 * (t.nranks - 1);
     if (t.a2a_cb) {
-        ps_sync(c.stream);
+        ps_sync(stream);
         if (t.a2a_cb(send, recv, nb * sizeof(double), t.user) != 0) fail(PS3D_ERR_DEVICE, "all-to-all callback failed");
         return;
     }
@@ -229,8 +233,8 @@ static void exchange(Ctx& c, const double* send, double* recv) {
     if (t.have_nccl()) {
         int rc = t.nccl.GroupStart();
         for (int d = 0; d < t.nranks && rc == 0; ++d) {
-            rc = t.nccl.Send(send + (size_t)d * nb, nb, NcclApi::kFloat64, d, t.comm, (void*)c.stream);
-            if (rc == 0) rc = t.nccl.Recv(recv + (size_t)d * nb, nb, NcclApi::kFloat64, d, t.comm, (void*)c.stream);
+            rc = t.nccl.Send(send + (size_t)d * nb, nb, NcclApi::kFloat64, d, t.comm, (void*)stream);
+            if (rc == 0) rc = t.nccl.Recv(recv + (size_t)d * nb, nb, NcclApi::kFloat64, d, t.comm, (void*)stream);
         }
         const int rc2 = t.nccl.GroupEnd();
         if (rc != 0 || rc2 != 0) fail(PS3D_ERR_DEVICE, "NCCL all-to-all failed: %s", t.nccl.GetErrorString(rc ? rc : rc2));
@@ -266,41 +270,76 @@ static void allreduce_host(Ctx& c, double* vals, int n, unsigned opmask) {
     for (int i = 0; i < n; ++i) vals[i] = ((opmask >> i) & 1) ? m[i] : s[i];
 }
 
+// A batch of 2-D FFTs as a two-sweep pipeline with the slab exchange in between:
+//   one rank : first sweep -> tmp -> second sweep
+//   P ranks  : first sweep(i) -> t1 ([d][xl][kyl][pz] blocks) -> all-to-all(i) on the comm stream -> t2 -> second
+//              sweep(i); the exchange of field i overlaps the first sweep of field i+1 and the second sweep of
+//              field i-1 (two buffer pairs, CUDA events between the two streams).
+// forward (fftxyp2s): first = y sweep, second = x sweep; inverse (fftxys2p): first = x, second = y.
+static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
+    if (c.nranks == 1) {
+        for (int i = 0; i < n; ++i) {
+            first[i].out = c.W[5].p;
+            run_sweep(c, first[i]);
+            second[i].in[0] = c.W[5].p;
+            run_sweep(c, second[i]);
+        }
+        return;
+    }
+    double* t1[2] = {c.W[5].p, c.W[7].p};
+    double* t2[2] = {c.W[6].p, c.W[8].p};
+#ifndef PS3D_EMU
+    const bool overlap = c.tr.have_nccl() && !c.tr.a2a_cb;
+#else
+    const bool overlap = false;
+#endif
+    if (!overlap) {
+        for (int i = 0; i < n; ++i) {
+            first[i].out = t1[0];
+            run_sweep(c, first[i]);
+            exchange(c, t1[0], t2[0], c.stream);
+            second[i].in[0] = t2[0];
+            run_sweep(c, second[i]);
+        }
+        return;
+    }
+#ifndef PS3D_EMU
+    if (n > 8) fail(PS3D_ERR_BAD_ARGUMENT, "fft2d_batch: at most 8 fields");
+    for (int i = 0; i <= n; ++i) {
+        if (i < n) {
+            first[i].out = t1[i & 1];
+            run_sweep(c, first[i]);
+            PS_CUDA_TRY(cudaEventRecord(c.ev_first[i], c.stream));
+            PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_first[i], 0));
+            if (i >= 2) PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_second[i - 2], 0));   // t2[i&1] free again
+            exchange(c, t1[i & 1], t2[i & 1], c.comm_stream);
+            PS_CUDA_TRY(cudaEventRecord(c.ev_a2a[i], c.comm_stream));
+        }
+        if (i >= 1) {
+            const int j = i - 1;
+            PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_a2a[j], 0));
+            second[j].in[0] = t2[j & 1];
+            run_sweep(c, second[j]);
+            PS_CUDA_TRY(cudaEventRecord(c.ev_second[j], c.stream));
+        }
+    }
+#endif
+}
+
+static Sweep sweep_plain(int axis, bool inv, bool diff, const double* in, double* out) {
+    return Sweep{axis, inv, diff ? PRO_DIFF : PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
+}
+
 // fftxyp2s on internal layouts: physical [xl][y][pz] -> semi-spectral [kx][kyl][pz]
-//   one rank : y sweep -> tmp -> x sweep -> out
-//   P ranks  : y sweep -> tmp ([d][xl][kyl][pz]) -> all-to-all -> tmp2 (= [kx][kyl][pz]) -> x sweep -> out
-static void fft2d_fwd_impl(Ctx& c, const Sweep& sy_in, double* out) {
-    double* t1 = c.W[5].p;
-    Sweep sy = sy_in;
-    sy.out = t1;
-    run_sweep(c, sy);
-    const double* xin = t1;
-    if (c.nranks > 1) { exchange(c, t1, c.W[6].p); xin = c.W[6].p; }
-    Sweep sx{0, false, PRO_PLAIN, {xin, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
-    run_sweep(c, sx);
-}
-
 static void fft2d_fwd(Ctx& c, const double* in, double* out) {
-    Sweep sy{1, false, PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, nullptr};
-    fft2d_fwd_impl(c, sy, out);
-}
-
-// a*(b+add1) - c*(d+add3) -> forward 2-D FFT
-static void fft2d_fwd_cross(Ctx& c, const double* a, const double* b, double add1, const double* cc, const double* d,
-                            double add3, double* out) {
-    Sweep sy{1, false, PRO_CROSS, {a, b, cc, d}, add1, add3, nullptr};
-    fft2d_fwd_impl(c, sy, out);
+    Sweep a = sweep_plain(1, false, false, in, nullptr), b = sweep_plain(0, false, false, nullptr, out);
+    fft2d_batch(c, 1, &a, &b);
 }
 
 // fftxys2p (optionally of d/dx or d/dy of the input): [kx][kyl][pz] -> [xl][y][pz]
 static void fft2d_inv(Ctx& c, const double* in, double* out, bool dx, bool dy) {
-    double* t1 = c.W[5].p;
-    Sweep sx{0, true, dx ? PRO_DIFF : PRO_PLAIN, {in, nullptr, nullptr, nullptr}, 0.0, 0.0, t1};
-    run_sweep(c, sx);
-    const double* yin = t1;
-    if (c.nranks > 1) { exchange(c, t1, c.W[6].p); yin = c.W[6].p; }
-    Sweep sy{1, true, dy ? PRO_DIFF : PRO_PLAIN, {yin, nullptr, nullptr, nullptr}, 0.0, 0.0, out};
-    run_sweep(c, sy);
+    Sweep a = sweep_plain(0, true, dx, in, nullptr), b = sweep_plain(1, true, dy, nullptr, out);
+    fft2d_batch(c, 1, &a, &b);
 }
 
 template <int NZ>
@@ -428,6 +467,14 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
 #endif
     c->tr.rank = rank; c->tr.nranks = nranks;
 #ifndef PS3D_EMU
+    if (nranks > 1) {
+        PS_CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) {
+            PS_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_first[i], cudaEventDisableTiming));
+            PS_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_a2a[i], cudaEventDisableTiming));
+            PS_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_second[i], cudaEventDisableTiming));
+        }
+    }
     if (nranks > 1 && nccl_id) {
         if (!c->tr.nccl.load()) throw StatusError{PS3D_ERR_DEVICE};
         NcclApi::UniqueId id;
@@ -489,7 +536,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
         c->kyd.upload(kyd, s);
     }
     c->stage.alloc(c->nnat);
-    for (int i = 0; i < (nranks > 1 ? 8 : 6); ++i) c->W[i].alloc(c->nint);
+    for (int i = 0; i < (nranks > 1 ? 9 : 6); ++i) c->W[i].alloc(c->nint);
     c->redS.alloc(64); c->redM.alloc(64);
     c->partial.alloc((size_t)RED_BLOCKS * 16);
     c->red.alloc(64);
@@ -604,7 +651,7 @@ static void do_finalise() {
     ps_sync(c->stream);
     DevBuf<double>* groups[] = {c->svor, c->vor, c->vel, c->svel, c->svorts, c->wa, c->wb};
     for (auto* g : groups) for (int i = 0; i < 3; ++i) g[i].release();
-    for (int i = 0; i < 8; ++i) c->W[i].release();
+    for (int i = 0; i < 9; ++i) c->W[i].release();
     c->redS.release(); c->redM.release();
 #ifndef PS3D_EMU
     if (c->tr.comm) c->tr.nccl.CommDestroy(c->tr.comm);
@@ -618,6 +665,12 @@ static void do_finalise() {
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 8; ++i) {
+        if (c->ev_first[i]) cudaEventDestroy(c->ev_first[i]);
+        if (c->ev_a2a[i]) cudaEventDestroy(c->ev_a2a[i]);
+        if (c->ev_second[i]) cudaEventDestroy(c->ev_second[i]);
+    }
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
 #else
     free(c->h_red);
@@ -636,8 +689,12 @@ static void do_vor2vel(Ctx& c) {
     a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
     a.dbg = getenv("PS3D_DBG") ? atoi(getenv("PS3D_DBG")) : 0;
     launch_v2v(c, a);
-    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.W[i].p, c.vor[i].p, false, false);
-    for (int i = 0; i < 3; ++i) fft2d_inv(c, c.svel[i].p, c.vel[i].p, false, false);
+    Sweep f[6], g[6];
+    for (int i = 0; i < 3; ++i) {
+        f[i] = sweep_plain(0, true, false, c.W[i].p, nullptr);        g[i] = sweep_plain(1, true, false, nullptr, c.vor[i].p);
+        f[3 + i] = sweep_plain(0, true, false, c.svel[i].p, nullptr); g[3 + i] = sweep_plain(1, true, false, nullptr, c.vel[i].p);
+    }
+    fft2d_batch(c, 6, f, g);
 }
 
 static void do_source(Ctx& c) {
@@ -645,9 +702,12 @@ static void do_source(Ctx& c) {
     const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
     const double *xi = c.vor[0].p, *eta = c.vor[1].p, *zeta = c.vor[2].p;
     // r = u*eta - v*xi ; q = w*xi - u*zeta ; p = v*zeta - w*eta   (inversion.f90:327,336,350)
-    fft2d_fwd_cross(c, u, eta, fc[1], v, xi, fc[0], c.W[0].p);
-    fft2d_fwd_cross(c, w, xi, fc[0], u, zeta, fc[2], c.W[1].p);
-    fft2d_fwd_cross(c, v, zeta, fc[2], w, eta, fc[1], c.W[2].p);
+    Sweep f[3] = {Sweep{1, false, PRO_CROSS, {u, eta, v, xi}, fc[1], fc[0], nullptr},
+                  Sweep{1, false, PRO_CROSS, {w, xi, u, zeta}, fc[0], fc[2], nullptr},
+                  Sweep{1, false, PRO_CROSS, {v, zeta, w, eta}, fc[2], fc[1], nullptr}};
+    Sweep g[3];
+    for (int i = 0; i < 3; ++i) g[i] = sweep_plain(0, false, false, nullptr, c.W[i].p);
+    fft2d_batch(c, 3, f, g);
     SrcArgs a;
     a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
     a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
@@ -781,11 +841,16 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
               (const double*)c.partial.p, RED_BLOCKS, 2, 0u, c.red.p);
     c.launches += 2;
     // velocity strain (advance.f90:199-217): derivative folded into the inverse sweeps
-    fft2d_inv(c, c.svel[0].p, c.W[0].p, true, false);    // du/dx
-    fft2d_inv(c, c.svel[0].p, c.W[1].p, false, true);    // du/dy
-    fft2d_inv(c, c.svel[2].p, c.W[2].p, true, false);    // dw/dx
-    fft2d_inv(c, c.svel[1].p, c.W[3].p, false, true);    // dv/dy
-    fft2d_inv(c, c.svel[2].p, c.W[4].p, false, true);    // dw/dy
+    {
+        const int comp[5] = {0, 0, 2, 1, 2};                        // du/dx, du/dy, dw/dx, dv/dy, dw/dy
+        const bool ddx_[5] = {true, false, true, false, false};
+        Sweep f[5], g[5];
+        for (int i = 0; i < 5; ++i) {
+            f[i] = sweep_plain(0, true, ddx_[i], c.svel[comp[i]].p, nullptr);
+            g[i] = sweep_plain(1, true, !ddx_[i], nullptr, c.W[i].p);
+        }
+        fft2d_batch(c, 5, f, g);
+    }
     StrainPtrs sp;
     sp.dudx = c.W[0].p; sp.dudy = c.W[1].p; sp.dwdx = c.W[2].p; sp.dvdy = c.W[3].p; sp.dwdy = c.W[4].p;
     for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
