@@ -1,0 +1,76 @@
+"""Committed golden vectors (tests/golden, made by tests/golden/make_golden.py from the oracle): the oracle must
+still reproduce them (CPU), and the CUDA path must match them (GPU)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ps3d_oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COLS = ["t", "dt", "vortmax", "vortrms", "vorch", "ggmax", "umax", "vmax", "wmax", "usggmax", "lsggmax"]
+
+
+def test_oracle_reproduces_golden_operators():
+    g = np.load(os.path.join(G, "operators_16x32x8.npz"))
+    s = O.PS3D(16, 32, 8, g["lower"], g["extent"])
+    f = g["f"]
+    for name, fn in (("fftxyp2s", s.fftxyp2s), ("fftsine", s.fftsine), ("fftcosine", s.fftcosine), ("diffx", s.diffx),
+                     ("diffy", s.diffy), ("diffz", s.central_diffz), ("combine", s.field_combine_semi_spectral),
+                     ("decompose", s.field_decompose_semi_spectral)):
+        assert np.max(np.abs(fn(f) - g[name])) < 1e-13, name
+
+
+def test_oracle_reproduces_golden_trajectory_prefix():
+    g = np.load(os.path.join(G, "beltrami32_cn2_100steps.npz"))
+    s = O.beltrami_setup(32)
+    t = 0.0
+    for i in range(5):
+        t, dt = s.advance(t, 100.0, "cn2", literal=True)
+        assert t == pytest.approx(g["series"][i, 0], rel=1e-12) and dt == pytest.approx(g["series"][i, 1], rel=1e-12)
+        assert s.diag["vorch"] == pytest.approx(g["series"][i, 4], rel=1e-11)
+
+
+@pytest.mark.gpu
+def test_cuda_operators_match_golden():
+    import ps3d_b200
+    lib = ps3d_b200.load()
+    g = np.load(os.path.join(G, "operators_16x32x8.npz"))
+    lib.init(16, 32, 8, g["lower"], g["extent"])
+    lib.init_inversion("Hou & Li")
+    try:
+        f = g["f"]
+        for name, fn in (("fftxyp2s", lib.fftxyp2s), ("fftsine", lib.fftsine), ("fftcosine", lib.fftcosine),
+                         ("diffx", lib.diffx), ("diffy", lib.diffy), ("diffz", lib.central_diffz),
+                         ("combine", lib.field_combine_semi_spectral), ("decompose", lib.field_decompose_semi_spectral)):
+            ref = g[name]
+            assert np.max(np.abs(fn(f) - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 1e-300), name
+    finally:
+        lib.finalise()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stepper,tag", [("cn2", "cn2"), ("impl-diff-rk4", "rk4")])
+def test_cuda_trajectory_matches_golden(stepper, tag):
+    """100 steps of Beltrami 32^3: dt and adapt diagnostics every step, KE / enstrophy / helicity at the end to 1e-10."""
+    import ps3d_b200
+    from ps3d_b200 import host
+    lib = ps3d_b200.load()
+    g = np.load(os.path.join(G, f"beltrami32_{tag}_100steps.npz"))
+    s = host.beltrami_solver(lib, 32, stepper=stepper)
+    try:
+        for i in range(100):
+            dt, diag = s.advance()
+            row = dict(zip(COLS, g["series"][i]))
+            assert s.t == pytest.approx(row["t"], rel=1e-11) and dt == pytest.approx(row["dt"], rel=1e-11), i
+            for k in COLS[2:]:
+                assert diag[k] == pytest.approx(row[k], rel=1e-10), (i, k)
+        lib.vor2vel()
+        d = lib.diagnostics()
+        for v, r in zip((d["ke"], d["en"], d["helicity"]), g["final"]):
+            assert v == pytest.approx(r, rel=1e-10)
+        svor = lib.download3("svor")[:, ::4, ::4, ::4]
+        assert np.max(np.abs(svor - g["svor_sample"])) < 1e-11 * np.max(np.abs(g["svor_sample"]))
+    finally:
+        s.close()
