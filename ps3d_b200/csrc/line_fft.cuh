@@ -24,26 +24,31 @@ enum { PRO_PLAIN = 0, PRO_DIFF = 1, PRO_CROSS = 2 };
 constexpr int LINE_ZC = 16;            // z values per tile row (pz is a multiple of this)
 constexpr int LINE_NF = LINE_ZC / 2;   // complex FFTs per tile
 
-// Row k of a line -> offset (doubles) from the tile base, computed arithmetically (no table loads):
-//  paired == 0: k * stride                         (x lines; physical side of y lines)
-//  paired == 1: spectral side of y lines in the paired ky order ky' = 0, n/2, 1, n-1, 2, n-2, ...;
-//               ky' = d * nyl + kyl is owned by rank d at local row kyl: ((d * dstride) + kyl) * stride
+// Row k of a line -> (destination block d, offset in doubles from the tile base), computed arithmetically
+// and branch-free so that the unrolled global accesses of a tile can all be issued back to back.
+//   kp = k, or for paired == 1 the position of ky = k in the paired order ky' = 0, n/2, 1, n-1, 2, n-2, ...
+//   d  = kp >> logblk (owner rank of the row), kl = kp & (2^logblk - 1) (row inside the owner's slab)
+//   offset = (self < 0 ? d : self) * nb + kl * stride
+// One rank, or reading/writing a local buffer laid out as P blocks: self = -1 and the block index is the
+// owner d (for a plain row map logblk = 30, so d = 0 and kl = k).  Peer-memory scatter (the sweep stores
+// straight into rank d's receive buffer, see LineArgs::outp): self = this rank, the block it fills there.
 struct RowMap {
     long long stride;
-    long long dstride;
-    int paired, n, lognyl;
+    long long nb;          // doubles per block (nxl * nyl * pz)
+    int paired, n, logblk, self;
 };
-// branch-free (selects only) so that the unrolled global loads of a tile can all be issued back to back;
-// for paired == 0 the host sets lognyl = 30, dstride = 0, i.e. d = 0 and kl = k
-__device__ __forceinline__ long long row_off(const RowMap& m, int k) {
+__device__ __forceinline__ long long row_off(const RowMap& m, int k, int& d) {
     const int h = m.n >> 1;
     int kq = (k < h) ? 2 * k : 2 * (m.n - k) + 1;
     kq = (k == 0) ? 0 : kq;
     kq = (k == h) ? 1 : kq;
     const int kp = m.paired ? kq : k;
-    const int d = kp >> m.lognyl, kl = kp & ((1 << m.lognyl) - 1);
-    return ((long long)d * m.dstride + kl) * m.stride;
+    d = kp >> m.logblk;
+    const int kl = kp & ((1 << m.logblk) - 1);
+    const int blk = (m.self < 0) ? d : m.self;
+    return (long long)blk * m.nb + (long long)kl * m.stride;
 }
+__device__ __forceinline__ long long row_off(const RowMap& m, int k) { int d; return row_off(m, k, d); }
 
 struct LineArgs {
     const double* in0;        // PLAIN/DIFF: the field.  CROSS: a
@@ -52,6 +57,7 @@ struct LineArgs {
     const double* in3;        // CROSS: d
     double add1, add3;        // CROSS: constants added to b and d (f_cor)
     double* out;
+    double* outp[8];          // peer-memory scatter: base of rank d's receive buffer (all = out otherwise)
     long long in_os, out_os;  // stride between consecutive outer lines (doubles)
     RowMap in_map, out_map;   // offset of row k from the tile base
     int nzc;                  // z-chunks per line (pz / 16)
@@ -61,8 +67,15 @@ struct LineArgs {
     int twscale;
 };
 
+__device__ __forceinline__ double* row_dst(const struct LineArgs& a, int k);
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+
+__device__ __forceinline__ double* row_dst(const LineArgs& a, int k) {
+    int d;
+    const long long off = row_off(a.out_map, k, d);
+    return a.outp[d & 7] + off;
+}
 
 template <int N, int PRO>
 __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_fwd(LineArgs a) {
@@ -102,15 +115,15 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
         const int k = u + e * (N / 8);
         if (k == 0) {
             const int i0 = ix(0);
-            st2(a.out + obase + row_off(a.out_map, 0), sre[i0] * sc, sim[i0] * sc);
+            st2(row_dst(a, 0) + obase, sre[i0] * sc, sim[i0] * sc);
             const int ih = ix(N / 2);
-            st2(a.out + obase + row_off(a.out_map, N / 2), sre[ih] * sc, sim[ih] * sc);
+            st2(row_dst(a, N / 2) + obase, sre[ih] * sc, sim[ih] * sc);
         } else {
             const int ik = ix(k), im = ix(N - k);
             const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
             // A_k = (C_k + conj C_{N-k})/2, B_k = (C_k - conj C_{N-k})/(2i)
-            st2(a.out + obase + row_off(a.out_map, k), (p + r) * hs, (q + s) * hs);       // Re A, Re B
-            st2(a.out + obase + row_off(a.out_map, N - k), (q - s) * hs, (r - p) * hs);   // Im A, Im B
+            st2(row_dst(a, k) + obase, (p + r) * hs, (q + s) * hs);       // Re A, Re B
+            st2(row_dst(a, N - k) + obase, (q - s) * hs, (r - p) * hs);   // Im A, Im B
         }
     }
 }
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     const double sc = a.scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-        st2(a.out + obase + row_off(a.out_map, u + e * (N / 8)), vr[e] * sc, vi[e] * sc);
+        st2(row_dst(a, u + e * (N / 8)) + obase, vr[e] * sc, vi[e] * sc);
 }
 
 template <int N>

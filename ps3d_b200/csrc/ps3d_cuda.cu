@@ -183,7 +183,8 @@ static void launch_line(Ctx& c, int n, bool inv, int pro, const LineArgs& a, int
 }
 
 // one x or y sweep.  axis: 0 = x, 1 = y.
-struct Sweep { int axis; bool inv; int pro; const double* in[4]; double add1, add3; double* out; };
+struct Sweep { int axis; bool inv; int pro; const double* in[4]; double add1, add3; double* out;
+               int scatter = -1; };   // >= 0: store straight into the peers' receive buffer `scatter` (peer memory)
 
 static void run_sweep(Ctx& c, const Sweep& s) {
     LineArgs a;
@@ -193,23 +194,29 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.nzc = c.pz / LINE_ZC;
     a.tw = c.tw.p;
     int n, nouter;
+    int lognyl = 0, lognxl = 0;
+    while ((1 << lognyl) < c.nyl) ++lognyl;
+    while ((1 << lognxl) < c.nxl) ++lognxl;
+    const long long nb = (long long)c.nxl * c.nyl * c.pz;
+    const int self = (s.scatter >= 0) ? c.rank : -1;
+    for (int d = 0; d < 8; ++d) a.outp[d] = (s.scatter >= 0 && d < c.nranks) ? c.tr.peer_t2[s.scatter][d] : s.out;
     if (s.axis == 1) {
         n = c.ny; nouter = c.nxl;
-        // physical side [xl][y][pz]; spectral side [xl][ky'][pz] (== [kx][kyl][pz] for one rank)
+        // physical side [xl][y][pz]; spectral side: P blocks [d][xl][kyl][pz] (== [kx][kyl][pz] after the exchange)
         const long long pos = (long long)c.ny * c.pz, sos = (long long)c.nyl * c.pz;
         a.in_os = s.inv ? sos : pos; a.out_os = s.inv ? pos : sos;
-        int lognyl = 0;
-        while ((1 << lognyl) < c.nyl) ++lognyl;
-        const RowMap phys{(long long)c.pz, 0, 0, n, 30};
-        const RowMap spec{(long long)c.pz, (long long)c.nxl * c.nyl, 1, n, lognyl};
-        a.in_map = s.inv ? spec : phys;
-        a.out_map = s.inv ? phys : spec;
+        const RowMap phys{(long long)c.pz, 0, 0, n, 30, -1};
+        const RowMap spec_in{(long long)c.pz, nb, 1, n, lognyl, -1};
+        const RowMap spec_out{(long long)c.pz, nb, 1, n, lognyl, self};
+        a.in_map = s.inv ? spec_in : phys;
+        a.out_map = s.inv ? phys : spec_out;
         a.kdiff = c.kyline.p;
     } else {
         n = c.nx; nouter = c.nyl;
         a.in_os = c.pz; a.out_os = c.pz;
-        const RowMap xm{(long long)c.nyl * c.pz, 0, 0, n, 30};
-        a.in_map = xm; a.out_map = xm;
+        const RowMap xin{(long long)c.nyl * c.pz, 0, 0, n, 30, -1};
+        const RowMap xout{(long long)c.nyl * c.pz, nb, 0, n, lognxl, self};      // block d = x / nxl
+        a.in_map = xin; a.out_map = xout;
         a.kdiff = c.kxl.p;
     }
     a.scale = 1.0 / std::sqrt((double)n);
@@ -270,6 +277,50 @@ static void allreduce_host(Ctx& c, double* vals, int n, unsigned opmask) {
     for (int i = 0; i < n; ++i) vals[i] = ((opmask >> i) & 1) ? m[i] : s[i];
 }
 
+#ifndef PS3D_EMU
+// all ranks' preceding work on the compute stream is complete (and its peer stores visible) before any rank continues
+static void cross_rank_barrier(Ctx& c) {
+    const int rc = c.tr.nccl.AllReduce(c.redM.p + 32, c.redM.p + 32, 1, NcclApi::kFloat64, NcclApi::kSum, c.tr.comm, (void*)c.stream);
+    if (rc != 0) fail(PS3D_ERR_DEVICE, "NCCL barrier failed: %s", c.tr.nccl.GetErrorString(rc));
+}
+
+// exchange CUDA IPC handles of the two receive buffers and map every peer's (NVSwitch: any-to-any peer access)
+static void setup_p2p(Ctx& c) {
+    Transport& t = c.tr;
+    if (!t.have_nccl() || getenv("PS3D_NO_P2P")) return;
+    const int P = t.nranks;
+    cudaIpcMemHandle_t mine[2];
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&mine[0], c.W[6].p) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], c.W[8].p) != cudaSuccess) ok = 0;
+    (void)cudaGetLastError();
+    const size_t hb = sizeof(mine);
+    DevBuf<unsigned char> all;
+    all.alloc(hb * P);
+    std::vector<unsigned char> host(hb * P, 0);
+    ps_h2d(all.p + hb * t.rank, mine, hb, c.stream);
+    int rc = t.nccl.AllGather(all.p + hb * t.rank, all.p, hb, NcclApi::kUint8, t.comm, (void*)c.stream);
+    if (rc != 0) fail(PS3D_ERR_DEVICE, "NCCL all-gather of IPC handles failed: %s", t.nccl.GetErrorString(rc));
+    ps_d2h(host.data(), all.p, hb * P, c.stream);
+    ps_sync(c.stream);
+    for (int p = 0; p < P && ok; ++p) {
+        for (int b = 0; b < 2; ++b) {
+            if (p == t.rank) { t.peer_t2[b][p] = (b ? c.W[8].p : c.W[6].p); continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, host.data() + hb * p + sizeof(h) * b, sizeof(h));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); break; }
+            t.ipc_opened[b][p] = ptr;
+            t.peer_t2[b][p] = (double*)ptr;
+        }
+    }
+    // every rank must take the same path
+    double flag = ok ? 0.0 : 1.0;
+    allreduce_host(c, &flag, 1, 1u);
+    t.p2p = (flag == 0.0);
+    all.release();
+}
+#endif
+
 // A batch of 2-D FFTs as a two-sweep pipeline with the slab exchange in between:
 //   one rank : first sweep -> tmp -> second sweep
 //   P ranks  : first sweep(i) -> t1 ([d][xl][kyl][pz] blocks) -> all-to-all(i) on the comm stream -> t2 -> second
@@ -288,6 +339,26 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
     }
     double* t1[2] = {c.W[5].p, c.W[7].p};
     double* t2[2] = {c.W[6].p, c.W[8].p};
+#ifndef PS3D_EMU
+    if (c.tr.p2p) {
+        // fused sweep + exchange: the first sweep of field i stores every row straight into the owner's
+        // receive buffer over NVLink (peer memory), a cross-rank barrier, then the second sweep.  Two
+        // receive buffers; the barrier of field i+1 orders the reuse of buffer i&1 (peers enter it only
+        // after their second sweep of field i), the barrier at batch start orders reuse across batches.
+        cross_rank_barrier(c);
+        for (int i = 0; i < n; ++i) {
+            first[i].out = t2[i & 1];
+            first[i].scatter = i & 1;
+            run_sweep(c, first[i]);
+            ++c.tr.n_alltoall;
+            c.tr.bytes_sent += (double)c.nxl * c.nyl * c.pz * 8.0 * (c.nranks - 1);
+            cross_rank_barrier(c);
+            second[i].in[0] = t2[i & 1];
+            run_sweep(c, second[i]);
+        }
+        return;
+    }
+#endif
 #ifndef PS3D_EMU
     const bool overlap = c.tr.have_nccl() && !c.tr.a2a_cb;
 #else
@@ -540,6 +611,9 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->redS.alloc(64); c->redM.alloc(64);
     c->partial.alloc((size_t)RED_BLOCKS * 16);
     c->red.alloc(64);
+#ifndef PS3D_EMU
+    if (nranks > 1) setup_p2p(*c);
+#endif
 }
 
 static void do_init_inversion(int filtering) {
@@ -654,6 +728,7 @@ static void do_finalise() {
     for (int i = 0; i < 9; ++i) c->W[i].release();
     c->redS.release(); c->redM.release();
 #ifndef PS3D_EMU
+    for (int b = 0; b < 2; ++b) for (int p = 0; p < 8; ++p) if (c->tr.ipc_opened[b][p]) cudaIpcCloseMemHandle(c->tr.ipc_opened[b][p]);
     if (c->tr.comm) c->tr.nccl.CommDestroy(c->tr.comm);
 #endif
     DevBuf<double>* singles[] = {&c->stage, &c->kxl, &c->kyline, &c->kxd, &c->kyd, &c->k2l2, &c->k2l2i, &c->zm, &c->zp,

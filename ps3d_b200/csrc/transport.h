@@ -28,11 +28,12 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, Comm, void*) = nullptr;
     int (*Recv)(void*, size_t, int, int, Comm, void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, Comm, void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, Comm, void*) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     void* handle = nullptr;
-    enum { kFloat64 = 8, kSum = 0, kMax = 2 };
+    enum { kUint8 = 1, kFloat64 = 8, kSum = 0, kMax = 2 };
 
     bool load() {
         if (handle) return true;
@@ -50,6 +51,7 @@ struct NcclApi {
         PS_NCCL_SYM(Send, "ncclSend")
         PS_NCCL_SYM(Recv, "ncclRecv")
         PS_NCCL_SYM(AllReduce, "ncclAllReduce")
+        PS_NCCL_SYM(AllGather, "ncclAllGather")
         PS_NCCL_SYM(GroupStart, "ncclGroupStart")
         PS_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         PS_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -65,6 +67,9 @@ struct Transport {
     alltoall_fn a2a_cb = nullptr;
     allreduce_fn ar_cb = nullptr;
     void* user = nullptr;
+    bool p2p = false;                 // sweeps store straight into the peers' receive buffers (CUDA IPC)
+    double* peer_t2[2][8] = {};       // [buffer][rank]: base of that rank's receive buffer
+    void* ipc_opened[2][8] = {};
     long long n_alltoall = 0;
     double bytes_sent = 0.0;
 
