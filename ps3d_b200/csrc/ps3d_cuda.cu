@@ -157,7 +157,7 @@ static void allow_smem(K, size_t) {}
 #endif
 
 #define PS_FOR_LINE_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
-#define PS_FOR_Z_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512)
+#define PS_FOR_Z_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
 
 template <int N>
 static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles) {
@@ -425,7 +425,7 @@ static void launch_zop(Ctx& c, int op, const double* in, double* out) {
 #define X(NN) case NN: launch_zop_n<NN>(c, op, in, out); break;
         PS_FOR_Z_SIZES(X)
 #undef X
-        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..512)", c.nz);
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..1024)", c.nz);
     }
 }
 
@@ -441,7 +441,7 @@ static void launch_v2v(Ctx& c, const V2VArgs& a) {
 #define X(NN) case NN: launch_v2v_n<NN>(c, a); break;
         PS_FOR_Z_SIZES(X)
 #undef X
-        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..512)", c.nz);
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..1024)", c.nz);
     }
 }
 
@@ -457,7 +457,7 @@ static void launch_src(Ctx& c, const SrcArgs& a) {
 #define X(NN) case NN: launch_src_n<NN>(c, a); break;
         PS_FOR_Z_SIZES(X)
 #undef X
-        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..512)", c.nz);
+        default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "nz = %d not supported (power of two, 8..1024)", c.nz);
     }
 }
 
@@ -493,9 +493,9 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
                     const void* nccl_id) {
     if (g_ctx) fail(PS3D_ERR_BAD_ARGUMENT, "ps3d_cuda_init called twice without ps3d_cuda_finalise");
     if (!lower || !extent) fail(PS3D_ERR_BAD_ARGUMENT, "null lower/extent");
-    if (!pow2(nx) || !pow2(ny) || !pow2(nz) || nx < 8 || ny < 8 || nz < 8 || nx > 1024 || ny > 1024 || nz > 512)
+    if (!pow2(nx) || !pow2(ny) || !pow2(nz) || nx < 8 || ny < 8 || nz < 8 || nx > 1024 || ny > 1024 || nz > 1024)
         fail(PS3D_ERR_UNSUPPORTED_SIZE,
-             "grid %dx%dx%d: this build supports power-of-two nx, ny in 8..1024 and nz in 8..512", nx, ny, nz);
+             "grid %dx%dx%d: this build supports power-of-two nx, ny, nz in 8..1024", nx, ny, nz);
     if (nranks < 1 || rank < 0 || rank >= nranks || nx % nranks || (ny / 2) % nranks)
         fail(PS3D_ERR_BAD_ARGUMENT, "bad rank layout %d/%d for %dx%d", rank, nranks, nx, ny);
     for (int i = 0; i < 3; ++i)

@@ -379,7 +379,7 @@ struct V2VArgs {
 };
 
 template <int NZ>
-__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ >= 512) ? 2 : 1) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
+__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
     PS_SMEM(double, sm);
     constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
     double* A = sm;
@@ -673,7 +673,7 @@ __device__ __forceinline__ void stage_diffz_decomposed(double* DX, const double*
 }
 
 template <int NZ>
-__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ >= 512) ? 2 : 1) k_source_spec(SpecGeom g, SrcArgs a) {
+__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_spec(SpecGeom g, SrcArgs a) {
     PS_SMEM(double, sm);
     constexpr int BUF = ZCfg<NZ>::BUF;
     double* R = sm;

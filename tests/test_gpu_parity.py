@@ -34,7 +34,7 @@ def open_grid(lib, nx, ny, nz, lower, extent, filtering="Hou & Li"):
     return O.PS3D(nx, ny, nz, lower, extent, filtering)
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 64), (16, 32, 8), (128, 64, 32), (8, 8, 8)])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (16, 32, 8), (128, 64, 32), (8, 8, 8), (16, 16, 1024), (1024, 8, 16)])
 def test_operators_white_noise(lib, shape):
     """isolated transforms on a white-noise field (all modes populated)."""
     nx, ny, nz = shape
