@@ -28,7 +28,7 @@ def trajectory(stepper, n=32, nsteps=100):
     s.vor2vel()
     final = np.array([s.get_kinetic_energy(), s.get_enstrophy(), s.get_helicity()])
     # a thin sample of the final spectral vorticity (every 4th mode / level) keeps the file small
-    return np.array(rows), final, s.svor[:, ::4, ::4, ::4].copy()
+    return np.array(rows), final, s.svor[:, ::4, ::4, ::4].copy(), float(np.max(np.abs(s.svor)))
 
 
 def operators(nx=16, ny=32, nz=8):
@@ -43,7 +43,8 @@ def operators(nx=16, ny=32, nz=8):
 
 if __name__ == "__main__":
     for stepper, tag in (("cn2", "cn2"), ("impl-diff-rk4", "rk4")):
-        rows, final, sample = trajectory(stepper)
-        np.savez_compressed(os.path.join(OUT, f"beltrami32_{tag}_100steps.npz"), series=rows, final=final, svor_sample=sample)
+        rows, final, sample, smax = trajectory(stepper)
+        np.savez_compressed(os.path.join(OUT, f"beltrami32_{tag}_100steps.npz"), series=rows, final=final, svor_sample=sample,
+                            svor_max=smax)
     np.savez_compressed(os.path.join(OUT, "operators_16x32x8.npz"), **operators())
     print("golden vectors written to", OUT)
