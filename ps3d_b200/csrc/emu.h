@@ -38,6 +38,7 @@ struct BlockState {
     ucontext_t sched;
     int cur = 0;
     std::vector<char> smem;
+    std::vector<double> xchg;          // warp-shuffle exchange slots (one per thread)
     const std::function<void()>* body = nullptr;
     ~BlockState() { for (char* s : stacks) free(s); }
 };
@@ -62,6 +63,30 @@ inline void yield() {
 #define gridDim (::emu::tl_gridDim)
 
 static inline void __syncthreads() { ::emu::yield(); }
+// Warp shuffles: every thread of the block must execute the same shuffle sequence (true for the kernels
+// here); a shuffle is two barrier rounds through a per-thread exchange slot.
+static inline int emu_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
+static inline double __shfl_up_sync(unsigned, double v, unsigned delta, int width = 32) {
+    ::emu::BlockState* bs = ::emu::tl_bs;
+    const int t = emu_tid();
+    bs->xchg[t] = v;
+    ::emu::yield();
+    const int lane = t % width;
+    const double r = (lane >= (int)delta) ? bs->xchg[t - delta] : v;
+    ::emu::yield();
+    return r;
+}
+static inline double __shfl_xor_sync(unsigned, double v, int mask, int width = 32) {
+    ::emu::BlockState* bs = ::emu::tl_bs;
+    const int t = emu_tid();
+    bs->xchg[t] = v;
+    ::emu::yield();
+    const int lane = t % width;
+    const int src = t - lane + ((lane ^ mask) % width);
+    const double r = (src < (int)bs->xchg.size()) ? bs->xchg[src] : v;
+    ::emu::yield();
+    return r;
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
@@ -91,6 +116,7 @@ static void run_block(BlockState& bs, dim3 bidx, dim3 grid, dim3 block, size_t s
     }
     bs.done.assign(nt, 0);
     bs.smem.assign(smem + 64, 0);
+    bs.xchg.assign(nt, 0.0);
     bs.body = &body;
     tl_bs = &bs;
     tl_blockIdx = bidx; tl_blockDim = block; tl_gridDim = grid;

@@ -18,11 +18,13 @@
 //    thread 0 also row nz) of ALL four slots, so every x/y mirror coupling is a
 //    register operation and the hyperbolic functions of a row are evaluated once
 //    and kept in registers for the whole kernel;
-//  * DST-I / DCT-I of length nz (reference stafft.f90:410-550 conventions) are
-//    done two columns at a time as one complex FFT of length 2 nz over the odd /
-//    even extensions: accurate (no post-processing recurrence) and built on the
-//    same block_cfft as the x/y passes; the two pair-FFTs of a field run
-//    concurrently on the two halves of the block.
+//  * DST-I / DCT-I of length nz follow the reference's own reduction to a real FFT of
+//    length nz (stafft.f90:410-550: pre-process, forfft, post-process), two columns per
+//    complex FFT of length nz (same block_cfft as the x/y passes).  The post-processing
+//    recurrence x(2j+1) = x(2j-1) +- sqrt2*wk(.) (stafft.f90:466-471, 526-533) is a prefix
+//    sum: done as a per-thread scan of 4 + a warp-shuffle scan, i.e. O(log n) roundings
+//    instead of the reference's O(n).  Two 4-slot fields are transformed concurrently
+//    (4 FFTs of nz/8 threads each = the whole block).
 //
 // The N-sized tables of the reference (phim, phip, thetam, thetap, dthetam,
 // dthetap, green, filt: inversion_utils.f90:281-369,484-542) are never
@@ -52,14 +54,18 @@ struct SpecGeom {
 
 template <int NZ>
 struct ZCfg {
-    static constexpr int M = 2 * NZ;              // pair-FFT length
-    static constexpr int TPF = M / 8;             // threads per pair FFT
-    static constexpr int NT = 2 * TPF;            // 2 pair FFTs = 4 slots of one field  (= NZ/2)
-    static constexpr int LC = NZ + 2;             // column buffer stride (rows 0..NZ used)
-    static constexpr int SCR = 2 * 2 * M;         // doubles of FFT scratch (2 FFTs x re/im x M)
+    static constexpr int TPF = NZ / 8;            // threads per complex FFT of length NZ (two columns)
+    static constexpr int NT = 4 * TPF;            // 4 FFTs = two 4-slot fields at a time  (= NZ/2)
+    static constexpr int LC = NZ + 16;            // column buffer stride (rows 0..NZ, swizzled in 16-row blocks)
     static constexpr int BUF = 4 * LC;            // doubles per 4-slot field buffer
+    static constexpr int NSIN = NZ / 2 + 2;       // sin(m pi/nz), m = 0..nz/2
+    static constexpr int SCR = 4 * 2 * NZ + NSIN + 64;   // FFT scratch (4 x re/im x NZ) + sine table + warp totals
     static constexpr int ZI = 3;                  // rows per thread: t, t+NT, and NZ (thread 0 only)
 };
+
+// row z of a column buffer: XOR swizzle inside 16-row blocks, so that both the unit-stride (z-owner)
+// and the stride-8 (transform output: thread u owns rows 8u..8u+7) accesses are bank-conflict free
+__device__ __forceinline__ int cz(int z) { return z ^ ((z >> 4) & 15); }
 
 // ---- group bookkeeping -----------------------------------------------------
 struct Grp {
@@ -125,15 +131,17 @@ template <int NZ>
 __device__ __forceinline__ Row4 row_load_s(const double* buf, int z) {
     constexpr int LC = ZCfg<NZ>::LC;
     Row4 x;
+    const int zz = cz(z);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) x.v[s] = buf[s * LC + z];
+    for (int s = 0; s < 4; ++s) x.v[s] = buf[s * LC + zz];
     return x;
 }
 template <int NZ>
 __device__ __forceinline__ void row_store_s(double* buf, int z, const Row4& x) {
     constexpr int LC = ZCfg<NZ>::LC;
+    const int zz = cz(z);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) buf[s * LC + z] = x.v[s];
+    for (int s = 0; s < 4; ++s) buf[s * LC + zz] = x.v[s];
 }
 
 // d/dx, d/dy of a row (sta3dfft.f90:325-329): slot s = 2*sx + sy,
@@ -224,61 +232,170 @@ __device__ __forceinline__ void hyp_theta(const Hyp& h, double ep, double em, do
     dthp = -h.k2if * ((h.Q * Lm - 1.0) * dphip - h.R * Lp * dphim);
 }
 
-// ---- z transforms on a 4-slot shared-memory field ---------------------------
-// DST-I of rows 1..NZ-1 of each slot (scaled sqrt(2/NZ)); rows 0 and NZ are
-// neither read nor written (stafft.f90:509-513).  Ends with a barrier; the
-// caller must have a barrier between its last write of X and this call.
+// ---- z transforms on 4-slot shared-memory fields ------------------------------
+enum { XF_DST = 0, XF_DCT = 1 };
+
+// shared scratch of the transforms
 template <int NZ>
-__device__ __forceinline__ void dst4(double* X, double* scr, const SpecGeom& g) {
-    constexpr int M = ZCfg<NZ>::M, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
-    const int t = threadIdx.x;
-    const int f = t / TPF, u = t - f * TPF;
-    double* x0 = X + (2 * f) * LC;
-    double* x1 = x0 + LC;
-    double vr[8], vi[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int j = u + e * (M / 8);
-        double a = 0.0, c = 0.0;
-        if (j > 0 && j < NZ) { a = x0[j]; c = x1[j]; }
-        else if (j > NZ) { a = -x0[M - j]; c = -x1[M - j]; }
-        vr[e] = a; vi[e] = c;
-    }
-    double* sre = scr + f * 2 * M;
-    double* sim = sre + M;
-    block_cfft<M, false>(vr, vi, u, true, sre, sim, IxSwz(), g.tw, g.ntw / M);
-    const double sc = rsqrt((double)M);     // 1/sqrt(2 nz)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int k = u + e * (M / 8);
-        if (k >= 1) { x0[k] = -vi[e] * sc; x1[k] = vr[e] * sc; }     // k < NZ always for e < 4
-    }
-    __syncthreads();
+struct ZScr {
+    double* fft;      // [4][2][NZ]
+    double* sintab;   // [NZ/2 + 1]  sin(m pi / NZ)
+    double* wt;       // [64] warp totals of the group scan / sum
+};
+template <int NZ>
+__device__ __forceinline__ ZScr<NZ> make_scr(double* base) {
+    ZScr<NZ> s;
+    s.fft = base; s.sintab = base + 8 * NZ; s.wt = s.sintab + ZCfg<NZ>::NSIN;
+    return s;
+}
+// fill the sine table (once per block; followed by a barrier in the caller)
+template <int NZ>
+__device__ __forceinline__ void scr_init(const ZScr<NZ>& sc, const SpecGeom& g) {
+    const int step = g.ntw / (2 * NZ);                      // tw[m] = exp(2 pi i m / ntw), ntw >= 2 NZ
+    for (int m = threadIdx.x; m <= NZ / 2; m += blockDim.x) sc.sintab[m] = __ldg(&g.tw[m * step]).y;
+}
+template <int NZ>
+__device__ __forceinline__ double sin_j(const ZScr<NZ>& sc, int j) { return sc.sintab[(j <= NZ / 2) ? j : NZ - j]; }
+template <int NZ>
+__device__ __forceinline__ double cos_j(const ZScr<NZ>& sc, int j) {
+    return (j <= NZ / 2) ? sc.sintab[NZ / 2 - j] : -sc.sintab[j - NZ / 2];
 }
 
-// DCT-I of rows 0..NZ of each slot (scaled sqrt(2/NZ)).  Ends with a barrier.
+// inclusive scan of (a, b) over the TPF consecutive threads of one FFT (u = index inside the FFT)
+template <int TPF>
+__device__ __forceinline__ void group_scan2(double& a, double& b, int u, double* wt) {
+    constexpr int W = (TPF < 32) ? TPF : 32;
+#pragma unroll
+    for (int d = 1; d < W; d <<= 1) {
+        const double ta = __shfl_up_sync(0xffffffffu, a, d, W);
+        const double tb = __shfl_up_sync(0xffffffffu, b, d, W);
+        if ((u & (W - 1)) >= d) { a += ta; b += tb; }
+    }
+    if (TPF > 32) {
+        const int w = u >> 5;
+        if ((u & 31) == 31) { wt[2 * w] = a; wt[2 * w + 1] = b; }
+        __syncthreads();
+        for (int v = 0; v < w; ++v) { a += wt[2 * v]; b += wt[2 * v + 1]; }
+    }
+}
+// sum of (a, b) over the TPF threads of one FFT, result in every thread
+template <int TPF>
+__device__ __forceinline__ void group_sum2(double& a, double& b, int u, double* wt) {
+    constexpr int W = (TPF < 32) ? TPF : 32;
+#pragma unroll
+    for (int d = W >> 1; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d, W);
+        b += __shfl_xor_sync(0xffffffffu, b, d, W);
+    }
+    if (TPF > 32) {
+        const int w = u >> 5;
+        if ((u & 31) == 0) { wt[2 * w] = a; wt[2 * w + 1] = b; }
+        __syncthreads();
+        a = 0.0; b = 0.0;
+        for (int v = 0; v < TPF / 32; ++v) { a += wt[2 * v]; b += wt[2 * v + 1]; }
+    }
+}
+
+// DST-I (rows 1..NZ-1; rows 0 and NZ neither read nor written, stafft.f90:509-513) or DCT-I (rows 0..NZ) of the
+// four slots of X0 and, concurrently, of X1 (may be null), scaled sqrt(2/NZ).  Reference algorithm
+// (stafft.f90:410-550) with two columns per complex FFT:
+//   DST: y_j = (x_j - x_{n-j})/2 + sin(j pi/n)(x_j + x_{n-j});  Y = FFT(y);
+//        X_1 = Y_0/2, X_{2k} = -Im Y_k, X_{2k+1} = X_{2k-1} + Re Y_k            (all times sqrt(2/n))
+//   DCT: y_0 = (x_0 + x_n)/2, y_j = (x_j + x_{n-j})/2 - sin(j pi/n)(x_j - x_{n-j});
+//        X_1 = x_0/2 - x_n/2 + sum_j x_j cos(j pi/n), X_0 = Y_0, X_{2k} = Re Y_k, X_n = Y_{n/2},
+//        X_{2k+1} = X_{2k-1} - Im Y_k
+// The caller must have a barrier between its last write of X0/X1 and this call; ends with a barrier.
 template <int NZ>
-__device__ __forceinline__ void dct4(double* X, double* scr, const SpecGeom& g) {
-    constexpr int M = ZCfg<NZ>::M, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
+__device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int kind1, const ZScr<NZ>& sc,
+                                       const SpecGeom& g) {
+    constexpr int n = NZ, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
     const int t = threadIdx.x;
-    const int f = t / TPF, u = t - f * TPF;
-    double* x0 = X + (2 * f) * LC;
-    double* x1 = x0 + LC;
+    const int fg = t / (2 * TPF), f = (t / TPF) & 1, u = t - (t / TPF) * TPF, fft = 2 * fg + f;
+    double* X = fg ? X1 : X0;
+    const int kind = fg ? kind1 : kind0;
+    const bool act = (X != nullptr);
+    double* xa = (act ? X : X0) + (2 * f) * LC;
+    double* xb = xa + LC;
+    double* sre = sc.fft + fft * 2 * n;
+    double* sim = sre + n;
+    double* wt = sc.wt + fft * 8;
+    const IxSwz ix;
+
+    // ---- pre-process: two real sequences -> one complex sequence
     double vr[8], vi[8];
+    double sa = 0.0, sb = 0.0;                 // DCT: X_1 partial sums
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int j = u + e * (M / 8);
-        const int jj = (j <= NZ) ? j : M - j;
-        vr[e] = x0[jj]; vi[e] = x1[jj];
+        const int j = u + e * TPF;
+        double yr = 0.0, yi = 0.0;
+        if (act) {
+            if (j == 0) {
+                if (kind == XF_DCT) {
+                    const double a0 = xa[cz(0)], an = xa[cz(n)], b0 = xb[cz(0)], bn = xb[cz(n)];
+                    yr = 0.5 * (a0 + an); yi = 0.5 * (b0 + bn);
+                    sa += 0.5 * (a0 - an); sb += 0.5 * (b0 - bn);
+                }
+            } else {
+                const double aj = xa[cz(j)], an = xa[cz(n - j)], bj = xb[cz(j)], bn = xb[cz(n - j)];
+                const double sn = sin_j<NZ>(sc, j);
+                if (kind == XF_DST) {
+                    yr = 0.5 * (aj - an) + sn * (aj + an);
+                    yi = 0.5 * (bj - bn) + sn * (bj + bn);
+                } else {
+                    yr = 0.5 * (aj + an) - sn * (aj - an);
+                    yi = 0.5 * (bj + bn) - sn * (bj - bn);
+                    const double cs = cos_j<NZ>(sc, j);
+                    sa += aj * cs; sb += bj * cs;
+                }
+            }
+        }
+        vr[e] = yr; vi[e] = yi;
     }
-    double* sre = scr + f * 2 * M;
-    double* sim = sre + M;
-    block_cfft<M, false>(vr, vi, u, true, sre, sim, IxSwz(), g.tw, g.ntw / M);
-    const double sc = rsqrt((double)M);
+    group_sum2<TPF>(sa, sb, u, wt);            // (only meaningful for DCT; executed uniformly)
+
+    block_cfft<n, false>(vr, vi, u, true, sre, sim, ix, g.tw, g.ntw / n);
+    __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 5; ++e) {
-        const int k = u + e * (M / 8);
-        if (k <= NZ) { x0[k] = vr[e] * sc; x1[k] = vi[e] * sc; }
+    for (int e = 0; e < 8; ++e) {
+        const int idx = ix(u + e * TPF);
+        sre[idx] = vr[e]; sim[idx] = vi[e];
+    }
+    __syncthreads();
+
+    // ---- post-process: thread u owns k = 4u .. 4u+3, i.e. output rows 8u .. 8u+7
+    double oa[4], ob[4], ea[4], eb[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int k = 4 * u + c;
+        if (k == 0) {
+            const double p = sre[ix(0)], q = sim[ix(0)];
+            if (kind == XF_DST) { oa[c] = 0.5 * p; ob[c] = 0.5 * q; ea[c] = 0.0; eb[c] = 0.0; }
+            else { oa[c] = sa; ob[c] = sb; ea[c] = p; eb[c] = q; }
+        } else {
+            const int ik = ix(k), im = ix(n - k);
+            const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
+            const double reA = 0.5 * (p + r), imA = 0.5 * (q - s), reB = 0.5 * (q + s), imB = 0.5 * (r - p);
+            if (kind == XF_DST) { oa[c] = reA; ob[c] = reB; ea[c] = -imA; eb[c] = -imB; }
+            else { oa[c] = -imA; ob[c] = -imB; ea[c] = reA; eb[c] = reB; }
+        }
+    }
+#pragma unroll
+    for (int c = 1; c < 4; ++c) { oa[c] += oa[c - 1]; ob[c] += ob[c - 1]; }
+    double ta = oa[3], tb = ob[3];
+    group_scan2<TPF>(ta, tb, u, wt + 4);
+    const double pa = ta - oa[3], pb = tb - ob[3];      // exclusive prefix of this thread
+    const double scl = sqrt(2.0 / (double)n);
+    double nyq_a = 0.0, nyq_b = 0.0;
+    if (u == 0 && kind == XF_DCT) { nyq_a = sre[ix(n / 2)]; nyq_b = sim[ix(n / 2)]; }
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int k = 4 * u + c;
+            xa[cz(2 * k + 1)] = scl * (oa[c] + pa);
+            xb[cz(2 * k + 1)] = scl * (ob[c] + pb);
+            if (k > 0 || kind == XF_DCT) { xa[cz(2 * k)] = scl * ea[c]; xb[cz(2 * k)] = scl * eb[c]; }
+        }
+        if (u == 0 && kind == XF_DCT) { xa[cz(n)] = scl * nyq_a; xb[cz(n)] = scl * nyq_b; }
     }
     __syncthreads();
 }
@@ -299,7 +416,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
     PS_SMEM(double, sm);
     constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
     double* X = sm;
-    double* scr = X + BUF;
+    const ZScr<NZ> scr = make_scr<NZ>(X + BUF);
+    scr_init<NZ>(scr, g);
     const Grp r = make_grp(g, blockIdx.x);
     Hyp h[2];
     HypRows<NZ> T;
@@ -341,14 +459,13 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const double* c = X + s * LC;
-                d.v[s] = (z == 0) ? g.dzi * (c[1] - c[0]) : (z == NZ) ? g.dzi * (c[NZ] - c[NZ - 1]) : (c[z + 1] - c[z - 1]) * g.hdzi;
+                d.v[s] = (z == 0) ? g.dzi * (c[cz(1)] - c[cz(0)]) : (z == NZ) ? g.dzi * (c[cz(NZ)] - c[cz(NZ - 1)]) : (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi;
             }
             row_store_g<NZ>(out, r, z, d);
         }
         return;
     }
-    if (op == ZOP_COSINE) dct4<NZ>(X, scr, g);
-    else dst4<NZ>(X, scr, g);
+    xform2<NZ>(X, (op == ZOP_COSINE) ? XF_DCT : XF_DST, nullptr, XF_DST, scr, g);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -357,7 +474,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         if (op == ZOP_SINE && z == NZ) { x.v[0] = x.v[1] = x.v[2] = x.v[3] = 0.0; }     // stafft.f90:546-549
         if (op == ZOP_COMBINE && z >= 1 && z < NZ) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) x.v[s] += X[s * LC] * T.phim[it][s & 1] + X[s * LC + NZ] * T.phip[it][s & 1];
+            for (int s = 0; s < 4; ++s) x.v[s] += X[s * LC + cz(0)] * T.phim[it][s & 1] + X[s * LC + cz(NZ)] * T.phip[it][s & 1];
         }
         row_store_g<NZ>(out, r, z, x);
     }
@@ -386,7 +503,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
     double* B = A + BUF;
     double* C = B + BUF;
     double* E = C + BUF;
-    double* scr = E + BUF;
+    const ZScr<NZ> scr = make_scr<NZ>(E + BUF);
+    scr_init<NZ>(scr, g);
     const Grp r = make_grp(g, blockIdx.x);
     Hyp h[2];
     h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
@@ -406,7 +524,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 
     // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; also the
     // semi-spectral zeta that feeds the inverse x/y passes (:81)
-    dst4<NZ>(C, scr, g);
+    xform2<NZ>(C, XF_DST, nullptr, XF_DST, scr, g);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -414,7 +532,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         Row4 c = row_load_s<NZ>(C, z);
         if (z >= 1 && z < NZ) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) c.v[s] += C[s * LC] * T.phim[it][s & 1] + C[s * LC + NZ] * T.phip[it][s & 1];
+            for (int s = 0; s < 4; ++s) c.v[s] += C[s * LC + cz(0)] * T.phim[it][s & 1] + C[s * LC + cz(NZ)] * T.phip[it][s & 1];
             row_store_s<NZ>(C, z, c);
         }
         row_store_g<NZ>(a.wsem2, r, z, c);
@@ -426,8 +544,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const double* c = C + s * LC;
-            e0[s] = g.dzi * (c[1] - c[0]);
-            en[s] = g.dzi * (c[NZ] - c[NZ - 1]);
+            e0[s] = g.dzi * (c[cz(1)] - c[cz(0)]);
+            en[s] = g.dzi * (c[cz(NZ)] - c[cz(NZ - 1)]);
         }
 #pragma unroll
         for (int it = 0; it < 3; ++it) {
@@ -439,13 +557,13 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
                 const double* c = C + s * LC;
                 if (z == 0) e.v[s] = e0[s];
                 else if (z == NZ) e.v[s] = en[s];
-                else e.v[s] = (c[z + 1] - c[z - 1]) * g.hdzi - (e0[s] * T.phim[it][s & 1] + en[s] * T.phip[it][s & 1]);
+                else e.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi - (e0[s] * T.phim[it][s & 1] + en[s] * T.phip[it][s & 1]);
             }
             row_store_s<NZ>(E, z, e);
         }
     }
     __syncthreads();
-    dst4<NZ>(E, scr, g);
+    xform2<NZ>(E, XF_DST, nullptr, XF_DST, scr, g);
 
     // D = B_x - A_y (:39-42); A = k2l2i (E_x + D_y), B = k2l2i (E_y - D_x), (0,0) keeps its mean (:55-76);
     // then the source of the w inversion D2 = A_y - B_x (:86-90) -> E buffer
@@ -485,12 +603,11 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
     // boundary values of D2 (:96-104) and of the mean vorticity (:163-164), before anything is overwritten
     double d0[4], dn[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) { d0[s] = E[s * LC]; dn[s] = E[s * LC + NZ]; }
-    const double a00 = A[0], a0n = A[NZ], b00 = B[0], b0n = B[NZ];
+    for (int s = 0; s < 4; ++s) { d0[s] = E[s * LC + cz(0)]; dn[s] = E[s * LC + cz(NZ)]; }
+    const double a00 = A[cz(0)], a0n = A[cz(NZ)], b00 = B[cz(0)], b0n = B[cz(NZ)];
 
     // vorticity to semi-spectral space for the inverse x/y passes (:80-82)
-    dst4<NZ>(A, scr, g);
-    dst4<NZ>(B, scr, g);
+    xform2<NZ>(A, XF_DST, B, XF_DST, scr, g);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -499,8 +616,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         if (z >= 1 && z < NZ) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                fa.v[s] += A[s * LC] * T.phim[it][s & 1] + A[s * LC + NZ] * T.phip[it][s & 1];
-                fb.v[s] += B[s * LC] * T.phim[it][s & 1] + B[s * LC + NZ] * T.phip[it][s & 1];
+                fa.v[s] += A[s * LC + cz(0)] * T.phim[it][s & 1] + A[s * LC + cz(NZ)] * T.phip[it][s & 1];
+                fb.v[s] += B[s * LC + cz(0)] * T.phim[it][s & 1] + B[s * LC + cz(NZ)] * T.phip[it][s & 1];
             }
         }
         row_store_g<NZ>(a.wsem0, r, z, fa);
@@ -540,9 +657,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         }
     }
     __syncthreads();
-    dct4<NZ>(A, scr, g);     // (:128)
-    dst4<NZ>(E, scr, g);     // (:129)
-    if (r.g00) dct4<NZ>(B, scr, g);
+    xform2<NZ>(A, XF_DCT, E, XF_DST, scr, g);     // (:128-129)
+    if (r.g00) xform2<NZ>(B, XF_DCT, nullptr, XF_DST, scr, g);
 
     // w = E + boundary part, dw/dz = es + as (:96-104, :136-139);
     // u = k2l2i (es_x + cs_y), v = k2l2i (es_y - cs_x), (0,0) <- ubar, vbar (:169-213)
@@ -570,8 +686,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         }
         if (r.g00) {
             const double gt = __ldg(&g.gamtop[z]), gb = __ldg(&g.gambot[z]);
-            u.v[0] = B[z] + b0n * gt - b00 * gb;               // ubar (:163)
-            v.v[0] = B[LC + z] - a0n * gt + a00 * gb;          // vbar (:164)
+            u.v[0] = B[cz(z)] + b0n * gt - b00 * gb;               // ubar (:163)
+            v.v[0] = B[LC + cz(z)] - a0n * gt + a00 * gb;          // vbar (:164)
         }
         if (a.dbg == 1) {
             Row4 t1, t2;
@@ -680,7 +796,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
     double* X = R + BUF;
     double* Y = X + BUF;
     double* W = Y + BUF;
-    double* scr = W + BUF;
+    const ZScr<NZ> scr = make_scr<NZ>(W + BUF);
+    scr_init<NZ>(scr, g);
     const Grp r = make_grp(g, blockIdx.x);
     Hyp h[2];
     h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
@@ -693,10 +810,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
     stage_diffz_decomposed<NZ>(Y, a.p, g, T, r);
     stage_decomposed<NZ>(W, a.q, T, r);
     __syncthreads();
-    dst4<NZ>(R, scr, g);
-    dst4<NZ>(X, scr, g);
-    dst4<NZ>(Y, scr, g);
-    dst4<NZ>(W, scr, g);
+    xform2<NZ>(R, XF_DST, X, XF_DST, scr, g);
+    xform2<NZ>(Y, XF_DST, W, XF_DST, scr, g);
     // xi, eta tendencies (inversion.f90:341-359); keep d(q)/dx of my rows for the zeta tendency
     Row4 qx[3] = {};
 #pragma unroll
@@ -716,7 +831,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
     // zeta tendency dq/dx - dp/dy (:363-367)
     stage_decomposed<NZ>(R, a.p, T, r);
     __syncthreads();
-    dst4<NZ>(R, scr, g);
+    xform2<NZ>(R, XF_DST, nullptr, XF_DST, scr, g);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
