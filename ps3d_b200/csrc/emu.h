@@ -88,6 +88,8 @@ static inline double __shfl_xor_sync(unsigned, double v, int mask, int width = 3
     return r;
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 

@@ -60,7 +60,11 @@ struct LineArgs {
     double* outp[8];          // peer-memory scatter: base of rank d's receive buffer (all = out otherwise)
     long long in_os, out_os;  // stride between consecutive outer lines (doubles)
     RowMap in_map, out_map;   // offset of row k from the tile base
-    int nzc;                  // z-chunks per line (pz / 16)
+    int nzc;                  // z-chunks handled by this launch (tiles = outer lines x nzc)
+    int zc0;                  // first z-chunk of this launch
+    int in_zc0, out_zc0;      // z-chunk held at offset 0 of the input / output array (0 for full arrays; = zc0 for
+                              // the compact, L2-resident intermediate of a chunked 2-D FFT)
+    int final_store;          // 1: streaming stores (result leaves the cache), 0: keep in L2 for the next sweep
     const double* kdiff;      // DIFF: wavenumber per k = 0..N/2 (0 at k = 0 and N/2)
     double scale;             // 1/sqrt(N)
     const double2* tw;
@@ -68,8 +72,13 @@ struct LineArgs {
 };
 
 __device__ __forceinline__ double* row_dst(const struct LineArgs& a, int k);
-__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+// sweep inputs are dead after the load: streaming (evict-first) loads
+__device__ __forceinline__ double2 ld2(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+__device__ __forceinline__ void st2f(int fin, double* p, double x, double y) {
+    if (fin) __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));
+    else *reinterpret_cast<double2*>(p) = make_double2(x, y);
+}
 
 __device__ __forceinline__ double* row_dst(const LineArgs& a, int k) {
     int d;
@@ -81,8 +90,8 @@ template <int N, int PRO>
 __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_fwd(LineArgs a) {
     PS_SMEM(double, sm);
     const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
-    const int o = blockIdx.x / a.nzc, zc = blockIdx.x - o * a.nzc;
-    const long long ibase = (long long)o * a.in_os + zc * LINE_ZC + 2 * f;
+    const int o = blockIdx.x / a.nzc, zc = a.zc0 + (blockIdx.x - o * a.nzc);
+    const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
     double vr[8], vi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -108,22 +117,22 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
         sre[idx] = vr[e]; sim[idx] = vi[e];
     }
     __syncthreads();
-    const long long obase = (long long)o * a.out_os + zc * LINE_ZC + 2 * f;
+    const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * LINE_ZC + 2 * f;
     const double sc = a.scale, hs = 0.5 * a.scale;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int k = u + e * (N / 8);
         if (k == 0) {
             const int i0 = ix(0);
-            st2(row_dst(a, 0) + obase, sre[i0] * sc, sim[i0] * sc);
+            st2f(a.final_store, row_dst(a, 0) + obase, sre[i0] * sc, sim[i0] * sc);
             const int ih = ix(N / 2);
-            st2(row_dst(a, N / 2) + obase, sre[ih] * sc, sim[ih] * sc);
+            st2f(a.final_store, row_dst(a, N / 2) + obase, sre[ih] * sc, sim[ih] * sc);
         } else {
             const int ik = ix(k), im = ix(N - k);
             const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
             // A_k = (C_k + conj C_{N-k})/2, B_k = (C_k - conj C_{N-k})/(2i)
-            st2(row_dst(a, k) + obase, (p + r) * hs, (q + s) * hs);       // Re A, Re B
-            st2(row_dst(a, N - k) + obase, (q - s) * hs, (r - p) * hs);   // Im A, Im B
+            st2f(a.final_store, row_dst(a, k) + obase, (p + r) * hs, (q + s) * hs);       // Re A, Re B
+            st2f(a.final_store, row_dst(a, N - k) + obase, (q - s) * hs, (r - p) * hs);   // Im A, Im B
         }
     }
 }
@@ -132,8 +141,8 @@ template <int N, int PRO>
 __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_inv(LineArgs a) {
     PS_SMEM(double, sm);
     const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
-    const int o = blockIdx.x / a.nzc, zc = blockIdx.x - o * a.nzc;
-    const long long ibase = (long long)o * a.in_os + zc * LINE_ZC + 2 * f;
+    const int o = blockIdx.x / a.nzc, zc = a.zc0 + (blockIdx.x - o * a.nzc);
+    const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
     double* sre = sm;
     double* sim = sm + LINE_NF * N;
     const IxIlv<LINE_NF> ix{f};
@@ -175,11 +184,11 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     fft_gather<N>(vr, vi, u, sre, sim, ix);
     __syncthreads();
     block_cfft<N, true>(vr, vi, u, true, sre, sim, ix, a.tw, a.twscale);
-    const long long obase = (long long)o * a.out_os + zc * LINE_ZC + 2 * f;
+    const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * LINE_ZC + 2 * f;
     const double sc = a.scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-        st2(row_dst(a, u + e * (N / 8)) + obase, vr[e] * sc, vi[e] * sc);
+        st2f(a.final_store, row_dst(a, u + e * (N / 8)) + obase, vr[e] * sc, vi[e] * sc);
 }
 
 template <int N>

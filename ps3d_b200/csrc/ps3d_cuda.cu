@@ -97,6 +97,7 @@ struct Ctx {
     double vvisc = 0.0;
     RollingMean rollmean;
     long long launches = 0;
+    int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
 
@@ -184,38 +185,45 @@ static void launch_line(Ctx& c, int n, bool inv, int pro, const LineArgs& a, int
 
 // one x or y sweep.  axis: 0 = x, 1 = y.
 struct Sweep { int axis; bool inv; int pro; const double* in[4]; double add1, add3; double* out;
-               int scatter = -1; };   // >= 0: store straight into the peers' receive buffer `scatter` (peer memory)
+               int scatter = -1;      // >= 0: store straight into the peers' receive buffer `scatter` (peer memory)
+               // z-chunk range of this launch and the compact (L2-resident) intermediate of a chunked 2-D FFT:
+               int zc0 = 0, nzc = -1;            // chunks [zc0, zc0 + nzc) of pz/16 (nzc < 0: all)
+               int in_pitch = 0, out_pitch = 0;  // doubles per column of the input / output array (0: pz)
+               int in_zc0 = 0, out_zc0 = 0;      // chunk stored at offset 0 of the input / output array
+               int final_store = 1; };
 
 static void run_sweep(Ctx& c, const Sweep& s) {
     LineArgs a;
     a.in0 = s.in[0]; a.in1 = s.in[1]; a.in2 = s.in[2]; a.in3 = s.in[3];
     a.add1 = s.add1; a.add3 = s.add3;
     a.out = s.out;
-    a.nzc = c.pz / LINE_ZC;
+    a.nzc = (s.nzc < 0) ? c.pz / LINE_ZC : s.nzc;
+    a.zc0 = s.zc0; a.in_zc0 = s.in_zc0; a.out_zc0 = s.out_zc0; a.final_store = s.final_store;
+    const long long ipz = s.in_pitch ? s.in_pitch : c.pz, opz = s.out_pitch ? s.out_pitch : c.pz;
     a.tw = c.tw.p;
     int n, nouter;
     int lognyl = 0, lognxl = 0;
     while ((1 << lognyl) < c.nyl) ++lognyl;
     while ((1 << lognxl) < c.nxl) ++lognxl;
-    const long long nb = (long long)c.nxl * c.nyl * c.pz;
+    const long long nbi = (long long)c.nxl * c.nyl * ipz, nbo = (long long)c.nxl * c.nyl * opz;
     const int self = (s.scatter >= 0) ? c.rank : -1;
     for (int d = 0; d < 8; ++d) a.outp[d] = (s.scatter >= 0 && d < c.nranks) ? c.tr.peer_t2[s.scatter][d] : s.out;
     if (s.axis == 1) {
         n = c.ny; nouter = c.nxl;
         // physical side [xl][y][pz]; spectral side: P blocks [d][xl][kyl][pz] (== [kx][kyl][pz] after the exchange)
-        const long long pos = (long long)c.ny * c.pz, sos = (long long)c.nyl * c.pz;
-        a.in_os = s.inv ? sos : pos; a.out_os = s.inv ? pos : sos;
-        const RowMap phys{(long long)c.pz, 0, 0, n, 30, -1};
-        const RowMap spec_in{(long long)c.pz, nb, 1, n, lognyl, -1};
-        const RowMap spec_out{(long long)c.pz, nb, 1, n, lognyl, self};
-        a.in_map = s.inv ? spec_in : phys;
-        a.out_map = s.inv ? phys : spec_out;
+        a.in_os = (s.inv ? (long long)c.nyl : (long long)c.ny) * ipz;
+        a.out_os = (s.inv ? (long long)c.ny : (long long)c.nyl) * opz;
+        const RowMap phys_in{ipz, 0, 0, n, 30, -1}, phys_out{opz, 0, 0, n, 30, -1};
+        const RowMap spec_in{ipz, nbi, 1, n, lognyl, -1};
+        const RowMap spec_out{opz, nbo, 1, n, lognyl, self};
+        a.in_map = s.inv ? spec_in : phys_in;
+        a.out_map = s.inv ? phys_out : spec_out;
         a.kdiff = c.kyline.p;
     } else {
         n = c.nx; nouter = c.nyl;
-        a.in_os = c.pz; a.out_os = c.pz;
-        const RowMap xin{(long long)c.nyl * c.pz, 0, 0, n, 30, -1};
-        const RowMap xout{(long long)c.nyl * c.pz, nb, 0, n, lognxl, self};      // block d = x / nxl
+        a.in_os = ipz; a.out_os = opz;
+        const RowMap xin{(long long)c.nyl * ipz, 0, 0, n, 30, -1};
+        const RowMap xout{(long long)c.nyl * opz, nbo, 0, n, lognxl, self};      // block d = x / nxl
         a.in_map = xin; a.out_map = xout;
         a.kdiff = c.kxl.p;
     }
@@ -329,11 +337,29 @@ static void setup_p2p(Ctx& c) {
 // forward (fftxyp2s): first = y sweep, second = x sweep; inverse (fftxys2p): first = x, second = y.
 static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
     if (c.nranks == 1) {
+        const int nzc = c.pz / LINE_ZC, G = c.l2_chunks;
+        if (G <= 0 || G >= nzc) {
+            for (int i = 0; i < n; ++i) {
+                first[i].out = c.W[5].p;
+                run_sweep(c, first[i]);
+                second[i].in[0] = c.W[5].p;
+                run_sweep(c, second[i]);
+            }
+            return;
+        }
+        // L2-blocked: the two sweeps of a 2-D FFT run chunk by chunk (G z-chunks of 16 levels at a time) through
+        // a compact intermediate [row][row][16 G] that is rewritten every chunk and therefore stays in the
+        // 126 MB L2: one HBM read and one HBM write per 2-D FFT instead of two of each
         for (int i = 0; i < n; ++i) {
-            first[i].out = c.W[5].p;
-            run_sweep(c, first[i]);
-            second[i].in[0] = c.W[5].p;
-            run_sweep(c, second[i]);
+            for (int z0 = 0, k = 0; z0 < nzc; z0 += G, ++k) {
+                double* t = (k & 1) ? c.W[5].p + (size_t)c.nx * c.ny * LINE_ZC * G : c.W[5].p;
+                const int g = std::min(G, nzc - z0);
+                Sweep a = first[i], b = second[i];
+                a.out = t; a.zc0 = z0; a.nzc = g; a.out_pitch = LINE_ZC * G; a.out_zc0 = z0; a.final_store = 0;
+                b.in[0] = t; b.zc0 = z0; b.nzc = g; b.in_pitch = LINE_ZC * G; b.in_zc0 = z0;
+                run_sweep(c, a);
+                run_sweep(c, b);
+            }
         }
         return;
     }
@@ -517,6 +543,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     g_ctx = c;
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
+    c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
     c->nxl = nx / nranks; c->nyl = ny / nranks;
