@@ -102,7 +102,8 @@ int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, i
 int ps3d_cuda_download(int field_id, int comp, double* host);
 int ps3d_cuda_upload(int field_id, int comp, const double* host);
 /* out[0..2] = kinetic energy, enstrophy (field_diagnostics.f90:85,172), helicity
- * (plotting/nc_reader.py:94-101 trapezoid mean of u.omega); out[3..7] reserved */
+ * (plotting/nc_reader.py:94-101 trapezoid mean of u.omega); out[3..7] = horizontal / vertical kinetic energy,
+ * horizontal / vertical enstrophy, max horizontal enstrophy (field_diagnostics.f90:128,153,211,248,233) */
 int ps3d_cuda_diagnostics(double out[8]);
 
 /* ---- multi-rank transport ----

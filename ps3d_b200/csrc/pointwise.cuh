@@ -181,8 +181,9 @@ __global__ void k_vor_mean(double* svor0, double* svor1, const double* __restric
 }
 
 // ---- field reductions ------------------------------------------------------------
-enum { RQ_MAXW2 = 0, RQ_SUMW2, RQ_SUMW0, RQ_SUMW1, RQ_SUMW2C, RQ_MAXU, RQ_MAXV, RQ_MAXWV, RQ_SUMU2, RQ_SUMUW, RQ_N };
-constexpr unsigned RQ_OPMASK = (1u << RQ_MAXW2) | (1u << RQ_MAXU) | (1u << RQ_MAXV) | (1u << RQ_MAXWV);
+enum { RQ_MAXW2 = 0, RQ_SUMW2, RQ_SUMW0, RQ_SUMW1, RQ_SUMW2C, RQ_MAXU, RQ_MAXV, RQ_MAXWV, RQ_SUMU2, RQ_SUMUW,
+       RQ_SUMUH, RQ_SUMWH, RQ_MAXWH, RQ_N };
+constexpr unsigned RQ_OPMASK = (1u << RQ_MAXW2) | (1u << RQ_MAXU) | (1u << RQ_MAXV) | (1u << RQ_MAXWV) | (1u << RQ_MAXWH);
 
 struct FieldPtrs { const double* vor[3]; const double* vel[3]; };
 
@@ -206,6 +207,9 @@ __global__ void k_field_reduce(FieldPtrs f, long long ncol, int nz, int pz, doub
         acc[RQ_MAXU] = fmax(acc[RQ_MAXU], u); acc[RQ_MAXV] = fmax(acc[RQ_MAXV], v); acc[RQ_MAXWV] = fmax(acc[RQ_MAXWV], ww);
         acc[RQ_SUMU2] += w * (u * u + v * v + ww * ww);
         acc[RQ_SUMUW] += w * (u * a + v * b + ww * c);
+        acc[RQ_SUMUH] += w * (u * u + v * v);                          // field_diagnostics.f90:135-142
+        acc[RQ_SUMWH] += w * (a * a + b * b);                          // :215-222
+        acc[RQ_MAXWH] = fmax(acc[RQ_MAXWH], a * a + b * b);           // :237 (sqrt taken on the host)
     }
     for (int q = 0; q < RQ_N; ++q) {
         const double r = block_reduce(acc[q], (RQ_OPMASK >> q) & 1, red);
@@ -233,6 +237,24 @@ __global__ void k_char_vorticity(FieldPtrs f, long long ncol, int nz, int pz, do
     const double r1 = block_reduce(l1, 0, red);
     const double r2 = block_reduce(l2, 0, red);
     if (threadIdx.x == 0) { partial[blockIdx.x * 2] = r1; partial[blockIdx.x * 2 + 1] = r2; }
+}
+
+// right-hand side of the pressure Poisson equation (fields_derived.f90:97-113) from the five strain fields and omega
+struct StrainPtrsFwd;
+__global__ void k_pressure_rhs(const double* __restrict__ dudx, const double* __restrict__ dudy, const double* __restrict__ dvdy,
+                               const double* __restrict__ dwdx, const double* __restrict__ dwdy, const double* __restrict__ xi,
+                               const double* __restrict__ eta, const double* __restrict__ zeta, double* __restrict__ out,
+                               long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double ux = dudx[i], uy = dudy[i], vy = dvdy[i], wx = dwdx[i], wy = dwdy[i];
+        const double wz = -(ux + vy);
+        out[i] = 2.0 * (ux * vy - uy * (zeta[i] + uy) + vy * wz - wy * (wy - xi[i]) + wz * ux - wx * (wx + eta[i]));
+    }
+}
+
+__global__ void k_add(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] + b[i];
 }
 
 // ---- Jacobi eigenvalues of the symmetrised strain (jacobi.f90) -----------------

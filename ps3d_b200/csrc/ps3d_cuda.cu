@@ -925,6 +925,18 @@ static void do_step(Ctx& c, double* t, double dt) {
     }
 }
 
+// the five velocity-gradient fields of advance.f90:199-217 -> W[0..4] = du/dx, du/dy, dw/dx, dv/dy, dw/dy
+static void strain_fields(Ctx& c) {
+    const int comp[5] = {0, 0, 2, 1, 2};
+    const bool ddx_[5] = {true, false, true, false, false};
+    Sweep f[5], g[5];
+    for (int i = 0; i < 5; ++i) {
+        f[i] = sweep_plain(0, true, ddx_[i], c.svel[comp[i]].p, nullptr);
+        g[i] = sweep_plain(1, true, !ddx_[i], nullptr, c.W[i].p);
+    }
+    fft2d_batch(c, 5, f, g);
+}
+
 static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype, int win, double* dt_out, double* diag) {
     const long long ncol = (long long)c.nxl * c.ny;
     field_reduce(c);
@@ -943,16 +955,7 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
               (const double*)c.partial.p, RED_BLOCKS, 2, 0u, c.red.p);
     c.launches += 2;
     // velocity strain (advance.f90:199-217): derivative folded into the inverse sweeps
-    {
-        const int comp[5] = {0, 0, 2, 1, 2};                        // du/dx, du/dy, dw/dx, dv/dy, dw/dy
-        const bool ddx_[5] = {true, false, true, false, false};
-        Sweep f[5], g[5];
-        for (int i = 0; i < 5; ++i) {
-            f[i] = sweep_plain(0, true, ddx_[i], c.svel[comp[i]].p, nullptr);
-            g[i] = sweep_plain(1, true, !ddx_[i], nullptr, c.W[i].p);
-        }
-        fft2d_batch(c, 5, f, g);
-    }
+    strain_fields(c);
     StrainPtrs sp;
     sp.dudx = c.W[0].p; sp.dudy = c.W[1].p; sp.dwdx = c.W[2].p; sp.dvdy = c.W[3].p; sp.dwdy = c.W[4].p;
     for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
@@ -1014,7 +1017,28 @@ static void do_upload_vorticity(Ctx& c, const double* vor_phys) {
 }
 
 // pressure (fields_derived.f90:67-157), lazily: needs the five strain fields
-static void do_pressure(Ctx& c, double* out_dev) { (void)c; (void)out_dev; fail(PS3D_ERR_UNSUPPORTED, "pressure download not implemented yet"); }
+// pressure (fields_derived.f90:67-157), evaluated on demand from the current svel / vor -> W[0]
+static void do_pressure(Ctx& c) {
+    strain_fields(c);
+    const long long n = (long long)c.nint;
+    // W[0..4] = du/dx, du/dy, dw/dx, dv/dy, dw/dy
+    PS_LAUNCH((k_pressure_rhs), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.W[0].p,
+              (const double*)c.W[1].p, (const double*)c.W[3].p, (const double*)c.W[2].p, (const double*)c.W[4].p,
+              (const double*)c.vor[0].p, (const double*)c.vor[1].p, (const double*)c.vor[2].p, c.W[0].p, n);
+    ++c.launches;
+    fft2d_fwd(c, c.W[0].p, c.W[1].p);
+    launch_zop(c, ZOP_POISSON, c.W[1].p, c.W[2].p);
+    fft2d_inv(c, c.W[2].p, c.W[0].p, false, false);
+}
+
+// horizontal_divergence (fields_derived.f90:161-182): delta = u_x + v_y -> W[0]
+static void do_delta(Ctx& c) {
+    fft2d_inv(c, c.svel[0].p, c.W[0].p, true, false);
+    fft2d_inv(c, c.svel[1].p, c.W[1].p, false, true);
+    PS_LAUNCH((k_add), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.W[0].p, (const double*)c.W[1].p,
+              c.W[0].p, (long long)c.nint);
+    ++c.launches;
+}
 
 }  // namespace ps3d
 
@@ -1166,13 +1190,10 @@ int ps3d_cuda_download(int field_id, int comp, double* host) {
     Ctx& c = ready();
     if (!host) fail(PS3D_ERR_BAD_ARGUMENT, "host pointer is null");
     if (field_id == PS3D_F_PRES || field_id == PS3D_F_DELTA) {
-        if (field_id == PS3D_F_DELTA) {
-            // horizontal_divergence (fields_derived.f90:161-182): delta = u_x + v_y
-            fft2d_inv(c, c.svel[0].p, c.W[0].p, true, false);
-            fft2d_inv(c, c.svel[1].p, c.W[1].p, false, true);
-            fail(PS3D_ERR_UNSUPPORTED, "delta download not implemented yet");
-        }
-        do_pressure(c, c.W[0].p);
+        // output-only quantities of adapt (advance.f90:278-282), evaluated lazily at output cadence
+        if (field_id == PS3D_F_DELTA) do_delta(c); else do_pressure(c);
+        to_host(c, c.W[0].p, host, false);
+        return PS3D_OK;
     }
     bool spectral = false;
     DevBuf<double>* f = field_by_id(c, field_id, spectral);
@@ -1205,6 +1226,11 @@ int ps3d_cuda_diagnostics(double out[8]) {
     out[0] = 0.5 * c.h_red[RQ_SUMU2] * ncelli;      // field_diagnostics.f90:93-103
     out[1] = 0.5 * c.h_red[RQ_SUMW2] * ncelli;      // :177-187
     out[2] = c.h_red[RQ_SUMUW] * ncelli;            // plotting/plot_vor_vel_he_evolution.py:62-65
+    out[3] = 0.5 * c.h_red[RQ_SUMUH] * ncelli;      // get_horizontal_kinetic_energy (field_diagnostics.f90:128)
+    out[4] = out[0] - out[3];                       // get_vertical_kinetic_energy (:153)
+    out[5] = 0.5 * c.h_red[RQ_SUMWH] * ncelli;      // get_horizontal_enstrophy (:211)
+    out[6] = out[1] - out[5];                       // get_vertical_enstrophy (:248)
+    out[7] = std::sqrt(c.h_red[RQ_MAXWH]);          // get_max_horizontal_enstrophy (:233)
     PS_API_END
 }
 

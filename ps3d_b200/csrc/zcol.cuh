@@ -405,7 +405,7 @@ __device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int ki
 // module procedures fftsine, fftcosine, diffx, diffy, central_diffz,
 // field_combine_semi_spectral, field_decompose_semi_spectral).
 // ---------------------------------------------------------------------------
-enum { ZOP_SINE = 0, ZOP_COSINE, ZOP_COMBINE, ZOP_DECOMPOSE, ZOP_DIFFZ, ZOP_DIFFX, ZOP_DIFFY };
+enum { ZOP_SINE = 0, ZOP_COSINE, ZOP_COMBINE, ZOP_DECOMPOSE, ZOP_DIFFZ, ZOP_DIFFX, ZOP_DIFFY, ZOP_POISSON };
 
 template <int NZ>
 constexpr size_t zop_smem_bytes() { return (size_t)(ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
@@ -465,7 +465,23 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         }
         return;
     }
-    xform2<NZ>(X, (op == ZOP_COSINE) ? XF_DCT : XF_DST, nullptr, XF_DST, scr, g);
+    xform2<NZ>(X, (op == ZOP_COSINE || op == ZOP_POISSON) ? XF_DCT : XF_DST, nullptr, XF_DST, scr, g);
+    if (op == ZOP_POISSON) {
+        // pressure Poisson solve between two cosine transforms (fields_derived.f90:125-148):
+        // rs <- green * rs with green(kz) = -1/(k^2+l^2+rkz^2), green(0) = -1/(k^2+l^2) (inversion_utils.f90:283-288)
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            Row4 x = row_load_s<NZ>(X, z);
+            const double rk = __ldg(&g.rkz[z]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x.v[s] *= (z == 0) ? -r.k2i[s & 1] : -1.0 / (r.k2[s & 1] + rk * rk);
+            row_store_s<NZ>(X, z, x);
+        }
+        __syncthreads();
+        xform2<NZ>(X, XF_DCT, nullptr, XF_DST, scr, g);
+    }
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);

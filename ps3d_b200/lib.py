@@ -200,6 +200,9 @@ class PS3DLib:
         self._call("ps3d_cuda_download", FIELD[field], comp, _ptr(out))
         return out
 
+    def pressure(self): return self.download("pres")
+    def horizontal_divergence(self): return self.download("delta")
+
     def download3(self, field):
         return np.stack([self.download(field, c) for c in range(3)])
 
@@ -210,7 +213,7 @@ class PS3DLib:
     def diagnostics(self):
         out = np.zeros(8)
         self._call("ps3d_cuda_diagnostics", _ptr(out))
-        return dict(ke=out[0], en=out[1], helicity=out[2])
+        return dict(ke=out[0], en=out[1], helicity=out[2], hke=out[3], vke=out[4], hen=out[5], ven=out[6], hemax=out[7])
 
     def kernel_launches(self): return int(self.dll.ps3d_cuda_kernel_launches())
     def last_advance_ms(self): return float(self.dll.ps3d_cuda_last_advance_ms())

@@ -64,9 +64,17 @@ def test_time_step(grid, stepper):
     assert d["ke"] == pytest.approx(s.get_kinetic_energy(), rel=1e-13)
     assert d["en"] == pytest.approx(s.get_enstrophy(), rel=1e-13)
     assert d["helicity"] == pytest.approx(s.get_helicity(), rel=1e-11, abs=1e-16)
+    hke = 0.5 * s._trap(s.vel[0] ** 2 + s.vel[1] ** 2) * s.ncelli           # field_diagnostics.f90:128-148
+    hen = 0.5 * s._trap(s.vor[0] ** 2 + s.vor[1] ** 2) * s.ncelli           # :211-228
+    assert d["hke"] == pytest.approx(hke, rel=1e-13) and d["vke"] == pytest.approx(s.get_kinetic_energy() - hke, rel=1e-11)
+    assert d["hen"] == pytest.approx(hen, rel=1e-13) and d["ven"] == pytest.approx(s.get_enstrophy() - hen, rel=1e-11)
+    assert d["hemax"] == pytest.approx(np.sqrt(np.max(s.vor[0] ** 2 + s.vor[1] ** 2)), rel=1e-13)
     lib.source()
     s.source()
     assert rel(lib.download3("svorts"), s.svorts) < TOL
+    # output-only fields of adapt, evaluated lazily (fields_derived.f90:67-182)
+    assert rel(lib.pressure(), s.pressure(*s.strain_fields())) < TOL
+    assert rel(lib.horizontal_divergence(), s.horizontal_divergence()) < TOL
     lib.init_diffusion(d["ke"], d["en"])
     lib.stepper_setup(stepper)
     t, dt, diag = lib.advance(0.0, 100.0)

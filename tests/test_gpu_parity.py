@@ -126,6 +126,8 @@ def test_vor2vel_source_white_noise_64(lib, filtering):
         lib.source()
         s.source()
         assert rel(lib.download3("svorts"), s.svorts) < FIELD_TOL
+        assert rel(lib.pressure(), s.pressure(*s.strain_fields())) < FIELD_TOL          # fields_derived.f90:67
+        assert rel(lib.horizontal_divergence(), s.horizontal_divergence()) < FIELD_TOL   # fields_derived.f90:161
         d = lib.diagnostics()
         assert d["ke"] == pytest.approx(s.get_kinetic_energy(), rel=1e-13)
         assert d["en"] == pytest.approx(s.get_enstrophy(), rel=1e-13)
@@ -242,3 +244,25 @@ def test_multi_gpu_slab_matches_oracle(nranks):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("worst") == nranks
+
+
+def test_cpp_driver_matches_oracle(lib):
+    """examples/ps3d_driver.cpp (C++ stand-in for ps3d.f90) through the same C ABI: 5 cn2 steps of Beltrami 32^3."""
+    import os
+    import re
+    import subprocess
+    import __graft_entry__ as G
+    exe = G.build_driver()
+    out = subprocess.run([exe, "--n", "32", "--steps", "5"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = O.beltrami_setup(32)
+    t = 0.0
+    dts = []
+    for _ in range(5):
+        t, dt = ref.advance(t, 100.0, "cn2", literal=True)
+        dts.append(dt)
+    got = [float(m) for m in re.findall(r"and time step\s+(\S+)", out.stdout)]
+    assert len(got) == 5 and all(g == pytest.approx(r, rel=1e-12) for g, r in zip(got, dts))
+    ref.vor2vel()
+    ke = float(re.search(r"ke (\S+)", out.stdout).group(1))
+    assert ke == pytest.approx(ref.get_kinetic_energy(), rel=1e-12)
