@@ -60,7 +60,8 @@ struct LineArgs {
     double* outp[8];          // peer-memory scatter: base of rank d's receive buffer (all = out otherwise)
     long long in_os, out_os;  // stride between consecutive outer lines (doubles)
     RowMap in_map, out_map;   // offset of row k from the tile base
-    int nzc;                  // z-chunks handled by this launch (tiles = outer lines x nzc)
+    int ntiles;               // tiles of this launch (outer lines x nzc); a block loops over tiles blockIdx.x, +gridDim.x, ...
+    int nzc;                  // z-chunks handled by this launch
     int zc0;                  // first z-chunk of this launch
     int in_zc0, out_zc0;      // z-chunk held at offset 0 of the input / output array (0 for full arrays; = zc0 for
                               // the compact, L2-resident intermediate of a chunked 2-D FFT)
@@ -90,7 +91,8 @@ template <int N, int PRO>
 __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_fwd(LineArgs a) {
     PS_SMEM(double, sm);
     const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
-    const int o = blockIdx.x / a.nzc, zc = a.zc0 + (blockIdx.x - o * a.nzc);
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
     const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
     double vr[8], vi[8];
 #pragma unroll
@@ -135,13 +137,16 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
             st2f(a.final_store, row_dst(a, N - k) + obase, (q - s) * hs, (r - p) * hs);   // Im A, Im B
         }
     }
+    __syncthreads();          // scratch is reused by the next tile of a persistent launch
+    }
 }
 
 template <int N, int PRO>
 __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_inv(LineArgs a) {
     PS_SMEM(double, sm);
     const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
-    const int o = blockIdx.x / a.nzc, zc = a.zc0 + (blockIdx.x - o * a.nzc);
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
     const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
     double* sre = sm;
     double* sim = sm + LINE_NF * N;
@@ -189,6 +194,8 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
 #pragma unroll
     for (int e = 0; e < 8; ++e)
         st2f(a.final_store, row_dst(a, u + e * (N / 8)) + obase, vr[e] * sc, vi[e] * sc);
+    __syncthreads();          // scratch is reused by the next tile of a persistent launch
+    }
 }
 
 template <int N>

@@ -97,6 +97,7 @@ struct Ctx {
     double vvisc = 0.0;
     RollingMean rollmean;
     long long launches = 0;
+    int num_sms = 148;
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
@@ -161,22 +162,22 @@ static void allow_smem(K, size_t) {}
 #define PS_FOR_Z_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
 
 template <int N>
-static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles) {
+static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
     const size_t sm = line_smem_bytes<N>();
-    const dim3 grid(ntiles), block(N);
+    const dim3 grid(max_ctas > 0 ? std::min(ntiles, max_ctas) : ntiles), block(N);
     if (!inv) {
-        if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS>), grid, block, sm, c.stream, a); }
-        else { allow_smem(k_line_fwd<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN>), grid, block, sm, c.stream, a); }
+        if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS>), grid, block, sm, stream, a); }
+        else { allow_smem(k_line_fwd<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN>), grid, block, sm, stream, a); }
     } else {
-        if (pro == PRO_DIFF) { allow_smem(k_line_inv<N, PRO_DIFF>, sm); PS_LAUNCH((k_line_inv<N, PRO_DIFF>), grid, block, sm, c.stream, a); }
-        else { allow_smem(k_line_inv<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_inv<N, PRO_PLAIN>), grid, block, sm, c.stream, a); }
+        if (pro == PRO_DIFF) { allow_smem(k_line_inv<N, PRO_DIFF>, sm); PS_LAUNCH((k_line_inv<N, PRO_DIFF>), grid, block, sm, stream, a); }
+        else { allow_smem(k_line_inv<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_inv<N, PRO_PLAIN>), grid, block, sm, stream, a); }
     }
     ++c.launches;
 }
 
-static void launch_line(Ctx& c, int n, bool inv, int pro, const LineArgs& a, int ntiles) {
+static void launch_line(Ctx& c, int n, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
     switch (n) {
-#define X(NN) case NN: launch_line_n<NN>(c, inv, pro, a, ntiles); break;
+#define X(NN) case NN: launch_line_n<NN>(c, inv, pro, a, ntiles, stream, max_ctas); break;
         PS_FOR_LINE_SIZES(X)
 #undef X
         default: fail(PS3D_ERR_UNSUPPORTED_SIZE, "line length %d not supported (power of two, 8..1024)", n);
@@ -190,7 +191,9 @@ struct Sweep { int axis; bool inv; int pro; const double* in[4]; double add1, ad
                int zc0 = 0, nzc = -1;            // chunks [zc0, zc0 + nzc) of pz/16 (nzc < 0: all)
                int in_pitch = 0, out_pitch = 0;  // doubles per column of the input / output array (0: pz)
                int in_zc0 = 0, out_zc0 = 0;      // chunk stored at offset 0 of the input / output array
-               int final_store = 1; };
+               int final_store = 1;
+               bool on_comm_stream = false;      // launch on the communication stream (peer-memory scatter sweeps)
+               int max_ctas = 0; };              // > 0: persistent launch with at most this many blocks
 
 static void run_sweep(Ctx& c, const Sweep& s) {
     LineArgs a;
@@ -229,7 +232,8 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     }
     a.scale = 1.0 / std::sqrt((double)n);
     a.twscale = c.ntw / n;
-    launch_line(c, n, s.inv, s.pro, a, nouter * a.nzc);
+    a.ntiles = nouter * a.nzc;
+    launch_line(c, n, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
 }
 
 // ---- slab exchange: P equal contiguous blocks, block d of `send` goes to rank d and lands as block
@@ -287,8 +291,8 @@ static void allreduce_host(Ctx& c, double* vals, int n, unsigned opmask) {
 
 #ifndef PS3D_EMU
 // all ranks' preceding work on the compute stream is complete (and its peer stores visible) before any rank continues
-static void cross_rank_barrier(Ctx& c) {
-    const int rc = c.tr.nccl.AllReduce(c.redM.p + 32, c.redM.p + 32, 1, NcclApi::kFloat64, NcclApi::kSum, c.tr.comm, (void*)c.stream);
+static void cross_rank_barrier(Ctx& c, ps_stream_t stream) {
+    const int rc = c.tr.nccl.AllReduce(c.redM.p + 32, c.redM.p + 32, 1, NcclApi::kFloat64, NcclApi::kSum, c.tr.comm, (void*)stream);
     if (rc != 0) fail(PS3D_ERR_DEVICE, "NCCL barrier failed: %s", c.tr.nccl.GetErrorString(rc));
 }
 
@@ -371,16 +375,29 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
         // receive buffer over NVLink (peer memory), a cross-rank barrier, then the second sweep.  Two
         // receive buffers; the barrier of field i+1 orders the reuse of buffer i&1 (peers enter it only
         // after their second sweep of field i), the barrier at batch start orders reuse across batches.
-        cross_rank_barrier(c);
+        // two streams: B (comm_stream) runs the NVLink-bound scatter sweeps as persistent launches with one
+        // block per SM and the barriers, A (stream) the HBM-bound second sweeps in the SM slots left free, so
+        // the scatter of field i+1 overlaps the second sweep of field i.
+        //   B: s1(i) ; wait[A: s2(i-1) done] ; barrier(i)         A: wait[B: barrier(i)] ; s2(i)
+        // s1(i+1) writes the peers' buffer (i+1)&1, last read by their s2(i-1): they enter barrier(i) only after it.
+        PS_CUDA_TRY(cudaEventRecord(c.ev_first[0], c.stream));
+        PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_first[0], 0));
+        cross_rank_barrier(c, c.comm_stream);
         for (int i = 0; i < n; ++i) {
             first[i].out = t2[i & 1];
             first[i].scatter = i & 1;
+            first[i].on_comm_stream = true;
+            first[i].max_ctas = c.num_sms;
             run_sweep(c, first[i]);
             ++c.tr.n_alltoall;
             c.tr.bytes_sent += (double)c.nxl * c.nyl * c.pz * 8.0 * (c.nranks - 1);
-            cross_rank_barrier(c);
+            if (i >= 1) PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_second[i - 1], 0));
+            cross_rank_barrier(c, c.comm_stream);
+            PS_CUDA_TRY(cudaEventRecord(c.ev_a2a[i], c.comm_stream));
+            PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_a2a[i], 0));
             second[i].in[0] = t2[i & 1];
             run_sweep(c, second[i]);
+            PS_CUDA_TRY(cudaEventRecord(c.ev_second[i], c.stream));
         }
         return;
     }
@@ -556,7 +573,16 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->nint = (size_t)c->nxl * ny * c->pz;
     c->nnat = (size_t)c->nxl * ny * c->nzp;
 #ifndef PS3D_EMU
-    PS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        PS_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PS_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+        cudaDeviceProp prop;
+        int dev = 0;
+        PS_CUDA_TRY(cudaGetDevice(&dev));
+        PS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        c->num_sms = prop.multiProcessorCount;
+    }
     PS_CUDA_TRY(cudaEventCreate(&c->ev0));
     PS_CUDA_TRY(cudaEventCreate(&c->ev1));
     PS_CUDA_TRY(cudaMallocHost((void**)&c->h_red, 64 * sizeof(double)));
@@ -566,7 +592,11 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->tr.rank = rank; c->tr.nranks = nranks;
 #ifndef PS3D_EMU
     if (nranks > 1) {
-        PS_CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        {
+            int lo = 0, hi = 0;
+            PS_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            PS_CUDA_TRY(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, lo));
+        }
         for (int i = 0; i < 8; ++i) {
             PS_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_first[i], cudaEventDisableTiming));
             PS_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_a2a[i], cudaEventDisableTiming));
