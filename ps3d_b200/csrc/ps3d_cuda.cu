@@ -98,6 +98,7 @@ struct Ctx {
     RollingMean rollmean;
     long long launches = 0;
     int num_sms = 148;
+    int p2p_ctas_per_sm = 2;             // PS3D_P2P_CTAS: blocks per SM of the persistent scatter sweeps (0 = full grid)
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
@@ -387,7 +388,7 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
             first[i].out = t2[i & 1];
             first[i].scatter = i & 1;
             first[i].on_comm_stream = true;
-            first[i].max_ctas = c.num_sms;
+            first[i].max_ctas = c.p2p_ctas_per_sm * c.num_sms;      // 0: full grid
             run_sweep(c, first[i]);
             ++c.tr.n_alltoall;
             c.tr.bytes_sent += (double)c.nxl * c.nyl * c.pz * 8.0 * (c.nranks - 1);
@@ -561,6 +562,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
+    c->p2p_ctas_per_sm = getenv("PS3D_P2P_CTAS") ? atoi(getenv("PS3D_P2P_CTAS")) : 2;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
     c->nxl = nx / nranks; c->nyl = ny / nranks;
