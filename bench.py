@@ -218,8 +218,16 @@ def main():
     dom = max(share, key=share.get)
     if dom == "line_sweeps":
         dom = "line_fwd_y"
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command (per launch),
+    # only quoted for the configuration it was captured on
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01g_ncu_kernels.json")
+    if os.path.exists(tpath) and n == 512 and world == 1:
+        t = json.load(open(tpath)).get(dom if dom in ("vor2vel_columns", "source_columns") else "line_fwd_y")
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["GBs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom]["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"]}
     step_bytes = SWEEPS[args.stepper] * 16 * n * n * (n + 1)   # whole job, peak = P x one GPU
     value = n ** 3 / (ms_step * 1e-3)                      # whole job: the grid is split over the ranks
