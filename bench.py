@@ -151,7 +151,7 @@ def main():
         nccl_id = box[0]
     solver = host.Solver(lib, n, n, n, lower, extent, stepper=args.stepper, rank=rank, nranks=world, nccl_id=nccl_id)
     nxl = n // world
-    vor_np = host.beltrami_vorticity(n, n, n, lower, extent)[:, rank * nxl:(rank + 1) * nxl].copy()
+    vor_np = host.beltrami_vorticity(n, n, n, lower, extent, x0=rank * nxl, x1=(rank + 1) * nxl)
     vor_pinned = torch.from_numpy(vor_np).pin_memory()
     vor_host = vor_pinned.numpy()
     solver.setup_fields(vor_host)

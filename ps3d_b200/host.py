@@ -13,20 +13,21 @@ import math
 import numpy as np
 
 
-def beltrami_vorticity(nx, ny, nz, lower, extent, k=2, l=2, m=1):
-    """Initial condition of examples/beltrami*.nml (beltrami.f90:141-181)."""
+def beltrami_vorticity(nx, ny, nz, lower, extent, k=2, l=2, m=1, x0=0, x1=None):
+    """Initial condition of examples/beltrami*.nml (beltrami.f90:141-181); x0:x1 selects an x-slab."""
     lower = np.asarray(lower, dtype=np.float64)
     extent = np.asarray(extent, dtype=np.float64)
     dx = extent / np.array([nx, ny, nz], dtype=np.float64)
     kk, ll, mm = float(k), float(l), float(m)
     alpha = math.sqrt(kk ** 2 + ll ** 2 + mm ** 2)
     fk2l2 = alpha / float(k ** 2 + l ** 2)
-    x = (lower[0] + dx[0] * np.arange(nx))[:, None, None]
+    x1 = nx if x1 is None else x1
+    x = (lower[0] + dx[0] * np.arange(x0, x1))[:, None, None]
     y = (lower[1] + dx[1] * np.arange(ny))[None, :, None]
     z = (lower[2] + dx[2] * np.arange(nz + 1))[None, None, :]
     cosmz, sinmz = np.cos(mm * z), np.sin(mm * z)
     s, c = np.sin(kk * x + ll * y), np.cos(kk * x + ll * y)
-    vor = np.empty((3, nx, ny, nz + 1))
+    vor = np.empty((3, x1 - x0, ny, nz + 1))
     vor[0] = fk2l2 * (kk * mm * sinmz - ll * alpha * cosmz) * s
     vor[1] = fk2l2 * (ll * mm * sinmz + kk * alpha * cosmz) * s
     vor[2] = alpha * cosmz * c
