@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=512, help="grid size (nx = ny = nz)")
+    ap.add_argument("--grid", "--n", dest="n", type=int, default=512, help="grid size (nx = ny = nz)")
     ap.add_argument("--stepper", default="cn2")
     ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
