@@ -85,6 +85,27 @@ def test_time_step(grid, stepper):
     assert rel(lib.download3("svor"), s.svor) < TOL
 
 
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_separate_entry_points_equal_advance(grid, stepper):
+    """vor2vel / adapt / source / step called one by one (the reference's module procedures) give the same step as
+    ps3d_cuda_advance (which folds the first stepper update into the source kernel)."""
+    lib, s, rng = grid
+    vor = rng.uniform(-1, 1, (3, s.nx, s.ny, s.nz + 1))
+    s.set_vorticity(vor)
+    lib.upload_vorticity(vor)
+    lib.vor2vel()
+    d = lib.diagnostics()
+    lib.init_diffusion(d["ke"], d["en"])
+    lib.stepper_setup(stepper)
+    lib.vor2vel()                                   # advance.f90:85
+    dt, diag = lib.adapt(0.0, 100.0)                # :88 (sets the diffusion operator)
+    lib.source()                                    # :95
+    t = lib.step(0.0, dt)                           # :102
+    to, dto = s.advance(0.0, 100.0, stepper, literal=True)
+    assert dt == pytest.approx(dto, rel=1e-13) and t == pytest.approx(to, rel=1e-13)
+    assert rel(lib.download3("svor"), s.svor) < TOL
+
+
 def test_error_paths(emu):
     with pytest.raises(PS3DError) as e:
         emu.vor2vel()

@@ -201,6 +201,25 @@ def test_per_step_error_resynchronised(lib, stepper):
         s.close()
 
 
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_separate_entry_points_equal_advance(lib, stepper):
+    """vor2vel / adapt / source / step called one by one (the reference's module procedures, advance.f90:85-102)
+    give the same step as ps3d_cuda_advance."""
+    from ps3d_b200 import host
+    ref = O.beltrami_setup(32)
+    s = host.beltrami_solver(lib, 32, stepper=stepper)
+    try:
+        lib.vor2vel()
+        dt, diag = lib.adapt(0.0, 100.0)
+        lib.source()
+        t = lib.step(0.0, dt)
+        to, dto = ref.advance(0.0, 100.0, stepper, literal=True)
+        assert dt == pytest.approx(dto, rel=1e-12) and t == pytest.approx(to, rel=1e-12)
+        assert rel(lib.download3("svor"), ref.svor) < FIELD_TOL
+    finally:
+        s.close()
+
+
 def test_full_size_properties_256(lib):
     """Properties that need no oracle at 256^3: inverse(forward) = identity, DST/DCT are
     self-inverse, linearity, combine/decompose are mutual inverses, Parseval for the packed FFT."""
