@@ -833,7 +833,7 @@ static void do_vor2vel(Ctx& c) {
     fft2d_batch(c, 6, f, g);
 }
 
-static void do_source(Ctx& c, const StepFuse* fuse = nullptr) {
+static void do_source(Ctx& c) {
     const double fc[3] = {0.0, 0.0, 0.0};    // physics.f90 f_cor: zero for the configurations in scope
     const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
     const double *xi = c.vor[0].p, *eta = c.vor[1].p, *zeta = c.vor[2].p;
@@ -847,7 +847,6 @@ static void do_source(Ctx& c, const StepFuse* fuse = nullptr) {
     SrcArgs a;
     a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
     a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
-    if (fuse) a.st = *fuse; else a.st.mode = 0;
     launch_src(c, a);
 }
 
@@ -926,62 +925,36 @@ static void rk4_update(Ctx& c, int stage, double c1, double c2, const double* pq
     ++c.launches;
 }
 
-static StepFuse step_fuse(Ctx& c, int stage, double c1, double c2, const double* pq) {
-    StepFuse f;
-    f.mode = (c.stepper == PS3D_STEPPER_CN2) ? 1 : 2;
-    f.stage = stage; f.c1 = c1; f.c2 = c2;
-    for (int i = 0; i < 3; ++i) { f.svor[i] = c.svor[i].p; f.wa[i] = c.wa[i].p; f.wb[i] = c.wb[i].p; }
-    f.f2d = c.fac2.p; f.filtz = c.filtz.p; f.vd = c.fac1.p; f.mq = c.fac1.p; f.pq = pq;
-    return f;
-}
-
-static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 / epq = epq**2 (impl_rk4.f90:151,185)
-    const long long ncol = (long long)c.nx * c.nyl;
-    PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, mode, 0.0, (const double*)nullptr,
-              (const double*)nullptr, c.fac1.p, c.fac2.p, ncol);
-    ++c.launches;
-}
-
-// source for the current state with the first stepper update folded into its store (advance.f90:95,102)
-static void do_source_first_update(Ctx& c, double dt) {
-    if (c.stepper == PS3D_STEPPER_CN2) {
-        const StepFuse f = step_fuse(c, 0, 0.5 * dt, 0.0, nullptr);       // cn2.f90:120-135
-        do_source(c, &f);
-        vor_mean(c, 1);                                                   // :137
-    } else {
-        const StepFuse f = step_fuse(c, 1, 0.5 * dt, dt / 6.0, c.filt2d.p);   // impl_rk4.f90:107-113, :227-229
-        do_source(c, &f);
-    }
-}
-
-// `first_done`: the first update (cn2.f90:120-137 / impl_rk4 substep one) was already applied by
-// do_source_first_update; otherwise it is applied here by the stand-alone update kernels.
-static void do_step(Ctx& c, double* t, double dt, bool first_done) {
+static void do_step(Ctx& c, double* t, double dt) {
     if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
+    const long long ncol = (long long)c.nx * c.nyl;
     if (c.stepper == PS3D_STEPPER_CN2) {
         const double dt2 = 0.5 * dt;                       // cn2.f90:101
-        if (!first_done) cn2_update(c, dt2, 0);            // :120-137
+        cn2_update(c, dt2, 0);                             // :120-137
         for (int iter = 0; iter < 2; ++iter) {             // niter = 2 (:34, :143-177)
             do_vor2vel(c);
-            const StepFuse f = step_fuse(c, 1, dt2, 0.0, nullptr);
-            do_source(c, &f);                              // source + update (:148-173)
-            vor_mean(c, 1);                                // :175
+            do_source(c);
+            cn2_update(c, dt2, 1);
         }
         *t += dt;
     } else {
         const double dt2 = 0.5 * dt, dt3 = dt / 3.0, dt6 = dt / 6.0;   // impl_rk4.f90:82-84
         // substep one filters the source with filt(0,:,:) (:227-229)
-        if (!first_done) rk4_update(c, 1, dt2, dt6, c.filt2d.p);
-        do_vor2vel(c);
-        { const StepFuse f = step_fuse(c, 2, dt2, dt3, c.fac2.p); do_source(c, &f); }    // :117-140
+        rk4_update(c, 1, dt2, dt6, c.filt2d.p);
+        do_vor2vel(c); do_source(c);
         *t += dt2;
-        do_vor2vel(c);
-        square_factor(c, 2);                                                              // :151
-        { const StepFuse f = step_fuse(c, 3, dt, dt3, c.fac2.p); do_source(c, &f); }     // :144-174
+        rk4_update(c, 2, dt2, dt3, c.fac2.p);
+        do_vor2vel(c); do_source(c);
         *t += dt2;
-        do_vor2vel(c);
-        square_factor(c, 3);                                                              // :185
-        { const StepFuse f = step_fuse(c, 4, dt6, 0.0, c.fac2.p); do_source(c, &f); }    // :179-203
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 2, 0.0, (const double*)nullptr,
+                  (const double*)nullptr, c.fac1.p, c.fac2.p, ncol);    // emq = emq**2 (:151)
+        ++c.launches;
+        rk4_update(c, 3, dt, dt3, c.fac2.p);
+        do_vor2vel(c); do_source(c);
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 3, 0.0, (const double*)nullptr,
+                  (const double*)nullptr, c.fac1.p, c.fac2.p, ncol);    // epq = epq**2 (:185)
+        ++c.launches;
+        rk4_update(c, 4, dt6, 0.0, c.fac2.p);
         vor_mean(c, 1);                                    // :205
     }
 }
@@ -1206,7 +1179,7 @@ int ps3d_cuda_adapt(double t, double t_limit, double alpha, int pretype_id, int 
 
 int ps3d_cuda_stepper_setup(int stepper_id) { PS_API_BEGIN do_stepper_setup(ready(), stepper_id); PS_API_END }
 int ps3d_cuda_set_diffusion(double dt, double pref) { PS_API_BEGIN Ctx& c = ready(); do_set_diffusion(c, dt, pref); ps_sync(c.stream); PS_API_END }
-int ps3d_cuda_step(double* t, double dt) { PS_API_BEGIN Ctx& c = ready(); if (!t) fail(PS3D_ERR_BAD_ARGUMENT, "t is null"); do_step(c, t, dt, false); ps_sync(c.stream); PS_API_END }
+int ps3d_cuda_step(double* t, double dt) { PS_API_BEGIN Ctx& c = ready(); if (!t) fail(PS3D_ERR_BAD_ARGUMENT, "t is null"); do_step(c, t, dt); ps_sync(c.stream); PS_API_END }
 
 int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, int win, double* dt_out, double diag_out[16]) {
     PS_API_BEGIN
@@ -1220,8 +1193,8 @@ int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, i
     double dt = 0.0;
     do_vor2vel(c);                                     // advance.f90:85
     do_adapt(c, *t, t_limit, alpha, pretype_id, win, &dt, diag_out);   // :88
-    do_source_first_update(c, dt);                     // :95 + the first update of :102
-    do_step(c, t, dt, true);                           // :102
+    do_source(c);                                      // :95
+    do_step(c, t, dt);                                 // :102
 #ifndef PS3D_EMU
     PS_CUDA_TRY(cudaEventRecord(c.ev1, c.stream));
     PS_CUDA_TRY(cudaEventSynchronize(c.ev1));
@@ -1339,7 +1312,7 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
             case 5: {
                 SrcArgs a;
                 a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
-                a.s0 = c.W[3].p; a.s1 = c.W[4].p; a.s2 = c.W[5].p; a.st.mode = 0;
+                a.s0 = c.W[3].p; a.s1 = c.W[4].p; a.s2 = c.W[5].p;
                 launch_src(c, a);
                 break;
             }

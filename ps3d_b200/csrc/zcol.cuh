@@ -75,7 +75,6 @@ struct Grp {
     double kx, ky;      // diff wavenumbers
     double k2[2], k2i[2];
     long long off[4];   // column offsets (doubles) of slots s = 2*sx + sy
-    long long col[4];   // column index kx*nyl + kyl of the slots (per-column tables of the steppers)
 };
 
 __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
@@ -93,10 +92,8 @@ __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
         const int kyl = 2 * r.ap + sy;
         r.k2[sy] = __ldg(&g.k2l2[(long long)r.b * g.nyl + kyl]);
         r.k2i[sy] = __ldg(&g.k2l2i[(long long)r.b * g.nyl + kyl]);
-        r.col[sy] = (long long)r.b * g.nyl + kyl;
-        r.col[2 + sy] = (long long)kxm * g.nyl + kyl;
-        r.off[sy] = r.col[sy] * g.pz;
-        r.off[2 + sy] = r.col[2 + sy] * g.pz;
+        r.off[sy] = ((long long)r.b * g.nyl + kyl) * g.pz;
+        r.off[2 + sy] = ((long long)kxm * g.nyl + kyl) * g.pz;
     }
     return r;
 }
@@ -758,64 +755,10 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 template <int NZ>
 constexpr size_t src_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
-// Time-stepper update folded into the store of the source (the reference's pointwise stage between
-// `source` and the next `vor2vel`): cn2.f90:120-135,162-173 / impl_rk4.f90:212-364 with the
-// combine -> x c(ky,kx) -> decompose pairs collapsed (identity a11).  Same arithmetic as k_cn2_update /
-// k_rk4_update in pointwise.cuh, which remain for the separate ps3d_cuda_step entry point.
-struct StepFuse {
-    int mode;                 // 0 = none, 1 = cn2, 2 = impl-diff-rk4
-    int stage;                // cn2: 0 = first update (defines vortsm), 1 = iteration.  rk4: substep 1..4
-    double c1, c2;
-    double* svor[3];
-    double* wa[3];            // cn2: vortsm      rk4: svori
-    double* wb[3];            // rk4: svorf
-    const double* f2d;        // cn2: vdiss*filt2d per column
-    const double* filtz;      // cn2: z part of the filter
-    const double* vd;         // cn2: vdiss per column ((0,0) column: filt = 1)
-    const double* mq;         // rk4: emq per column
-    const double* pq;         // rk4: epq (or filt(0,:,:) in substep one) per column
-};
-
 struct SrcArgs {
     const double* r; const double* q; const double* p;   // semi-spectral fluxes
     double* s0; double* s1; double* s2;                  // svorts (mixed spectral)
-    StepFuse st;
 };
-
-// apply the stepper update to row z of component `comp`; S is the source row (rk4: scaled in place by pq,
-// as impl_rk4.f90:264-270 does to svorts)
-__device__ __forceinline__ void apply_step(const StepFuse& st, int comp, const Grp& r, int z, Row4& S) {
-    if (st.mode == 0) return;
-    double* q = st.svor[comp];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (s >= 2 && r.dupx) continue;
-        const long long i = r.off[s] + z, col = r.col[s];
-        if (st.mode == 1) {
-            double fac = __ldg(&st.f2d[col]) * __ldg(&st.filtz[z]);
-            if (r.g00 && s == 0) fac = __ldg(&st.vd[0]);                 // filt(:,0,0) = 1
-            double sm;
-            if (st.stage == 0) { sm = q[i] + st.c1 * S.v[s]; st.wa[comp][i] = sm; }
-            else sm = st.wa[comp][i];
-            q[i] = fac * (sm + st.c1 * S.v[s]);
-        } else {
-            const double mq = __ldg(&st.mq[col]);
-            const double sv = __ldg(&st.pq[col]) * S.v[s];
-            S.v[s] = sv;
-            if (st.stage == 1) {
-                const double qi = q[i];
-                st.wa[comp][i] = qi;
-                q[i] = mq * (qi + st.c1 * sv);
-                st.wb[comp][i] = qi + st.c2 * sv;
-            } else if (st.stage == 4) {
-                q[i] = mq * (st.wb[comp][i] + st.c1 * sv);
-            } else {
-                q[i] = mq * (st.wa[comp][i] + st.c1 * sv);
-                st.wb[comp][i] = st.wb[comp][i] + st.c2 * sv;
-            }
-        }
-    }
-}
 
 // stage a semi-spectral field F (global) with its harmonic part removed -> buffer X (rows 0, NZ kept),
 // and optionally the same for central_diffz(F) -> buffer DX.
@@ -896,8 +839,6 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
         Row4 s0, s1;
 #pragma unroll
         for (int s = 0; s < 4; ++s) { s0.v[s] = ry.v[s] - dq.v[s]; s1.v[s] = dp.v[s] - rx.v[s]; }
-        apply_step(a.st, 0, r, z, s0);
-        apply_step(a.st, 1, r, z, s1);
         row_store_g<NZ>(a.s0, r, z, s0);       // dr/dy - dq/dz
         row_store_g<NZ>(a.s1, r, z, s1);       // dp/dz - dr/dx
         qx[it] = ddx(row_load_s<NZ>(W, z), r);
@@ -915,7 +856,6 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
         Row4 s2;
 #pragma unroll
         for (int s = 0; s < 4; ++s) s2.v[s] = qx[it].v[s] - py.v[s];
-        apply_step(a.st, 2, r, z, s2);
         row_store_g<NZ>(a.s2, r, z, s2);
     }
 }
