@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     }
     __syncthreads();          // scratch is reused by the next tile of a persistent launch
     }
+    if (a.out_map.self >= 0) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
 }
 
 template <int N, int PRO>
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
         st2f(a.final_store, row_dst(a, u + e * (N / 8)) + obase, vr[e] * sc, vi[e] * sc);
     __syncthreads();          // scratch is reused by the next tile of a persistent launch
     }
+    if (a.out_map.self >= 0) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
 }
 
 template <int N>
