@@ -55,7 +55,7 @@ struct DevBuf {
     }
 };
 
-static const int RED_BLOCKS = 1184;   // 148 SMs x 8
+static const int RED_BLOCKS = 1184;   // 148 SMs x 8 (upper bound; small grids use one block per 256 elements)
 static const int RED_THREADS = 256;
 
 struct RollingMean {   // utils/rolling_mean.f90:36-69
@@ -97,6 +97,7 @@ struct Ctx {
     double vvisc = 0.0;
     RollingMean rollmean;
     long long launches = 0;
+    int red_blocks = RED_BLOCKS;         // blocks of the two-stage reductions: fixed per grid size -> deterministic sums
     int num_sms = 148;
     int p2p_ctas_per_sm = -1;            // PS3D_P2P_CTAS: blocks per SM of the persistent scatter sweeps (0 = full grid, -1 = auto)
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
@@ -670,6 +671,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->stage.alloc(c->nnat);
     for (int i = 0; i < (nranks > 1 ? 9 : 6); ++i) c->W[i].alloc(c->nint);
     c->redS.alloc(64); c->redM.alloc(64);
+    c->red_blocks = (int)std::min<size_t>((size_t)RED_BLOCKS, (c->nint + RED_THREADS - 1) / RED_THREADS);
     c->partial.alloc((size_t)RED_BLOCKS * 16);
     c->red.alloc(64);
 #ifndef PS3D_EMU
@@ -866,10 +868,10 @@ static FieldPtrs field_ptrs(Ctx& c) {
 // reduces the physical fields into c.red[0..RQ_N)
 static void field_reduce(Ctx& c) {
     const long long ncol = (long long)c.nxl * c.ny;
-    PS_LAUNCH((k_field_reduce), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+    PS_LAUNCH((k_field_reduce), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
               field_ptrs(c), ncol, c.nz, c.pz, c.partial.p);
     PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
-              (const double*)c.partial.p, RED_BLOCKS, (int)RQ_N, RQ_OPMASK, c.red.p);
+              (const double*)c.partial.p, c.red_blocks, (int)RQ_N, RQ_OPMASK, c.red.p);
     c.launches += 2;
 }
 
@@ -983,10 +985,10 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     allreduce_host(c, r1, RQ_N, RQ_OPMASK);             // advance.f90:299-305, field_diagnostics.f90:418-424
     const double vortmax = std::sqrt(r1[RQ_MAXW2]);
     const double vortrms = std::sqrt(r1[RQ_SUMW2] / (double)c.ncell);
-    PS_LAUNCH((k_char_vorticity), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+    PS_LAUNCH((k_char_vorticity), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
               field_ptrs(c), ncol, c.nz, c.pz, vortrms, c.partial.p);
     PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
-              (const double*)c.partial.p, RED_BLOCKS, 2, 0u, c.red.p);
+              (const double*)c.partial.p, c.red_blocks, 2, 0u, c.red.p);
     c.launches += 2;
     // velocity strain (advance.f90:199-217): derivative folded into the inverse sweeps
     strain_fields(c);
@@ -994,10 +996,10 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     sp.dudx = c.W[0].p; sp.dudy = c.W[1].p; sp.dwdx = c.W[2].p; sp.dvdy = c.W[3].p; sp.dwdy = c.W[4].p;
     for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
     // k_strain writes partial[b*3..], after the char-vorticity final reduce has consumed partial (same stream)
-    PS_LAUNCH((k_strain), dim3(RED_BLOCKS), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream, sp, ncol, c.nz,
+    PS_LAUNCH((k_strain), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream, sp, ncol, c.nz,
               c.pz, c.strict_jacobi, c.partial.p);
     PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
-              (const double*)c.partial.p, RED_BLOCKS, 3, 7u, c.red.p + 2);
+              (const double*)c.partial.p, c.red_blocks, 3, 7u, c.red.p + 2);
     c.launches += 2;
     ps_d2h(c.h_red, c.red.p, 5 * sizeof(double), c.stream);
     ps_sync(c.stream);
