@@ -825,7 +825,6 @@ static void do_vor2vel(Ctx& c) {
     a.svor0 = c.svor[0].p; a.svor1 = c.svor[1].p; a.svor2 = c.svor[2].p;
     a.wsem0 = c.W[0].p; a.wsem1 = c.W[1].p; a.wsem2 = c.W[2].p;
     a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
-    a.dbg = getenv("PS3D_DBG") ? atoi(getenv("PS3D_DBG")) : 0;
     launch_v2v(c, a);
     Sweep f[6], g[6];
     for (int i = 0; i < 3; ++i) {
@@ -1306,7 +1305,7 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
                 // writes go to scratch so that the resident state is not disturbed
                 a.svor0 = c.W[0].p; a.svor1 = c.W[1].p; a.svor2 = c.svor[2].p;
                 a.wsem0 = c.W[2].p; a.wsem1 = c.W[3].p; a.wsem2 = c.W[4].p;
-                a.svel0 = c.W[5].p; a.svel1 = c.W[5].p; a.svel2 = c.W[5].p; a.dbg = 0;
+                a.svel0 = c.W[5].p; a.svel1 = c.W[5].p; a.svel2 = c.W[5].p;
                 if (r == 0) { ps_d2d(c.W[0].p, c.svor[0].p, c.nint * sizeof(double), c.stream); ps_d2d(c.W[1].p, c.svor[1].p, c.nint * sizeof(double), c.stream); }
                 launch_v2v(c, a);
                 break;

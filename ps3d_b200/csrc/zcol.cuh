@@ -59,7 +59,7 @@ struct ZCfg {
     static constexpr int LC = NZ + 16;            // column buffer stride (rows 0..NZ, swizzled in 16-row blocks)
     static constexpr int BUF = 4 * LC;            // doubles per 4-slot field buffer
     static constexpr int NSIN = NZ / 2 + 2;       // sin(m pi/nz), m = 0..nz/2
-    static constexpr int SCR = 4 * 2 * NZ + NSIN + 64;   // FFT scratch (4 x re/im x NZ) + sine table + warp totals
+    static constexpr int SCR = 4 * 2 * NZ + NSIN + 64 + 32;   // FFT scratch (4 x re/im x NZ) + sine table + warp totals + kept scalars
     static constexpr int ZI = 3;                  // rows per thread: t, t+NT, and NZ (thread 0 only)
 };
 
@@ -174,10 +174,10 @@ __device__ __forceinline__ Hyp make_hyp(const SpecGeom& g, const Grp& r, int sy)
 }
 
 // per-thread table for the rows this thread owns: phim, phip for sy = 0, 1 (inversion_utils.f90:505-519)
+// (only phim/phip stay in registers for the whole kernel; exp(-kl zp), exp(-kl zm) are recovered where the
+//  theta functions need them: ep = phim + ef phip, em = phip + ef phim)
 template <int NZ>
 struct HypRows {
-    double zm[3], zp[3];
-    double ep[3][2], em[3][2];
     double phim[3][2], phip[3][2];
 };
 
@@ -190,27 +190,22 @@ __device__ __forceinline__ void hyp_rows(HypRows<NZ>& T, const Hyp (&h)[2], cons
         if (z < 0) {
             // never read, but keep every register defined on every path: ptxas 12.9 was seen to emit spill
             // loads without the matching stores for values that are undefined on some lanes
-            T.zm[it] = T.zp[it] = 0.0;
-            T.ep[it][0] = T.ep[it][1] = T.em[it][0] = T.em[it][1] = 0.0;
             T.phim[it][0] = T.phim[it][1] = T.phip[it][0] = T.phip[it][1] = 0.0;
             continue;
         }
-        T.zm[it] = __ldg(&g.zm[z]);
-        T.zp[it] = __ldg(&g.zp[z]);
+        const double zm = __ldg(&g.zm[z]), zp = __ldg(&g.zp[z]);
 #pragma unroll
         for (int sy = 0; sy < 2; ++sy) {
             if (sy == 1 && same) {
-                T.ep[it][1] = T.ep[it][0]; T.em[it][1] = T.em[it][0];
                 T.phim[it][1] = T.phim[it][0]; T.phip[it][1] = T.phip[it][0];
                 continue;
             }
-            const double ep = exp(-(h[sy].kl * T.zp[it]));
-            const double em = exp(-(h[sy].kl * T.zm[it]));
-            T.ep[it][sy] = ep; T.em[it][sy] = em;
             if (h[sy].lin) {
-                T.phim[it][sy] = T.zm[it] / g.Lz;
-                T.phip[it][sy] = T.zp[it] / g.Lz;
+                T.phim[it][sy] = zm / g.Lz;
+                T.phip[it][sy] = zp / g.Lz;
             } else {
+                const double ep = exp(-(h[sy].kl * zp));
+                const double em = exp(-(h[sy].kl * zm));
                 T.phim[it][sy] = h[sy].div * (ep - h[sy].ef * em);
                 T.phip[it][sy] = h[sy].div * (em - h[sy].ef * ep);
             }
@@ -219,9 +214,10 @@ __device__ __forceinline__ void hyp_rows(HypRows<NZ>& T, const Hyp (&h)[2], cons
 }
 
 // thetam, thetap, dthetam, dthetap of one row (inversion_utils.f90:518-541)
-__device__ __forceinline__ void hyp_theta(const Hyp& h, double ep, double em, double zm, double zp, double phim,
+__device__ __forceinline__ void hyp_theta(const Hyp& h, double zm, double zp, double phim,
                                           double phip, double& thm, double& thp, double& dthm, double& dthp) {
     if (h.lin) { thm = thp = dthm = dthp = 0.0; return; }
+    const double ep = phim + h.ef * phip, em = phip + h.ef * phim;     // exp(-kl zp), exp(-kl zm)
     const double Lm = h.kl * zm;
     const double Lp = h.kl * zp;
     const double dphim = -h.kl * h.div * (ep + h.ef * em);
@@ -241,11 +237,12 @@ struct ZScr {
     double* fft;      // [4][2][NZ]
     double* sintab;   // [NZ/2 + 1]  sin(m pi / NZ)
     double* wt;       // [64] warp totals of the group scan / sum
+    double* keep;     // [32] block-wide scalars parked between stages (keeps them out of registers)
 };
 template <int NZ>
 __device__ __forceinline__ ZScr<NZ> make_scr(double* base) {
     ZScr<NZ> s;
-    s.fft = base; s.sintab = base + 8 * NZ; s.wt = s.sintab + ZCfg<NZ>::NSIN;
+    s.fft = base; s.sintab = base + 8 * NZ; s.wt = s.sintab + ZCfg<NZ>::NSIN; s.keep = s.wt + 64;
     return s;
 }
 // fill the sine table (once per block; followed by a barrier in the caller)
@@ -508,7 +505,6 @@ struct V2VArgs {
     double* svor0; double* svor1; const double* svor2;   // in/out, in/out, in
     double* wsem0; double* wsem1; double* wsem2;         // semi-spectral vorticity (out)
     double* svel0; double* svel1; double* svel2;         // semi-spectral velocity (out)
-    int dbg;
 };
 
 template <int NZ>
@@ -583,7 +579,6 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 
     // D = B_x - A_y (:39-42); A = k2l2i (E_x + D_y), B = k2l2i (E_y - D_x), (0,0) keeps its mean (:55-76);
     // then the source of the w inversion D2 = A_y - B_x (:86-90) -> E buffer
-    double ub[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};     // (0,0) group: ubar/vbar sources of my rows
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -609,18 +604,15 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 #pragma unroll
         for (int s = 0; s < 4; ++s) d.v[s] = ay2.v[s] - bx2.v[s];
         row_store_s<NZ>(E, z, d);
-        if (r.g00 && z >= 1 && z < NZ) {                     // :153-154
-            const double rkzi = 1.0 / __ldg(&g.rkz[z]);
-            ub[it] = -rkzi * fb.v[0];
-            vb[it] = rkzi * fa.v[0];
-        }
     }
     __syncthreads();
     // boundary values of D2 (:96-104) and of the mean vorticity (:163-164), before anything is overwritten
-    double d0[4], dn[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) { d0[s] = E[s * LC + cz(0)]; dn[s] = E[s * LC + cz(NZ)]; }
-    const double a00 = A[cz(0)], a0n = A[cz(NZ)], b00 = B[cz(0)], b0n = B[cz(NZ)];
+    // (parked in shared memory: they are needed again only in the last stage)
+    if (threadIdx.x < 4) {
+        const int s = threadIdx.x;
+        scr.keep[s] = E[s * LC + cz(0)];
+        scr.keep[4 + s] = E[s * LC + cz(NZ)];
+    }
 
     // vorticity to semi-spectral space for the inverse x/y passes (:80-82)
     xform2<NZ>(A, XF_DST, B, XF_DST, scr, g);
@@ -667,8 +659,14 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         for (int it = 0; it < 3; ++it) {
             const int z = my_row<NZ>(it);
             if (z < 0) continue;
+            // the (0,0) column of svor is not touched by the projection (:72-76): read it back from memory
             Row4 m;
-            m.v[0] = ub[it]; m.v[1] = vb[it]; m.v[2] = 0.0; m.v[3] = 0.0;
+            m.v[0] = m.v[1] = m.v[2] = m.v[3] = 0.0;
+            if (z >= 1 && z < NZ) {                             // :153-154
+                const double rkzi = 1.0 / __ldg(&g.rkz[z]);
+                m.v[0] = -rkzi * a.svor1[r.off[0] + z];
+                m.v[1] = rkzi * a.svor0[r.off[0] + z];
+            }
             row_store_s<NZ>(B, z, m);
         }
     }
@@ -678,18 +676,26 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 
     // w = E + boundary part, dw/dz = es + as (:96-104, :136-139);
     // u = k2l2i (es_x + cs_y), v = k2l2i (es_y - cs_x), (0,0) <- ubar, vbar (:169-213)
+    double d0[4], dn[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { d0[s] = scr.keep[s]; dn[s] = scr.keep[4 + s]; }
+    double a00 = 0.0, a0n = 0.0, b00 = 0.0, b0n = 0.0;
+    if (r.g00) {
+        a00 = a.svor0[r.off[0]]; a0n = a.svor0[r.off[0] + NZ];
+        b00 = a.svor1[r.off[0]]; b0n = a.svor1[r.off[0] + NZ];
+    }
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
         const Row4 as = row_load_s<NZ>(A, z), ds = row_load_s<NZ>(E, z), cs = row_load_s<NZ>(C, z);
+        const double zm = __ldg(&g.zm[z]), zp = __ldg(&g.zp[z]);
         Row4 es, w;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const int sy = s & 1;
             double thm, thp, dthm, dthp;
-            hyp_theta(h[sy], T.ep[it][sy], T.em[it][sy], T.zm[it], T.zp[it], T.phim[it][sy], T.phip[it][sy],
-                      thm, thp, dthm, dthp);
+            hyp_theta(h[sy], zm, zp, T.phim[it][sy], T.phip[it][sy], thm, thp, dthm, dthp);
             es.v[s] = d0[s] * dthm + dn[s] * dthp + as.v[s];
             w.v[s] = (z == 0 || z == NZ) ? 0.0 : ds.v[s] + d0[s] * thm + dn[s] * thp;
         }
@@ -704,41 +710,6 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
             const double gt = __ldg(&g.gamtop[z]), gb = __ldg(&g.gambot[z]);
             u.v[0] = B[cz(z)] + b0n * gt - b00 * gb;               // ubar (:163)
             v.v[0] = B[LC + cz(z)] - a0n * gt + a00 * gb;          // vbar (:164)
-        }
-        if (a.dbg == 1) {
-            Row4 t1, t2;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                double thm, thp, dthm, dthp;
-                hyp_theta(h[s & 1], T.ep[it][s & 1], T.em[it][s & 1], T.zm[it], T.zp[it], T.phim[it][s & 1], T.phip[it][s & 1],
-                          thm, thp, dthm, dthp);
-                t1.v[s] = dthm; t2.v[s] = dthp;
-            }
-            if (a.dbg == 1) { u = es; v = as; w = t1; }
-            (void)t2;
-        }
-        if (a.dbg == 4) {
-            Row4 t1, t2, t3;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                double thm, thp, dthm, dthp;
-                hyp_theta(h[s & 1], T.ep[it][s & 1], T.em[it][s & 1], T.zm[it], T.zp[it], T.phim[it][s & 1], T.phip[it][s & 1],
-                          thm, thp, dthm, dthp);
-                t1.v[s] = dthm; t2.v[s] = dthp; t3.v[s] = (s & 2) ? thp : thm;
-            }
-            u = t1; v = t2; w = t3;
-        }
-        if (a.dbg == 3) {
-            Row4 t1, t2, t3;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { t1.v[s] = (s & 2) ? T.zm[it] : T.ep[it][s & 1]; t2.v[s] = (s & 2) ? T.zp[it] : T.em[it][s & 1]; t3.v[s] = (s & 2) ? T.phip[it][s & 1] : T.phim[it][s & 1]; }
-            u = t1; v = t2; w = t3;
-        }
-        if (a.dbg == 2) {
-            Row4 t1, t2;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { t1.v[s] = d0[s]; t2.v[s] = dn[s]; }
-            u = t1; v = t2; w = ds;
         }
         row_store_g<NZ>(a.svel0, r, z, u);
         row_store_g<NZ>(a.svel1, r, z, v);
@@ -828,8 +799,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
     __syncthreads();
     xform2<NZ>(R, XF_DST, X, XF_DST, scr, g);
     xform2<NZ>(Y, XF_DST, W, XF_DST, scr, g);
-    // xi, eta tendencies (inversion.f90:341-359); keep d(q)/dx of my rows for the zeta tendency
-    Row4 qx[3] = {};
+    // xi, eta tendencies (inversion.f90:341-359)
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -841,7 +811,6 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
         for (int s = 0; s < 4; ++s) { s0.v[s] = ry.v[s] - dq.v[s]; s1.v[s] = dp.v[s] - rx.v[s]; }
         row_store_g<NZ>(a.s0, r, z, s0);       // dr/dy - dq/dz
         row_store_g<NZ>(a.s1, r, z, s1);       // dp/dz - dr/dx
-        qx[it] = ddx(row_load_s<NZ>(W, z), r);
     }
     __syncthreads();
     // zeta tendency dq/dx - dp/dy (:363-367)
@@ -852,10 +821,10 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        const Row4 py = ddy(row_load_s<NZ>(R, z), r);
+        const Row4 py = ddy(row_load_s<NZ>(R, z), r), qx = ddx(row_load_s<NZ>(W, z), r);
         Row4 s2;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) s2.v[s] = qx[it].v[s] - py.v[s];
+        for (int s = 0; s < 4; ++s) s2.v[s] = qx.v[s] - py.v[s];
         row_store_g<NZ>(a.s2, r, z, s2);
     }
 }
