@@ -75,6 +75,7 @@ struct Grp {
     double kx, ky;      // diff wavenumbers
     double k2[2], k2i[2];
     long long off[4];   // column offsets (doubles) of slots s = 2*sx + sy
+    long long col[4];   // column index kx*nyl + kyl of the slots (per-column tables of the steppers)
 };
 
 __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
@@ -92,8 +93,10 @@ __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
         const int kyl = 2 * r.ap + sy;
         r.k2[sy] = __ldg(&g.k2l2[(long long)r.b * g.nyl + kyl]);
         r.k2i[sy] = __ldg(&g.k2l2i[(long long)r.b * g.nyl + kyl]);
-        r.off[sy] = ((long long)r.b * g.nyl + kyl) * g.pz;
-        r.off[2 + sy] = ((long long)kxm * g.nyl + kyl) * g.pz;
+        r.col[sy] = (long long)r.b * g.nyl + kyl;
+        r.col[2 + sy] = (long long)kxm * g.nyl + kyl;
+        r.off[sy] = r.col[sy] * g.pz;
+        r.off[2 + sy] = r.col[2 + sy] * g.pz;
     }
     return r;
 }
@@ -501,11 +504,67 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
 template <int NZ>
 constexpr size_t v2v_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
+// Pending time-stepper update applied while the columns are staged (the pointwise stage that precedes vor2vel
+// inside the steppers: cn2.f90:120-137,162-175, impl_rk4.f90:107-113,133-140,166-174 with the
+// combine -> x c(ky,kx) -> decompose pairs collapsed), including adjust_vorticity_mean
+// (field_diagnostics.f90:604-619) for cn2.  Same arithmetic as k_cn2_update / k_rk4_update + k_vor_mean.
+struct StepFuse {
+    int mode;                 // 0 = none, 1 = cn2, 2 = impl-diff-rk4
+    int stage;                // cn2: 0 = first update (defines vortsm), 1 = iteration.  rk4: substep 1..3
+    double c1, c2;
+    double* svorts[3];
+    double* wa[3];            // cn2: vortsm      rk4: svori
+    double* wb[3];            // rk4: svorf
+    const double* f2d;        // cn2: vdiss*filt2d per column
+    const double* filtz;      // cn2: z part of the filter
+    const double* vd;         // cn2: vdiss per column ((0,0) column: filt = 1)
+    const double* mq;         // rk4: emq per column
+    const double* pq;         // rk4: epq (or filt(0,:,:) in substep one) per column
+    const double* wz;         // weights of sum_k dst(x)(k)   (mean vorticity)
+    const double* ini_mean;   // [2]
+    double fnzi;
+};
+
 struct V2VArgs {
-    double* svor0; double* svor1; const double* svor2;   // in/out, in/out, in
+    double* svor0; double* svor1; double* svor2;         // in/out (svor2 is only written when an update is pending)
     double* wsem0; double* wsem1; double* wsem2;         // semi-spectral vorticity (out)
     double* svel0; double* svel1; double* svel2;         // semi-spectral velocity (out)
+    StepFuse st;
 };
+
+// row z of component `comp` of the updated svor
+__device__ __forceinline__ Row4 staged_update(const StepFuse& st, int comp, const double* svor, const Grp& r, int z) {
+    Row4 out;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        out.v[s] = 0.0;
+        if (s >= 2 && r.dupx) continue;
+        const long long i = r.off[s] + z, col = r.col[s];
+        const double S = st.svorts[comp][i];
+        if (st.mode == 1) {
+            double fac = __ldg(&st.f2d[col]) * __ldg(&st.filtz[z]);
+            if (r.g00 && s == 0) fac = __ldg(&st.vd[0]);                 // filt(:,0,0) = 1
+            double sm;
+            if (st.stage == 0) { sm = svor[i] + st.c1 * S; st.wa[comp][i] = sm; }
+            else sm = st.wa[comp][i];
+            out.v[s] = fac * (sm + st.c1 * S);
+        } else {
+            const double mq = __ldg(&st.mq[col]);
+            const double sv = __ldg(&st.pq[col]) * S;
+            st.svorts[comp][i] = sv;                                     // impl_rk4.f90:264-270 scales svorts in place
+            if (st.stage == 1) {
+                const double qi = svor[i];
+                st.wa[comp][i] = qi;
+                out.v[s] = mq * (qi + st.c1 * sv);
+                st.wb[comp][i] = qi + st.c2 * sv;
+            } else {
+                out.v[s] = mq * (st.wa[comp][i] + st.c1 * sv);
+                st.wb[comp][i] = st.wb[comp][i] + st.c2 * sv;
+            }
+        }
+    }
+    return out;
+}
 
 template <int NZ>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
@@ -523,16 +582,49 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
     HypRows<NZ> T;
     hyp_rows<NZ>(T, h, g, r);
 
-    // stage svor
+    // stage svor (applying a pending stepper update on the way)
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        row_store_s<NZ>(A, z, row_load_g<NZ>(a.svor0, r, z));
-        row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
-        row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
+        if (a.st.mode == 0) {
+            row_store_s<NZ>(A, z, row_load_g<NZ>(a.svor0, r, z));
+            row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
+            row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
+        } else {
+            row_store_s<NZ>(A, z, staged_update(a.st, 0, a.svor0, r, z));
+            row_store_s<NZ>(B, z, staged_update(a.st, 1, a.svor1, r, z));
+            const Row4 c = staged_update(a.st, 2, a.svor2, r, z);
+            row_store_s<NZ>(C, z, c);
+            row_store_g<NZ>(a.svor2, r, z, c);
+        }
     }
     __syncthreads();
+    if (a.st.mode == 1 && r.g00) {
+        // adjust_vorticity_mean (field_diagnostics.f90:584-619) on the (0,0) column of xi, eta (slot 0 of A, B)
+        double pa = 0.0, pb = 0.0;
+        for (int j = 1 + (int)threadIdx.x; j < NZ; j += (int)blockDim.x) {
+            const double w = __ldg(&a.st.wz[j]);
+            pa += w * A[cz(j)]; pb += w * B[cz(j)];
+        }
+        // block sum through the scratch (not in use yet)
+        scr.fft[threadIdx.x] = pa; scr.fft[blockDim.x + threadIdx.x] = pb;
+        __syncthreads();
+        for (int st_ = blockDim.x >> 1; st_ > 0; st_ >>= 1) {
+            if ((int)threadIdx.x < st_) {
+                scr.fft[threadIdx.x] += scr.fft[threadIdx.x + st_];
+                scr.fft[blockDim.x + threadIdx.x] += scr.fft[blockDim.x + threadIdx.x + st_];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < 2) {
+            double* col = threadIdx.x ? B : A;
+            const double savg = 0.5 * (col[cz(0)] + col[cz(NZ)]) + a.st.fnzi * scr.fft[threadIdx.x ? blockDim.x : 0];
+            const double d = __ldg(&a.st.ini_mean[threadIdx.x]) - savg;
+            col[cz(0)] += d; col[cz(NZ)] += d;
+        }
+        __syncthreads();
+    }
 
     // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; also the
     // semi-spectral zeta that feeds the inverse x/y passes (:81)
