@@ -97,7 +97,8 @@ struct Ctx {
     double vvisc = 0.0;
     RollingMean rollmean;
     long long launches = 0;
-    int fuse_update = 1;                 // PS3D_FUSE_UPDATE=0: stand-alone stepper update kernels everywhere
+    int fuse_update = 0;                 // PS3D_FUSE_UPDATE=1: apply pending stepper updates while vor2vel stages its columns
+                                         // (measured slower on B200: 87.7 vs 77.3 ms/step at 512^3 cn2 -> off by default)
     int red_blocks = RED_BLOCKS;         // blocks of the two-stage reductions: fixed per grid size -> deterministic sums
     int num_sms = 148;
     int p2p_ctas_per_sm = -1;            // PS3D_P2P_CTAS: blocks per SM of the persistent scatter sweeps (0 = full grid, -1 = auto)
@@ -566,7 +567,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
-    c->fuse_update = getenv("PS3D_FUSE_UPDATE") ? atoi(getenv("PS3D_FUSE_UPDATE")) : 1;
+    c->fuse_update = getenv("PS3D_FUSE_UPDATE") ? atoi(getenv("PS3D_FUSE_UPDATE")) : 0;
     c->p2p_ctas_per_sm = getenv("PS3D_P2P_CTAS") ? atoi(getenv("PS3D_P2P_CTAS")) : -1;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
@@ -946,8 +947,9 @@ static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 /
     ++c.launches;
 }
 
-// Every stepper update that is followed by vor2vel is applied while vor2vel stages its columns
-// (c.fuse_update, default on); the last update of a step uses the stand-alone streaming kernels.
+// With c.fuse_update every stepper update that is followed by vor2vel is applied while vor2vel stages its
+// columns (the last update of a step always uses the stand-alone streaming kernels).  Default: off, the
+// streaming update kernels run at HBM speed while the column kernel is latency bound.
 static void do_step(Ctx& c, double* t, double dt) {
     if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
     const bool fuse = c.fuse_update != 0;

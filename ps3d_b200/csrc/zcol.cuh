@@ -532,38 +532,60 @@ struct V2VArgs {
     StepFuse st;
 };
 
-// row z of component `comp` of the updated svor
-__device__ __forceinline__ Row4 staged_update(const StepFuse& st, int comp, const double* svor, const Grp& r, int z) {
-    Row4 out;
+// rows z of the three components of the updated svor.  All global loads of the row are issued before the first
+// store (the compiler cannot move loads across the stores: the pointers may alias), so the row costs one
+// memory latency instead of one per element.
+__device__ __forceinline__ void staged_update(const StepFuse& st, double* const (&svor)[3], const Grp& r, int z,
+                                              Row4 (&out)[3]) {
+    double S[3][4], P[3][4], Q[3][4], fac[4], mq[4], pq[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        out.v[s] = 0.0;
-        if (s >= 2 && r.dupx) continue;
+        const bool act = !(s >= 2 && r.dupx);
         const long long i = r.off[s] + z, col = r.col[s];
-        const double S = st.svorts[comp][i];
-        if (st.mode == 1) {
-            double fac = __ldg(&st.f2d[col]) * __ldg(&st.filtz[z]);
-            if (r.g00 && s == 0) fac = __ldg(&st.vd[0]);                 // filt(:,0,0) = 1
-            double sm;
-            if (st.stage == 0) { sm = svor[i] + st.c1 * S; st.wa[comp][i] = sm; }
-            else sm = st.wa[comp][i];
-            out.v[s] = fac * (sm + st.c1 * S);
-        } else {
-            const double mq = __ldg(&st.mq[col]);
-            const double sv = __ldg(&st.pq[col]) * S;
-            st.svorts[comp][i] = sv;                                     // impl_rk4.f90:264-270 scales svorts in place
-            if (st.stage == 1) {
-                const double qi = svor[i];
-                st.wa[comp][i] = qi;
-                out.v[s] = mq * (qi + st.c1 * sv);
-                st.wb[comp][i] = qi + st.c2 * sv;
+        fac[s] = mq[s] = pq[s] = 0.0;
+        if (act) {
+            if (st.mode == 1) {
+                fac[s] = __ldg(&st.f2d[col]) * __ldg(&st.filtz[z]);
+                if (r.g00 && s == 0) fac[s] = __ldg(&st.vd[0]);          // filt(:,0,0) = 1
             } else {
-                out.v[s] = mq * (st.wa[comp][i] + st.c1 * sv);
-                st.wb[comp][i] = st.wb[comp][i] + st.c2 * sv;
+                mq[s] = __ldg(&st.mq[col]); pq[s] = __ldg(&st.pq[col]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            S[c][s] = P[c][s] = Q[c][s] = 0.0;
+            if (!act) continue;
+            S[c][s] = st.svorts[c][i];
+            const bool first = (st.mode == 1) ? (st.stage == 0) : (st.stage == 1);
+            P[c][s] = first ? svor[c][i] : st.wa[c][i];                  // svor^n, or vortsm / svori
+            if (st.mode == 2 && st.stage > 1) Q[c][s] = st.wb[c][i];     // svorf
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            out[c].v[s] = 0.0;
+            if (s >= 2 && r.dupx) continue;
+            const long long i = r.off[s] + z;
+            if (st.mode == 1) {
+                double sm = P[c][s];
+                if (st.stage == 0) { sm = P[c][s] + st.c1 * S[c][s]; st.wa[c][i] = sm; }
+                out[c].v[s] = fac[s] * (sm + st.c1 * S[c][s]);
+            } else {
+                const double sv = pq[s] * S[c][s];
+                st.svorts[c][i] = sv;                                    // impl_rk4.f90:264-270 scales svorts in place
+                if (st.stage == 1) {
+                    st.wa[c][i] = P[c][s];
+                    out[c].v[s] = mq[s] * (P[c][s] + st.c1 * sv);
+                    st.wb[c][i] = P[c][s] + st.c2 * sv;
+                } else {
+                    out[c].v[s] = mq[s] * (P[c][s] + st.c1 * sv);
+                    st.wb[c][i] = Q[c][s] + st.c2 * sv;
+                }
             }
         }
     }
-    return out;
 }
 
 template <int NZ>
@@ -592,11 +614,13 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
             row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
             row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
         } else {
-            row_store_s<NZ>(A, z, staged_update(a.st, 0, a.svor0, r, z));
-            row_store_s<NZ>(B, z, staged_update(a.st, 1, a.svor1, r, z));
-            const Row4 c = staged_update(a.st, 2, a.svor2, r, z);
-            row_store_s<NZ>(C, z, c);
-            row_store_g<NZ>(a.svor2, r, z, c);
+            double* const sv[3] = {a.svor0, a.svor1, a.svor2};
+            Row4 q[3];
+            staged_update(a.st, sv, r, z, q);
+            row_store_s<NZ>(A, z, q[0]);
+            row_store_s<NZ>(B, z, q[1]);
+            row_store_s<NZ>(C, z, q[2]);
+            row_store_g<NZ>(a.svor2, r, z, q[2]);
         }
     }
     __syncthreads();
