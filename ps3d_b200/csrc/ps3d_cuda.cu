@@ -97,7 +97,6 @@ struct Ctx {
     double vvisc = 0.0;
     RollingMean rollmean;
     long long launches = 0;
-    int fuse_update = 0;                 // PS3D_FUSE_UPDATE=1: apply pending stepper updates while vor2vel stages its columns
                                          // (measured slower on B200: 87.7 vs 77.3 ms/step at 512^3 cn2 -> off by default)
     int red_blocks = RED_BLOCKS;         // blocks of the two-stage reductions: fixed per grid size -> deterministic sums
     int num_sms = 148;
@@ -567,7 +566,6 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
-    c->fuse_update = getenv("PS3D_FUSE_UPDATE") ? atoi(getenv("PS3D_FUSE_UPDATE")) : 0;
     c->p2p_ctas_per_sm = getenv("PS3D_P2P_CTAS") ? atoi(getenv("PS3D_P2P_CTAS")) : -1;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
@@ -823,9 +821,8 @@ static void do_finalise() {
 // ---------------------------------------------------------------------------
 // resident-mode operators
 // ---------------------------------------------------------------------------
-static void do_vor2vel(Ctx& c, const StepFuse* fuse = nullptr) {
+static void do_vor2vel(Ctx& c) {
     V2VArgs a;
-    if (fuse) a.st = *fuse; else a.st.mode = 0;
     a.svor0 = c.svor[0].p; a.svor1 = c.svor[1].p; a.svor2 = c.svor[2].p;
     a.wsem0 = c.W[0].p; a.wsem1 = c.W[1].p; a.wsem2 = c.W[2].p;
     a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
@@ -930,16 +927,6 @@ static void rk4_update(Ctx& c, int stage, double c1, double c2, const double* pq
     ++c.launches;
 }
 
-static StepFuse step_fuse(Ctx& c, int stage, double c1, double c2, const double* pq) {
-    StepFuse f;
-    f.mode = (c.stepper == PS3D_STEPPER_CN2) ? 1 : 2;
-    f.stage = stage; f.c1 = c1; f.c2 = c2;
-    for (int i = 0; i < 3; ++i) { f.svorts[i] = c.svorts[i].p; f.wa[i] = c.wa[i].p; f.wb[i] = c.wb[i].p; }
-    f.f2d = c.fac2.p; f.filtz = c.filtz.p; f.vd = c.fac1.p; f.mq = c.fac1.p; f.pq = pq;
-    f.wz = c.wz.p; f.ini_mean = c.ini_mean.p; f.fnzi = 1.0 / (double)c.nz;
-    return f;
-}
-
 static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 / epq = epq**2 (impl_rk4.f90:151,185)
     const long long ncol = (long long)c.nx * c.nyl;
     PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, mode, 0.0, (const double*)nullptr,
@@ -947,36 +934,31 @@ static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 /
     ++c.launches;
 }
 
-// With c.fuse_update every stepper update that is followed by vor2vel is applied while vor2vel stages its
-// columns (the last update of a step always uses the stand-alone streaming kernels).  Default: off, the
-// streaming update kernels run at HBM speed while the column kernel is latency bound.
 static void do_step(Ctx& c, double* t, double dt) {
     if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
-    const bool fuse = c.fuse_update != 0;
     if (c.stepper == PS3D_STEPPER_CN2) {
         const double dt2 = 0.5 * dt;                       // cn2.f90:101
-        if (!fuse) cn2_update(c, dt2, 0);                  // :120-137
+        cn2_update(c, dt2, 0);                             // :120-137
         for (int iter = 0; iter < 2; ++iter) {             // niter = 2 (:34, :143-177)
-            if (fuse) { const StepFuse f = step_fuse(c, iter == 0 ? 0 : 1, dt2, 0.0, nullptr); do_vor2vel(c, &f); }
-            else do_vor2vel(c);
+            do_vor2vel(c);
             do_source(c);
-            if (!fuse || iter == 1) cn2_update(c, dt2, 1);
+            cn2_update(c, dt2, 1);
         }
         *t += dt;
     } else {
         const double dt2 = 0.5 * dt, dt3 = dt / 3.0, dt6 = dt / 6.0;   // impl_rk4.f90:82-84
         // substep one filters the source with filt(0,:,:) (:227-229)
-        if (fuse) { const StepFuse f = step_fuse(c, 1, dt2, dt6, c.filt2d.p); do_vor2vel(c, &f); }
-        else { rk4_update(c, 1, dt2, dt6, c.filt2d.p); do_vor2vel(c); }
+        rk4_update(c, 1, dt2, dt6, c.filt2d.p);
+        do_vor2vel(c);
         do_source(c);
         *t += dt2;
-        if (fuse) { const StepFuse f = step_fuse(c, 2, dt2, dt3, c.fac2.p); do_vor2vel(c, &f); }
-        else { rk4_update(c, 2, dt2, dt3, c.fac2.p); do_vor2vel(c); }
+        rk4_update(c, 2, dt2, dt3, c.fac2.p);
+        do_vor2vel(c);
         do_source(c);
         *t += dt2;
         square_factor(c, 2);                               // emq = emq**2 (:151)
-        if (fuse) { const StepFuse f = step_fuse(c, 3, dt, dt3, c.fac2.p); do_vor2vel(c, &f); }
-        else { rk4_update(c, 3, dt, dt3, c.fac2.p); do_vor2vel(c); }
+        rk4_update(c, 3, dt, dt3, c.fac2.p);
+        do_vor2vel(c);
         do_source(c);
         square_factor(c, 3);                               // epq = epq**2 (:185)
         rk4_update(c, 4, dt6, 0.0, c.fac2.p);
@@ -1329,7 +1311,7 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
                 // writes go to scratch so that the resident state is not disturbed
                 a.svor0 = c.W[0].p; a.svor1 = c.W[1].p; a.svor2 = c.svor[2].p;
                 a.wsem0 = c.W[2].p; a.wsem1 = c.W[3].p; a.wsem2 = c.W[4].p;
-                a.svel0 = c.W[5].p; a.svel1 = c.W[5].p; a.svel2 = c.W[5].p; a.st.mode = 0;
+                a.svel0 = c.W[5].p; a.svel1 = c.W[5].p; a.svel2 = c.W[5].p;
                 if (r == 0) { ps_d2d(c.W[0].p, c.svor[0].p, c.nint * sizeof(double), c.stream); ps_d2d(c.W[1].p, c.svor[1].p, c.nint * sizeof(double), c.stream); }
                 launch_v2v(c, a);
                 break;

@@ -504,87 +504,29 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
 template <int NZ>
 constexpr size_t v2v_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
-// Pending time-stepper update applied while the columns are staged (the pointwise stage that precedes vor2vel
-// inside the steppers: cn2.f90:120-137,162-175, impl_rk4.f90:107-113,133-140,166-174 with the
-// combine -> x c(ky,kx) -> decompose pairs collapsed), including adjust_vorticity_mean
-// (field_diagnostics.f90:604-619) for cn2.  Same arithmetic as k_cn2_update / k_rk4_update + k_vor_mean.
-struct StepFuse {
-    int mode;                 // 0 = none, 1 = cn2, 2 = impl-diff-rk4
-    int stage;                // cn2: 0 = first update (defines vortsm), 1 = iteration.  rk4: substep 1..3
-    double c1, c2;
-    double* svorts[3];
-    double* wa[3];            // cn2: vortsm      rk4: svori
-    double* wb[3];            // rk4: svorf
-    const double* f2d;        // cn2: vdiss*filt2d per column
-    const double* filtz;      // cn2: z part of the filter
-    const double* vd;         // cn2: vdiss per column ((0,0) column: filt = 1)
-    const double* mq;         // rk4: emq per column
-    const double* pq;         // rk4: epq (or filt(0,:,:) in substep one) per column
-    const double* wz;         // weights of sum_k dst(x)(k)   (mean vorticity)
-    const double* ini_mean;   // [2]
-    double fnzi;
-};
-
 struct V2VArgs {
-    double* svor0; double* svor1; double* svor2;         // in/out (svor2 is only written when an update is pending)
+    double* svor0; double* svor1; double* svor2;         // in/out
     double* wsem0; double* wsem1; double* wsem2;         // semi-spectral vorticity (out)
     double* svel0; double* svel1; double* svel2;         // semi-spectral velocity (out)
-    StepFuse st;
 };
 
-// rows z of the three components of the updated svor.  All global loads of the row are issued before the first
-// store (the compiler cannot move loads across the stores: the pointers may alias), so the row costs one
-// memory latency instead of one per element.
-__device__ __forceinline__ void staged_update(const StepFuse& st, double* const (&svor)[3], const Grp& r, int z,
-                                              Row4 (&out)[3]) {
-    double S[3][4], P[3][4], Q[3][4], fac[4], mq[4], pq[4];
+// The solenoidal projection of inversion.f90:39-76 on one row (all four slots):
+//   D = B_x - A_y;  A <- k2l2i (E_x + D_y),  B <- k2l2i (E_y - D_x);  the (0,0) column keeps its values.
+// It only mixes slots with the same k^2 + l^2 and has no z dependence, so it commutes with the z transforms and
+// with adding/removing the harmonic part: the kernel applies it once to the mixed-spectral rows (-> new svor)
+// and once to the semi-spectral rows (-> input of the inverse x/y passes) instead of transforming the
+// projected fields again.
+__device__ __forceinline__ void project_row(Row4& fa, Row4& fb, const Row4& fe, const Grp& r) {
+    const Row4 bx = ddx(fb, r), ay = ddy(fa, r);
+    Row4 d;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) d.v[s] = bx.v[s] - ay.v[s];
+    const Row4 ex = ddx(fe, r), ey = ddy(fe, r), dx_ = ddx(d, r), dy_ = ddy(d, r);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const bool act = !(s >= 2 && r.dupx);
-        const long long i = r.off[s] + z, col = r.col[s];
-        fac[s] = mq[s] = pq[s] = 0.0;
-        if (act) {
-            if (st.mode == 1) {
-                fac[s] = __ldg(&st.f2d[col]) * __ldg(&st.filtz[z]);
-                if (r.g00 && s == 0) fac[s] = __ldg(&st.vd[0]);          // filt(:,0,0) = 1
-            } else {
-                mq[s] = __ldg(&st.mq[col]); pq[s] = __ldg(&st.pq[col]);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            S[c][s] = P[c][s] = Q[c][s] = 0.0;
-            if (!act) continue;
-            S[c][s] = st.svorts[c][i];
-            const bool first = (st.mode == 1) ? (st.stage == 0) : (st.stage == 1);
-            P[c][s] = first ? svor[c][i] : st.wa[c][i];                  // svor^n, or vortsm / svori
-            if (st.mode == 2 && st.stage > 1) Q[c][s] = st.wb[c][i];     // svorf
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            out[c].v[s] = 0.0;
-            if (s >= 2 && r.dupx) continue;
-            const long long i = r.off[s] + z;
-            if (st.mode == 1) {
-                double sm = P[c][s];
-                if (st.stage == 0) { sm = P[c][s] + st.c1 * S[c][s]; st.wa[c][i] = sm; }
-                out[c].v[s] = fac[s] * (sm + st.c1 * S[c][s]);
-            } else {
-                const double sv = pq[s] * S[c][s];
-                st.svorts[c][i] = sv;                                    // impl_rk4.f90:264-270 scales svorts in place
-                if (st.stage == 1) {
-                    st.wa[c][i] = P[c][s];
-                    out[c].v[s] = mq[s] * (P[c][s] + st.c1 * sv);
-                    st.wb[c][i] = P[c][s] + st.c2 * sv;
-                } else {
-                    out[c].v[s] = mq[s] * (P[c][s] + st.c1 * sv);
-                    st.wb[c][i] = Q[c][s] + st.c2 * sv;
-                }
-            }
-        }
+        if (r.g00 && s == 0) continue;
+        fa.v[s] = r.k2i[s & 1] * (ex.v[s] + dy_.v[s]);
+        fb.v[s] = r.k2i[s & 1] * (ey.v[s] - dx_.v[s]);
     }
 }
 
@@ -604,55 +546,21 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
     HypRows<NZ> T;
     hyp_rows<NZ>(T, h, g, r);
 
-    // stage svor (applying a pending stepper update on the way)
+    // stage svor
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        if (a.st.mode == 0) {
-            row_store_s<NZ>(A, z, row_load_g<NZ>(a.svor0, r, z));
-            row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
-            row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
-        } else {
-            double* const sv[3] = {a.svor0, a.svor1, a.svor2};
-            Row4 q[3];
-            staged_update(a.st, sv, r, z, q);
-            row_store_s<NZ>(A, z, q[0]);
-            row_store_s<NZ>(B, z, q[1]);
-            row_store_s<NZ>(C, z, q[2]);
-            row_store_g<NZ>(a.svor2, r, z, q[2]);
-        }
+        row_store_s<NZ>(A, z, row_load_g<NZ>(a.svor0, r, z));
+        row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
+        row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
     }
     __syncthreads();
-    if (a.st.mode == 1 && r.g00) {
-        // adjust_vorticity_mean (field_diagnostics.f90:584-619) on the (0,0) column of xi, eta (slot 0 of A, B)
-        double pa = 0.0, pb = 0.0;
-        for (int j = 1 + (int)threadIdx.x; j < NZ; j += (int)blockDim.x) {
-            const double w = __ldg(&a.st.wz[j]);
-            pa += w * A[cz(j)]; pb += w * B[cz(j)];
-        }
-        // block sum through the scratch (not in use yet)
-        scr.fft[threadIdx.x] = pa; scr.fft[blockDim.x + threadIdx.x] = pb;
-        __syncthreads();
-        for (int st_ = blockDim.x >> 1; st_ > 0; st_ >>= 1) {
-            if ((int)threadIdx.x < st_) {
-                scr.fft[threadIdx.x] += scr.fft[threadIdx.x + st_];
-                scr.fft[blockDim.x + threadIdx.x] += scr.fft[blockDim.x + threadIdx.x + st_];
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x < 2) {
-            double* col = threadIdx.x ? B : A;
-            const double savg = 0.5 * (col[cz(0)] + col[cz(NZ)]) + a.st.fnzi * scr.fft[threadIdx.x ? blockDim.x : 0];
-            const double d = __ldg(&a.st.ini_mean[threadIdx.x]) - savg;
-            col[cz(0)] += d; col[cz(NZ)] += d;
-        }
-        __syncthreads();
-    }
 
-    // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; also the
-    // semi-spectral zeta that feeds the inverse x/y passes (:81)
-    xform2<NZ>(C, XF_DST, nullptr, XF_DST, scr, g);
+    // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; this is also the
+    // semi-spectral zeta that feeds the inverse x/y passes (:81).  A (xi) rides along: its sine sum is the
+    // interior of combine(xi_old), used by the semi-spectral projection below.
+    xform2<NZ>(C, XF_DST, A, XF_DST, scr, g);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -666,7 +574,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         row_store_g<NZ>(a.wsem2, r, z, c);
     }
     __syncthreads();
-    // E = decompose(central_diffz(C)) (:46-47): FD, harmonic part removed, then DST
+    // E = decompose(central_diffz(C)) (:46-47): FD, harmonic part removed, then DST (with eta in B)
     {
         double e0[4], en[4];
 #pragma unroll
@@ -691,63 +599,51 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         }
     }
     __syncthreads();
-    xform2<NZ>(E, XF_DST, nullptr, XF_DST, scr, g);
+    xform2<NZ>(E, XF_DST, B, XF_DST, scr, g);
 
-    // D = B_x - A_y (:39-42); A = k2l2i (E_x + D_y), B = k2l2i (E_y - D_x), (0,0) keeps its mean (:55-76);
-    // then the source of the w inversion D2 = A_y - B_x (:86-90) -> E buffer
+    // Solenoidal projection (:39-76), twice (see project_row):
+    //  * semi-spectral rows (combine(xi_old), combine(eta_old), dzeta/dz) -> wsem0, wsem1, the vorticity that the
+    //    inverse x/y passes take to physical space (:80-82);
+    //  * mixed-spectral rows (xi_old, eta_old re-read from memory, E) -> new svor, and the source of the w
+    //    inversion D2 = A_y - B_x (:86-90) -> E buffer.
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        Row4 fa = row_load_s<NZ>(A, z), fb = row_load_s<NZ>(B, z);
+        Row4 sa = row_load_s<NZ>(A, z), sb = row_load_s<NZ>(B, z), se;
+        Row4 fa = row_load_g<NZ>(a.svor0, r, z), fb = row_load_g<NZ>(a.svor1, r, z);
         const Row4 fe = row_load_s<NZ>(E, z);
-        const Row4 bx = ddx(fb, r), ay = ddy(fa, r);
-        Row4 d;
+        if (z >= 1 && z < NZ) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) d.v[s] = bx.v[s] - ay.v[s];
-        const Row4 ex = ddx(fe, r), ey = ddy(fe, r), dx_ = ddx(d, r), dy_ = ddy(d, r);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            if (r.g00 && s == 0) continue;
-            fa.v[s] = r.k2i[s & 1] * (ex.v[s] + dy_.v[s]);
-            fb.v[s] = r.k2i[s & 1] * (ey.v[s] - dx_.v[s]);
+            for (int s = 0; s < 4; ++s) {
+                const double* c = C + s * LC;
+                sa.v[s] += A[s * LC + cz(0)] * T.phim[it][s & 1] + A[s * LC + cz(NZ)] * T.phip[it][s & 1];
+                sb.v[s] += B[s * LC + cz(0)] * T.phim[it][s & 1] + B[s * LC + cz(NZ)] * T.phip[it][s & 1];
+                se.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi;
+            }
+        } else {
+            se = fe;            // rows 0, NZ of E still hold the one-sided differences
         }
+        project_row(sa, sb, se, r);
+        row_store_g<NZ>(a.wsem0, r, z, sa);
+        row_store_g<NZ>(a.wsem1, r, z, sb);
+        project_row(fa, fb, fe, r);
         row_store_g<NZ>(a.svor0, r, z, fa);
         row_store_g<NZ>(a.svor1, r, z, fb);
-        row_store_s<NZ>(A, z, fa);
-        row_store_s<NZ>(B, z, fb);
         const Row4 ay2 = ddy(fa, r), bx2 = ddx(fb, r);
+        Row4 d;
 #pragma unroll
         for (int s = 0; s < 4; ++s) d.v[s] = ay2.v[s] - bx2.v[s];
         row_store_s<NZ>(E, z, d);
     }
     __syncthreads();
-    // boundary values of D2 (:96-104) and of the mean vorticity (:163-164), before anything is overwritten
-    // (parked in shared memory: they are needed again only in the last stage)
+    // boundary values of D2 (:96-104), before anything is overwritten (parked in shared memory: they are
+    // needed again only in the last stage)
     if (threadIdx.x < 4) {
         const int s = threadIdx.x;
         scr.keep[s] = E[s * LC + cz(0)];
         scr.keep[4 + s] = E[s * LC + cz(NZ)];
     }
-
-    // vorticity to semi-spectral space for the inverse x/y passes (:80-82)
-    xform2<NZ>(A, XF_DST, B, XF_DST, scr, g);
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        Row4 fa = row_load_s<NZ>(A, z), fb = row_load_s<NZ>(B, z);
-        if (z >= 1 && z < NZ) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                fa.v[s] += A[s * LC + cz(0)] * T.phim[it][s & 1] + A[s * LC + cz(NZ)] * T.phip[it][s & 1];
-                fb.v[s] += B[s * LC + cz(0)] * T.phim[it][s & 1] + B[s * LC + cz(NZ)] * T.phip[it][s & 1];
-            }
-        }
-        row_store_g<NZ>(a.wsem0, r, z, fa);
-        row_store_g<NZ>(a.wsem1, r, z, fb);
-    }
-    __syncthreads();
 
     // invert Laplacian (:108-122): E <- green * D2 (rows 1..nz-1), A <- rkz * E (cosine series of dw/dz)
 #pragma unroll
@@ -837,57 +733,32 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 // vorticity tendency, spectral part (reference inversion.f90:298-371 after the
 // fftxyp2s calls).  Inputs are the x/y-transformed fluxes r, q, p
 // (semi-spectral); central_diffz commutes with the x/y FFT, so dq/dz and dp/dz
-// are formed here instead of through two more 2-D FFTs.
+// are formed here instead of through two more 2-D FFTs.  The reference
+// decomposes r, dq/dz, dp/dz, q, p separately (five sine transforms) and then
+// combines them with diffx/diffy; those horizontal derivatives have no z
+// dependence and only mix slots that share k^2 + l^2 (hence phim, phip), so
+// they commute with the decomposition and the curl is taken first:
+//   svorts = decompose( r_y - q_z,  p_z - r_x,  q_x - p_y )      (three sine transforms).
 // ---------------------------------------------------------------------------
 template <int NZ>
-constexpr size_t src_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
+constexpr size_t src_smem_bytes() { return (size_t)(3 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
 
 struct SrcArgs {
     const double* r; const double* q; const double* p;   // semi-spectral fluxes
     double* s0; double* s1; double* s2;                  // svorts (mixed spectral)
 };
 
-// stage a semi-spectral field F (global) with its harmonic part removed -> buffer X (rows 0, NZ kept),
-// and optionally the same for central_diffz(F) -> buffer DX.
-template <int NZ>
-__device__ __forceinline__ void stage_decomposed(double* X, const double* __restrict__ F, const HypRows<NZ>& T,
-                                                 const Grp& r) {
-    const Row4 x0 = row_load_g<NZ>(F, r, 0), xn = row_load_g<NZ>(F, r, NZ);
+// semi-spectral curl of one row from the rows z-1, z, z+1 of q, p and row z of r; dz = 1/(2 dz) in the
+// interior, 1/dz with (lo, hi) = (z, z+1) or (z-1, z) at the boundaries (inversion_utils.f90:653-680)
+__device__ __forceinline__ void curl_row(const Row4& fr, const Row4& fq, const Row4& fp, const Row4& qlo,
+                                         const Row4& qhi, const Row4& plo, const Row4& phi, double dz,
+                                         const Grp& r, Row4& s0, Row4& s1, Row4& s2) {
+    const Row4 ry = ddy(fr, r), rx = ddx(fr, r), qx = ddx(fq, r), py = ddy(fp, r);
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        Row4 x = row_load_g<NZ>(F, r, z);
-        if (z >= 1 && z < NZ) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) x.v[s] -= x0.v[s] * T.phim[it][s & 1] + xn.v[s] * T.phip[it][s & 1];
-        }
-        row_store_s<NZ>(X, z, x);
-    }
-}
-
-template <int NZ>
-__device__ __forceinline__ void stage_diffz_decomposed(double* DX, const double* __restrict__ F, const SpecGeom& g,
-                                                       const HypRows<NZ>& T, const Grp& r) {
-    const Row4 f0 = row_load_g<NZ>(F, r, 0), f1 = row_load_g<NZ>(F, r, 1);
-    const Row4 fn = row_load_g<NZ>(F, r, NZ), fm = row_load_g<NZ>(F, r, NZ - 1);
-    Row4 e0, en;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) { e0.v[s] = g.dzi * (f1.v[s] - f0.v[s]); en.v[s] = g.dzi * (fn.v[s] - fm.v[s]); }
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        Row4 d;
-        if (z == 0) d = e0;
-        else if (z == NZ) d = en;
-        else {
-            const Row4 up = row_load_g<NZ>(F, r, z + 1), dn = row_load_g<NZ>(F, r, z - 1);
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                d.v[s] = (up.v[s] - dn.v[s]) * g.hdzi - (e0.v[s] * T.phim[it][s & 1] + en.v[s] * T.phip[it][s & 1]);
-        }
-        row_store_s<NZ>(DX, z, d);
+    for (int s = 0; s < 4; ++s) {
+        s0.v[s] = ry.v[s] - (qhi.v[s] - qlo.v[s]) * dz;      // dr/dy - dq/dz (:341-347)
+        s1.v[s] = (phi.v[s] - plo.v[s]) * dz - rx.v[s];      // dp/dz - dr/dx (:353-359)
+        s2.v[s] = qx.v[s] - py.v[s];                         // dq/dx - dp/dy (:363-367)
     }
 }
 
@@ -895,11 +766,10 @@ template <int NZ>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_spec(SpecGeom g, SrcArgs a) {
     PS_SMEM(double, sm);
     constexpr int BUF = ZCfg<NZ>::BUF;
-    double* R = sm;
-    double* X = R + BUF;
-    double* Y = X + BUF;
-    double* W = Y + BUF;
-    const ZScr<NZ> scr = make_scr<NZ>(W + BUF);
+    double* S0 = sm;
+    double* S1 = S0 + BUF;
+    double* S2 = S1 + BUF;
+    const ZScr<NZ> scr = make_scr<NZ>(S2 + BUF);
     scr_init<NZ>(scr, g);
     const Grp r = make_grp(g, blockIdx.x);
     Hyp h[2];
@@ -907,41 +777,53 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_sp
     HypRows<NZ> T;
     hyp_rows<NZ>(T, h, g, r);
 
-    // R = decompose(r), X = decompose(dq/dz), Y = decompose(dp/dz), W = decompose(q)
-    stage_decomposed<NZ>(R, a.r, T, r);
-    stage_diffz_decomposed<NZ>(X, a.q, g, T, r);
-    stage_diffz_decomposed<NZ>(Y, a.p, g, T, r);
-    stage_decomposed<NZ>(W, a.q, T, r);
-    __syncthreads();
-    xform2<NZ>(R, XF_DST, X, XF_DST, scr, g);
-    xform2<NZ>(Y, XF_DST, W, XF_DST, scr, g);
-    // xi, eta tendencies (inversion.f90:341-359)
+    // boundary rows of the curl (every thread: they define the harmonic part that is removed from its rows)
+    Row4 b0[3], bn[3];
+    {
+        const Row4 r0 = row_load_g<NZ>(a.r, r, 0), q0 = row_load_g<NZ>(a.q, r, 0), p0 = row_load_g<NZ>(a.p, r, 0);
+        const Row4 q1 = row_load_g<NZ>(a.q, r, 1), p1 = row_load_g<NZ>(a.p, r, 1);
+        curl_row(r0, q0, p0, q0, q1, p0, p1, g.dzi, r, b0[0], b0[1], b0[2]);
+        const Row4 rn = row_load_g<NZ>(a.r, r, NZ), qn = row_load_g<NZ>(a.q, r, NZ), pn = row_load_g<NZ>(a.p, r, NZ);
+        const Row4 qm = row_load_g<NZ>(a.q, r, NZ - 1), pm = row_load_g<NZ>(a.p, r, NZ - 1);
+        curl_row(rn, qn, pn, qm, qn, pm, pn, g.dzi, r, bn[0], bn[1], bn[2]);
+    }
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        const Row4 fr = row_load_s<NZ>(R, z), dq = row_load_s<NZ>(X, z), dp = row_load_s<NZ>(Y, z);
-        const Row4 ry = ddy(fr, r), rx = ddx(fr, r);
-        Row4 s0, s1;
+        Row4 s[3];
+        if (z == 0) { s[0] = b0[0]; s[1] = b0[1]; s[2] = b0[2]; }
+        else if (z == NZ) { s[0] = bn[0]; s[1] = bn[1]; s[2] = bn[2]; }
+        else {
+            const Row4 fr = row_load_g<NZ>(a.r, r, z), fq = row_load_g<NZ>(a.q, r, z), fp = row_load_g<NZ>(a.p, r, z);
+            const Row4 qlo = row_load_g<NZ>(a.q, r, z - 1), qhi = row_load_g<NZ>(a.q, r, z + 1);
+            const Row4 plo = row_load_g<NZ>(a.p, r, z - 1), phi = row_load_g<NZ>(a.p, r, z + 1);
+            curl_row(fr, fq, fp, qlo, qhi, plo, phi, g.hdzi, r, s[0], s[1], s[2]);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) { s0.v[s] = ry.v[s] - dq.v[s]; s1.v[s] = dp.v[s] - rx.v[s]; }
-        row_store_g<NZ>(a.s0, r, z, s0);       // dr/dy - dq/dz
-        row_store_g<NZ>(a.s1, r, z, s1);       // dp/dz - dr/dx
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    s[c].v[k] -= b0[c].v[k] * T.phim[it][k & 1] + bn[c].v[k] * T.phip[it][k & 1];
+        }
+        row_store_s<NZ>(S0, z, s[0]);
+        row_store_s<NZ>(S1, z, s[1]);
+        row_store_s<NZ>(S2, z, s[2]);
     }
     __syncthreads();
-    // zeta tendency dq/dx - dp/dy (:363-367)
-    stage_decomposed<NZ>(R, a.p, T, r);
-    __syncthreads();
-    xform2<NZ>(R, XF_DST, nullptr, XF_DST, scr, g);
+    xform2<NZ>(S0, XF_DST, S1, XF_DST, scr, g);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        const Row4 py = ddy(row_load_s<NZ>(R, z), r), qx = ddx(row_load_s<NZ>(W, z), r);
-        Row4 s2;
+        row_store_g<NZ>(a.s0, r, z, row_load_s<NZ>(S0, z));
+        row_store_g<NZ>(a.s1, r, z, row_load_s<NZ>(S1, z));
+    }
+    xform2<NZ>(S2, XF_DST, nullptr, XF_DST, scr, g);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) s2.v[s] = qx.v[s] - py.v[s];
-        row_store_g<NZ>(a.s2, r, z, s2);
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        row_store_g<NZ>(a.s2, r, z, row_load_s<NZ>(S2, z));
     }
 }
 

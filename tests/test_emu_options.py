@@ -67,10 +67,3 @@ def test_geophysical_length_scale_and_anisotropic_grid(emu):
 def test_time_limit_clips_dt(emu):
     t, to = run_pair(emu, (8, 8, 8), [-0.5 * math.pi] * 3, [math.pi] * 3, limit=0.03, nsteps=2)
     assert t == pytest.approx(0.03, rel=1e-12) and to == pytest.approx(0.03, rel=1e-12)
-
-
-@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
-def test_update_fused_into_vor2vel_staging(emu, stepper, monkeypatch):
-    """PS3D_FUSE_UPDATE=1 (off by default: measured slower) must give the same trajectory."""
-    monkeypatch.setenv("PS3D_FUSE_UPDATE", "1")
-    run_pair(emu, (8, 16, 8), [-0.5 * math.pi] * 3, [math.pi] * 3, stepper=stepper, nsteps=2)
