@@ -19,22 +19,37 @@
 
 namespace ps3d {
 
-// Scratch index policies (bank-conflict-free for the stride-R Stockham scatter AND the unit-stride gather;
-// shared memory has 32 4-byte banks, a half-warp of 8-byte accesses must hit 16 distinct 8-byte columns):
-//  IxSwz  : one FFT per scratch line, lanes of a warp are consecutive butterflies u.  XOR swizzle
-//           b0^=i4, b1^=i5, b2^=i6, b3^=i6: the bits that vary across a half-warp in pass 1 (i3..i6),
-//           pass 2 (i0..i2,i6) and pass 3 (i0..i3) always map onto 16 distinct columns.  No padding.
-//  IxIlv  : NF FFTs interleaved (element i of FFT f at NF*sigma(i) + f), lanes = f fastest then u.  sigma
-//           XORs bit 3 (NF = 8) or bits 3,4 (NF = 4) into the low bits so that the 16/NF butterflies of a
-//           half-warp land on distinct columns in both the stride-8 scatter and the unit-stride gather.
+// Scratch layouts of the Stockham exchanges (put/get of complex element i of this thread's FFT):
+//  IxSwz  : one FFT per scratch line, re and im in two separate planes of doubles (sre, sim), lanes of a warp
+//           are consecutive butterflies u.  XOR swizzle b0^=i4, b1^=i5, b2^=i6, b3^=i6: the bits that vary
+//           across a half-warp in pass 1 (i3..i6), pass 2 (i0..i2,i6) and pass 3 (i0..i3) always map onto 16
+//           distinct 8-byte columns (shared memory: 32 4-byte banks).  No padding.  Used by the z-column
+//           kernels, whose two column buffers are the two planes.
+//  IxIlv  : NF = 8 FFTs interleaved as complex numbers: element i of FFT f is the double2 at 8*i + f of one
+//           array (sre; sim unused), lanes = f fastest then u.  A quarter-warp (the unit of a 128-bit shared
+//           access) is the 8 FFTs at one element index: one contiguous 128-byte row, conflict-free in the
+//           stride-8 scatter and the unit-stride gather alike, half the shared-memory instructions of split
+//           planes and no swizzle arithmetic.  Used by the x/y line kernels.
 struct IxSwz {
     __device__ __forceinline__ int operator()(int i) const { return i ^ (((i >> 4) & 7) | (((i >> 6) & 1) << 3)); }
+    __device__ __forceinline__ void put(double* sre, double* sim, int i, double re, double im) const {
+        const int k = (*this)(i);
+        sre[k] = re; sim[k] = im;
+    }
+    __device__ __forceinline__ void get(const double* sre, const double* sim, int i, double& re, double& im) const {
+        const int k = (*this)(i);
+        re = sre[k]; im = sim[k];
+    }
 };
 template <int NF>
 struct IxIlv {
     int f;
-    __device__ __forceinline__ int operator()(int i) const {
-        return NF * (i ^ ((i >> 3) & (16 / NF - 1))) + f;
+    __device__ __forceinline__ void put(double* sre, double*, int i, double re, double im) const {
+        reinterpret_cast<double2*>(sre)[NF * i + f] = make_double2(re, im);
+    }
+    __device__ __forceinline__ void get(const double* sre, const double*, int i, double& re, double& im) const {
+        const double2 c = reinterpret_cast<const double2*>(sre)[NF * i + f];
+        re = c.x; im = c.y;
     }
 };
 
@@ -94,25 +109,28 @@ __device__ __forceinline__ void radix(double* xr, double* xi) {
     }
 }
 
+// Twiddle sources.  Only the radix-8 passes that are not the last pass carry twiddles (the radix-4/2 tail is
+// always the last pass), and butterfly b of such a pass needs W^m, W^2m, ..., W^7m with m = s * (b / s),
+// W = exp(-+2 pi i / N).  A source hands out W^m, W^2m, W^4m as (cos, sin) pairs; the other powers are single
+// products in fft_pass.
+//  TwGlobal : read-only global table tw[j] = exp(2 pi i j / NTW), NTW = twscale * N; all three powers come
+//             from the table (correctly rounded).  Used by the x/y line kernels.
+//  TwSin    : (zcol.cuh) W^m from the block's shared sine table, W^2m and W^4m by squaring.
+struct TwGlobal {
+    const double2* __restrict__ tw;
+    int twscale;
+    __device__ __forceinline__ void get(int /*pass*/, int s, int p, double2& w1, double2& w2, double2& w4) const {
+        const int m1 = s * p * twscale;
+        w1 = __ldg(&tw[m1]); w2 = __ldg(&tw[2 * m1]); w4 = __ldg(&tw[4 * m1]);
+    }
+};
 // One Stockham DIF pass of radix R on the thread's eight values.
 //   butterfly g (g < 8/R) has index b = u + g*N/8 in [0, N/R); its inputs are
 //   v[g + k*(8/R)], its outputs overwrite the same registers (output j at
 //   v[g + j*(8/R)]) and belong at x'[q + s*(R*p + j)], p = b / s, q = b % s.
-// `s` is the product of the radices of the previous passes.
-// tw[m] = (cos(2 pi m / NTW), sin(2 pi m / NTW)), twscale = NTW / N.
-// twiddles of one radix-8 butterfly: W^m1, W^2m1, W^4m1 (loaded ahead of the exchange that precedes the pass)
-struct Tw3 { double2 w1, w2, w4; };
-template <int N>
-__device__ __forceinline__ Tw3 tw_load8(int u, int s, const double2* __restrict__ tw, int twscale) {
-    const int m1 = s * (u / s) * twscale;
-    Tw3 t;
-    t.w1 = __ldg(&tw[m1]); t.w2 = __ldg(&tw[2 * m1]); t.w4 = __ldg(&tw[4 * m1]);
-    return t;
-}
-
-template <int N, int R, bool INV>
-__device__ __forceinline__ void fft_pass(double (&vr)[8], double (&vi)[8], int u, int s,
-                                         const double2* __restrict__ tw, int twscale, const Tw3* pre = nullptr) {
+// `s` is the product of the radices of the previous passes, `pass` their number.
+template <int N, int R, bool INV, class TW>
+__device__ __forceinline__ void fft_pass(double (&vr)[8], double (&vi)[8], int u, int s, int pass, const TW& tws) {
     constexpr int G = 8 / R;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -120,28 +138,20 @@ __device__ __forceinline__ void fft_pass(double (&vr)[8], double (&vi)[8], int u
 #pragma unroll
         for (int k = 0; k < R; ++k) { xr[k] = vr[g + k * G]; xi[k] = vi[g + k * G]; }
         radix<R, INV>(xr, xi);
-        if (s * R < N) {
+        if (R == 8 && s * R < N) {
             const int b = u + g * (N / 8);
             const int p = b / s;
-            const int m1 = s * p * twscale;
-            // W^m1, W^2m1, W^4m1 from the table (correctly rounded), the other powers as single products:
-            // 3 table loads per butterfly instead of 7, at most one extra rounding per twiddle
-            double wr[R], wi[R];
+            double wr[8], wi[8];
             {
-                const double2 w1 = (R == 8 && pre) ? pre->w1 : __ldg(&tw[m1]);
+                double2 w1, w2, w4;
+                tws.get(pass, s, p, w1, w2, w4);
                 wr[1] = w1.x; wi[1] = INV ? w1.y : -w1.y;
-                if (R > 2) {
-                    const double2 w2 = (R == 8 && pre) ? pre->w2 : __ldg(&tw[2 * m1]);
-                    wr[2] = w2.x; wi[2] = INV ? w2.y : -w2.y;
-                    wr[3] = wr[1] * wr[2] - wi[1] * wi[2]; wi[3] = wr[1] * wi[2] + wi[1] * wr[2];
-                }
-                if (R > 4) {
-                    const double2 w4 = (R == 8 && pre) ? pre->w4 : __ldg(&tw[4 * m1]);
-                    wr[4] = w4.x; wi[4] = INV ? w4.y : -w4.y;
-                    wr[5] = wr[1] * wr[4] - wi[1] * wi[4]; wi[5] = wr[1] * wi[4] + wi[1] * wr[4];
-                    wr[6] = wr[2] * wr[4] - wi[2] * wi[4]; wi[6] = wr[2] * wi[4] + wi[2] * wr[4];
-                    wr[7] = wr[3] * wr[4] - wi[3] * wi[4]; wi[7] = wr[3] * wi[4] + wi[3] * wr[4];
-                }
+                wr[2] = w2.x; wi[2] = INV ? w2.y : -w2.y;
+                wr[4] = w4.x; wi[4] = INV ? w4.y : -w4.y;
+                wr[3] = wr[1] * wr[2] - wi[1] * wi[2]; wi[3] = wr[1] * wi[2] + wi[1] * wr[2];
+                wr[5] = wr[1] * wr[4] - wi[1] * wi[4]; wi[5] = wr[1] * wi[4] + wi[1] * wr[4];
+                wr[6] = wr[2] * wr[4] - wi[2] * wi[4]; wi[6] = wr[2] * wi[4] + wi[2] * wr[4];
+                wr[7] = wr[3] * wr[4] - wi[3] * wi[4]; wi[7] = wr[3] * wi[4] + wi[3] * wr[4];
             }
 #pragma unroll
             for (int j = 1; j < R; ++j) {
@@ -166,9 +176,7 @@ __device__ __forceinline__ void fft_scatter(const double (&vr)[8], const double 
         const int q = b - p * s;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int idx = ix(q + s * (R * p + j));
-            sre[idx] = vr[g + j * G];
-            sim[idx] = vi[g + j * G];
+            ix.put(sre, sim, q + s * (R * p + j), vr[g + j * G], vi[g + j * G]);
         }
     }
 }
@@ -178,9 +186,7 @@ __device__ __forceinline__ void fft_gather(double (&vr)[8], double (&vi)[8], int
                                            const double* __restrict__ sre, const double* __restrict__ sim, const IX& ix) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int idx = ix(u + e * (N / 8));
-        vr[e] = sre[idx];
-        vi[e] = sim[idx];
+        ix.get(sre, sim, u + e * (N / 8), vr[e], vi[e]);
     }
 }
 
@@ -191,37 +197,25 @@ __host__ __device__ constexpr bool is_pow2(int n) { return n > 0 && (n & (n - 1)
 
 // Full transform.  All N/8 threads of the FFT must call this together (it
 // contains __syncthreads(), so every thread of the BLOCK must take part, with
-// `active` false for threads that own no FFT).  sre/sim: this FFT's scratch
-// line (N doubles each for IxSwz).  The scratch must not be in use by other
-// threads when the call is entered.
-template <int N, bool INV, class IX>
+// `active` false for threads that own no FFT: they neither read nor write the
+// scratch).  sre/sim: this FFT's scratch line (N doubles each for IxSwz).  The
+// scratch must not be in use by other threads when the call is entered.
+template <int N, bool INV, class IX, class TW>
 __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int u, bool active,
                                            double* __restrict__ sre, double* __restrict__ sim, const IX& ix,
-                                           const double2* __restrict__ tw, int twscale) {
+                                           const TW& tws) {
     static_assert(is_pow2(N) && N >= 8, "power-of-two lengths >= 8 only");
     int s = 1;
-    // radix-8 passes while at least a factor 8 remains beyond this pass or the remainder is exactly 8
     constexpr int L = (N == 8) ? 3 : (N == 16) ? 4 : (N == 32) ? 5 : (N == 64) ? 6 : (N == 128) ? 7 :
                       (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : (N == 4096) ? 12 : -1;
     static_assert(L > 0, "unsupported FFT length");
     constexpr int N8 = L / 3;            // number of radix-8 passes
-    constexpr int TAIL = 1 << (L % 3);   // 1, 2 or 4
-#ifdef PS3D_TW_PREFETCH
-    Tw3 t = tw_load8<N>(u, 1, tw, twscale);
-#endif
+    constexpr int TAIL = 1 << (L % 3);   // 1, 2 or 4: radix of the last pass when L is not a multiple of 3
 #pragma unroll
     for (int pass = 0; pass < N8; ++pass) {
-#ifdef PS3D_TW_PREFETCH
-        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale, (pass == 0 || s * 8 < N) ? &t : nullptr);
-#else
-        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, tw, twscale);
-#endif
+        if (active) fft_pass<N, 8, INV>(vr, vi, u, s, pass, tws);
         const bool last = (pass == N8 - 1) && (TAIL == 1);
         if (!last) {
-            // twiddles of the next radix-8 pass travel with the exchange (hides their L1/L2 latency)
-#ifdef PS3D_TW_PREFETCH
-            if (pass + 1 < N8 && s * 64 < N) t = tw_load8<N>(u, s * 8, tw, twscale);
-#endif
             if (pass > 0) __syncthreads();               // WAR: everyone has gathered
             if (active) fft_scatter<N, 8>(vr, vi, u, s, sre, sim, ix);
             __syncthreads();
@@ -230,9 +224,9 @@ __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int
         s *= 8;
     }
     if (TAIL == 2) {
-        if (active) fft_pass<N, 2, INV>(vr, vi, u, s, tw, twscale);
+        if (active) fft_pass<N, 2, INV>(vr, vi, u, s, N8, tws);
     } else if (TAIL == 4) {
-        if (active) fft_pass<N, 4, INV>(vr, vi, u, s, tw, twscale);
+        if (active) fft_pass<N, 4, INV>(vr, vi, u, s, N8, tws);
     }
 }
 

@@ -9,7 +9,7 @@
 // FFT: c = a + i b, separated afterwards by Hermitian symmetry), each by N/8
 // threads: block = N threads, lane = (f = t&7, u = t>>3) so that one warp
 // load instruction covers 4 rows x 128 B (the minimum number of L1 wavefronts).
-// The 8 FFTs are interleaved in the shared-memory scratch (IxIlv<8>).
+// The 8 FFTs are interleaved, as complex numbers, in the shared-memory scratch (IxIlv<8>).
 //
 // Output packing is the reference's (stafft.f90:55-58): row k holds Re X_k,
 // row N-k holds Im X_k (k = 1..N/2-1), rows 0 and N/2 the real DC/Nyquist
@@ -73,6 +73,15 @@ struct LineArgs {
 };
 
 __device__ __forceinline__ double* row_dst(const struct LineArgs& a, int k);
+// The row offsets of a tile do not depend on the tile, so the compiler hoists all of them out of the
+// persistent tile loop and then spills them (64-bit each) to local memory; an opaque copy of the thread's
+// row index keeps the (cheap, branch-free) offset arithmetic inside the loop and the kernel spill-free.
+__device__ __forceinline__ int tile_local(int u) {
+#ifndef PS3D_EMU
+    asm volatile("" : "+r"(u));
+#endif
+    return u;
+}
 // sweep inputs are dead after the load: streaming (evict-first) loads
 __device__ __forceinline__ double2 ld2(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
@@ -94,10 +103,11 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
     const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
+    const int ul = tile_local(u);
     double vr[8], vi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const long long off = ibase + row_off(a.in_map, u + e * (N / 8));
+        const long long off = ibase + row_off(a.in_map, ul + e * (N / 8));
         if (PRO == PRO_CROSS) {
             const double2 x0 = ld2(a.in0 + off), x1 = ld2(a.in1 + off);
             const double2 x2 = ld2(a.in2 + off), x3 = ld2(a.in3 + off);
@@ -111,27 +121,26 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     double* sre = sm;
     double* sim = sm + LINE_NF * N;
     const IxIlv<LINE_NF> ix{f};
-    block_cfft<N, false>(vr, vi, u, true, sre, sim, ix, a.tw, a.twscale);
+    block_cfft<N, false>(vr, vi, u, true, sre, sim, ix, TwGlobal{a.tw, a.twscale});
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int idx = ix(u + e * (N / 8));
-        sre[idx] = vr[e]; sim[idx] = vi[e];
-    }
+    for (int e = 0; e < 8; ++e) ix.put(sre, sim, u + e * (N / 8), vr[e], vi[e]);
     __syncthreads();
     const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * LINE_ZC + 2 * f;
     const double sc = a.scale, hs = 0.5 * a.scale;
-#pragma unroll
+#pragma unroll(PRO == PRO_CROSS ? 2 : 4)
     for (int e = 0; e < 4; ++e) {
         const int k = u + e * (N / 8);
         if (k == 0) {
-            const int i0 = ix(0);
-            st2f(a.final_store, row_dst(a, 0) + obase, sre[i0] * sc, sim[i0] * sc);
-            const int ih = ix(N / 2);
-            st2f(a.final_store, row_dst(a, N / 2) + obase, sre[ih] * sc, sim[ih] * sc);
+            double p, q;
+            ix.get(sre, sim, 0, p, q);
+            st2f(a.final_store, row_dst(a, 0) + obase, p * sc, q * sc);
+            ix.get(sre, sim, N / 2, p, q);
+            st2f(a.final_store, row_dst(a, N / 2) + obase, p * sc, q * sc);
         } else {
-            const int ik = ix(k), im = ix(N - k);
-            const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
+            double p, q, r, s;
+            ix.get(sre, sim, k, p, q);
+            ix.get(sre, sim, N - k, r, s);
             // A_k = (C_k + conj C_{N-k})/2, B_k = (C_k - conj C_{N-k})/(2i)
             st2f(a.final_store, row_dst(a, k) + obase, (p + r) * hs, (q + s) * hs);       // Re A, Re B
             st2f(a.final_store, row_dst(a, N - k) + obase, (q - s) * hs, (r - p) * hs);   // Im A, Im B
@@ -181,15 +190,14 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
             rk = z ? 0.0 : xa[e].x; qk = z ? 0.0 : xa[e].y;
             rm = z ? 0.0 : xb[e].x; qm = z ? 0.0 : xb[e].y;
         }
-        const int ik = ix(k), im = ix(kb);
-        sre[ik] = rk; sim[ik] = qk;
-        sre[im] = rm; sim[im] = qm;
+        ix.put(sre, sim, k, rk, qk);
+        ix.put(sre, sim, kb, rm, qm);
     }
     __syncthreads();
     double vr[8], vi[8];
     fft_gather<N>(vr, vi, u, sre, sim, ix);
     __syncthreads();
-    block_cfft<N, true>(vr, vi, u, true, sre, sim, ix, a.tw, a.twscale);
+    block_cfft<N, true>(vr, vi, u, true, sre, sim, ix, TwGlobal{a.tw, a.twscale});
     const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * LINE_ZC + 2 * f;
     const double sc = a.scale;
 #pragma unroll

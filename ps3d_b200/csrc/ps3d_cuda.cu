@@ -133,9 +133,14 @@ struct Ctx {
         g.zm = zm.p; g.zp = zp.p; g.rkz = rkz.p; g.gamtop = gamtop.p; g.gambot = gambot.p;
         g.Lz = extent[2]; g.dzi = 1.0 / dx[2]; g.hdzi = 0.5 * (1.0 / dx[2]);
         g.tw = tw.p; g.ntw = ntw;
+        g.ap0 = 0; g.npf = nyl / 2;               // all groups (operator mode)
         return g;
     }
     int ngroups() const { return (nx / 2 + 1) * (nyl / 2); }
+    // the hot-loop column kernels run as two launches: the fast instantiation on the pairs (a, ny-a), a >= 1,
+    // and the general one on the pair (0, ny/2) of the rank that owns ky = 0 (zcol.cuh)
+    SpecGeom geom_fast() const { SpecGeom g = geom(); g.ap0 = (rank == 0) ? 1 : 0; g.npf = nyl / 2 - g.ap0; return g; }
+    SpecGeom geom_gen() const { SpecGeom g = geom(); g.ap0 = 0; g.npf = 1; return g; }
 };
 
 static Ctx* g_ctx = nullptr;
@@ -479,10 +484,19 @@ static void launch_zop(Ctx& c, int op, const double* in, double* out) {
 
 template <int NZ>
 static void launch_v2v_n(Ctx& c, const V2VArgs& a) {
-    const size_t sm = v2v_smem_bytes<NZ>();
-    allow_smem(k_vor2vel_spec<NZ>, sm);
-    PS_LAUNCH((k_vor2vel_spec<NZ>), dim3(c.ngroups()), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom(), a);
-    ++c.launches;
+    const SpecGeom gf = c.geom_fast();
+    if (gf.npf > 0) {
+        const size_t sm = v2v_smem_bytes<NZ>(false);
+        allow_smem(k_vor2vel_spec<NZ, false>, sm);
+        PS_LAUNCH((k_vor2vel_spec<NZ, false>), dim3((c.nx / 2 + 1) * gf.npf), dim3(ZCfg<NZ>::NT), sm, c.stream, gf, a);
+        ++c.launches;
+    }
+    if (c.rank == 0) {
+        const size_t sm = v2v_smem_bytes<NZ>(true);
+        allow_smem(k_vor2vel_spec<NZ, true>, sm);
+        PS_LAUNCH((k_vor2vel_spec<NZ, true>), dim3(c.nx / 2 + 1), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom_gen(), a);
+        ++c.launches;
+    }
 }
 static void launch_v2v(Ctx& c, const V2VArgs& a) {
     switch (c.nz) {
@@ -495,10 +509,19 @@ static void launch_v2v(Ctx& c, const V2VArgs& a) {
 
 template <int NZ>
 static void launch_src_n(Ctx& c, const SrcArgs& a) {
-    const size_t sm = src_smem_bytes<NZ>();
-    allow_smem(k_source_spec<NZ>, sm);
-    PS_LAUNCH((k_source_spec<NZ>), dim3(c.ngroups()), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom(), a);
-    ++c.launches;
+    const SpecGeom gf = c.geom_fast();
+    if (gf.npf > 0) {
+        const size_t sm = src_smem_bytes<NZ>(false);
+        allow_smem(k_source_spec<NZ, false>, sm);
+        PS_LAUNCH((k_source_spec<NZ, false>), dim3((c.nx / 2 + 1) * gf.npf), dim3(ZCfg<NZ>::NT), sm, c.stream, gf, a);
+        ++c.launches;
+    }
+    if (c.rank == 0) {
+        const size_t sm = src_smem_bytes<NZ>(true);
+        allow_smem(k_source_spec<NZ, true>, sm);
+        PS_LAUNCH((k_source_spec<NZ, true>), dim3(c.nx / 2 + 1), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom_gen(), a);
+        ++c.launches;
+    }
 }
 static void launch_src(Ctx& c, const SrcArgs& a) {
     switch (c.nz) {

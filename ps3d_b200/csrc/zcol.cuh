@@ -13,14 +13,20 @@
 // the y-mirror of a column is its neighbour kyl^1 and a slab of ky' is closed
 // under mirroring (replaces mpi_reverse entirely).
 //
+// Two instantiations of every kernel (template parameter GEN):
+//  * GEN = false, the fast path: pairs (a, ny-a) with a >= 1.  Both columns of a pair share k^2 + l^2, hence
+//    one set of harmonic functions phi-/phi+/theta per block.
+//  * GEN = true: the pair (0, ny/2) (different k^2 + l^2 per column, holds the (0,0) column with its linear
+//    harmonic functions and the mean-flow work).  nx/2 + 1 blocks on the rank that owns ky = 0.
+//
 // Work split inside a block (NT = nz/2 threads):
 //  * pointwise stages are "z-owner": thread t owns rows z = t, t + NT (and
 //    thread 0 also row nz) of ALL four slots, so every x/y mirror coupling is a
-//    register operation and the hyperbolic functions of a row are evaluated once
-//    and kept in registers for the whole kernel;
+//    register operation;
 //  * DST-I / DCT-I of length nz follow the reference's own reduction to a real FFT of
 //    length nz (stafft.f90:410-550: pre-process, forfft, post-process), two columns per
-//    complex FFT of length nz (same block_cfft as the x/y passes).  The post-processing
+//    complex FFT of length nz (same block_cfft as the x/y passes), IN PLACE: the two column
+//    buffers are the re/im exchange scratch of their own FFT.  The post-processing
 //    recurrence x(2j+1) = x(2j-1) +- sqrt2*wk(.) (stafft.f90:466-471, 526-533) is a prefix
 //    sum: done as a per-thread scan of 4 + a warp-shuffle scan, i.e. O(log n) roundings
 //    instead of the reference's O(n).  Two 4-slot fields are transformed concurrently
@@ -28,7 +34,11 @@
 //
 // The N-sized tables of the reference (phim, phip, thetam, thetap, dthetam,
 // dthetap, green, filt: inversion_utils.f90:281-369,484-542) are never
-// stored: they are recomputed per group from exp(-kl*zp), exp(-kl*zm).
+// stored in HBM: phim/phip of the block's (kx, ky) are built once per block in shared memory from
+// exp(-kl*zp), exp(-kl*zm), the thetas are derived from them where they are used.
+//
+// Shared memory at nz = 512: 4 column buffers of 4 x 513 doubles + 10.8 KB of tables = 74.7 KB, registers
+// capped at 80: three blocks (24 warps) per SM.
 #pragma once
 
 #include "fft_core.cuh"
@@ -37,7 +47,7 @@ namespace ps3d {
 
 struct SpecGeom {
     int nx, nyl, nz, pz;
-    int has00;              // this rank owns the (kx,ky) = (0,0) column (at kx = 0, kyl = 0)
+    int has00;              // this rank owns the (kx,ky) = (0,0) column (at kx = 0, kyl = 0), i.e. the pair (0, ny/2)
     const double* kxd;      // [nx/2+1]  x wavenumber used by diffx for slot pair b (0 at b = 0, nx/2)
     const double* kyd;      // [nyl/2]   y wavenumber used by diffy for local pair a' (0 for the (0, ny/2) pair)
     const double* k2l2;     // [nx/2+1][nyl]  k^2+l^2   (inversion_utils.f90:240-258)
@@ -50,17 +60,30 @@ struct SpecGeom {
     double Lz, dzi, hdzi;
     const double2* tw;
     int ntw;
+    int ap0, npf;           // group mapping of a launch: block id -> b = id / npf, a' = ap0 + id % npf
 };
 
 template <int NZ>
 struct ZCfg {
     static constexpr int TPF = NZ / 8;            // threads per complex FFT of length NZ (two columns)
     static constexpr int NT = 4 * TPF;            // 4 FFTs = two 4-slot fields at a time  (= NZ/2)
-    static constexpr int LC = NZ + 16;            // column buffer stride (rows 0..NZ, swizzled in 16-row blocks)
+    // column buffer stride: rows 0..NZ, XOR-swizzled in 16-row blocks (row NZ lands at NZ + (NZ/16 & 15))
+    static constexpr int LC = (((NZ >> 4) & 15) != 0) ? NZ + 16 : NZ + 1;
     static constexpr int BUF = 4 * LC;            // doubles per 4-slot field buffer
     static constexpr int NSIN = NZ / 2 + 2;       // sin(m pi/nz), m = 0..nz/2
-    static constexpr int SCR = 4 * 2 * NZ + NSIN + 64 + 32;   // FFT scratch (4 x re/im x NZ) + sine table + warp totals + kept scalars
+    static constexpr int PST = NZ + 1;            // stride of one phim / phip plane
     static constexpr int ZI = 3;                  // rows per thread: t, t+NT, and NZ (thread 0 only)
+    // tables behind the column buffers: sines, phim/phip planes (one per distinct k^2+l^2), warp totals (40),
+    // parked scalars (24)
+    static constexpr int aux(bool gen) { return NSIN + (gen ? 4 : 2) * PST + 40 + 24; }
+    // blocks per SM the launch bounds ask for: what shared memory allows, at no fewer than 80 registers
+    static constexpr int ctas(int nbuf, bool gen) {
+        const int bytes = (nbuf * BUF + aux(gen)) * 8 + 1024;
+        int c = 233472 / bytes;
+        if (c > 768 / NT) c = 768 / NT;
+        if (c > 8) c = 8;
+        return c < 1 ? 1 : c;
+    }
 };
 
 // row z of a column buffer: XOR swizzle inside 16-row blocks, so that both the unit-stride (z-owner)
@@ -68,23 +91,24 @@ struct ZCfg {
 __device__ __forceinline__ int cz(int z) { return z ^ ((z >> 4) & 15); }
 
 // ---- group bookkeeping -----------------------------------------------------
+template <bool GEN> __device__ __forceinline__ constexpr int sy_of(int s) { return GEN ? (s & 1) : 0; }
+
 struct Grp {
     int b, ap;
     bool dupx;          // b == 0 or b == nx/2: the x-mirror slot is the column itself (inactive)
     bool g00;           // this group holds the (0,0) column in slot 0
     double kx, ky;      // diff wavenumbers
-    double k2[2], k2i[2];
+    double k2[2], k2i[2];   // per sy (fast path: [0] only)
     long long off[4];   // column offsets (doubles) of slots s = 2*sx + sy
-    long long col[4];   // column index kx*nyl + kyl of the slots (per-column tables of the steppers)
 };
 
+template <bool GEN>
 __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
     Grp r;
-    const int npair = g.nyl / 2;
-    r.b = gid / npair;
-    r.ap = gid - r.b * npair;
+    r.b = gid / g.npf;
+    r.ap = g.ap0 + (gid - r.b * g.npf);
     r.dupx = (r.b == 0) || (2 * r.b == g.nx);
-    r.g00 = g.has00 && r.b == 0 && r.ap == 0;
+    r.g00 = GEN && g.has00 && r.b == 0 && r.ap == 0;
     r.kx = __ldg(&g.kxd[r.b]);
     r.ky = __ldg(&g.kyd[r.ap]);
     const int kxm = r.dupx ? r.b : g.nx - r.b;
@@ -93,16 +117,11 @@ __device__ __forceinline__ Grp make_grp(const SpecGeom& g, int gid) {
         const int kyl = 2 * r.ap + sy;
         r.k2[sy] = __ldg(&g.k2l2[(long long)r.b * g.nyl + kyl]);
         r.k2i[sy] = __ldg(&g.k2l2i[(long long)r.b * g.nyl + kyl]);
-        r.col[sy] = (long long)r.b * g.nyl + kyl;
-        r.col[2 + sy] = (long long)kxm * g.nyl + kyl;
-        r.off[sy] = r.col[sy] * g.pz;
-        r.off[2 + sy] = r.col[2 + sy] * g.pz;
+        r.off[sy] = ((long long)r.b * g.nyl + kyl) * g.pz;
+        r.off[2 + sy] = ((long long)kxm * g.nyl + kyl) * g.pz;
     }
     return r;
 }
-
-// number of active slots: 2 when the x-mirror is the column itself
-__device__ __forceinline__ int nslots(const Grp& r) { return r.dupx ? 2 : 4; }
 
 // ---- z-owner helpers ----------------------------------------------------------
 // row owned by this thread in iteration `it` (-1: none)
@@ -160,6 +179,54 @@ __device__ __forceinline__ Row4 ddy(const Row4& f, const Grp& r) {
     return d;
 }
 
+// ---- shared tables behind the column buffers ---------------------------------
+template <int NZ>
+struct ZScr {
+    double* sintab;   // [NZ/2 + 1]  sin(m pi / NZ)
+    double* phim;     // [planes][PST]  harmonic functions of this block's (kx, ky): plane sy (fast path: one plane)
+    double* phip;
+    double* wt;       // [40] warp totals of the group scan / sum
+    double* keep;     // [24] block-wide scalars parked between stages (keeps them out of registers)
+};
+template <int NZ, bool GEN>
+__device__ __forceinline__ ZScr<NZ> make_scr(double* base) {
+    typedef ZCfg<NZ> Z;
+    ZScr<NZ> s;
+    s.sintab = base;
+    s.phim = s.sintab + Z::NSIN;
+    s.phip = s.phim + (GEN ? 2 : 1) * Z::PST;
+    s.wt = s.phip + (GEN ? 2 : 1) * Z::PST;
+    s.keep = s.wt + 40;
+    return s;
+}
+// sine table (once per block; followed by a barrier in the caller)
+template <int NZ>
+__device__ __forceinline__ void scr_init(const ZScr<NZ>& sc, const SpecGeom& g) {
+    const int step = g.ntw / (2 * NZ);                      // tw[m] = exp(2 pi i m / ntw), ntw >= 2 NZ
+    for (int m = threadIdx.x; m <= NZ / 2; m += blockDim.x) sc.sintab[m] = __ldg(&g.tw[m * step]).y;
+}
+template <int NZ>
+__device__ __forceinline__ double sin_j(const ZScr<NZ>& sc, int j) { return sc.sintab[(j <= NZ / 2) ? j : NZ - j]; }
+template <int NZ>
+__device__ __forceinline__ double cos_j(const ZScr<NZ>& sc, int j) {
+    return (j <= NZ / 2) ? sc.sintab[NZ / 2 - j] : -sc.sintab[j - NZ / 2];
+}
+
+// FFT twiddles of the z transforms from the sine table (fft_core.cuh, "Twiddle sources"): the butterflies of the
+// twiddled passes need W^m with m = s * (b / s) < NZ/8, and (cos, sin)(2 pi m / NZ) = (sintab[NZ/2 - 2m], sintab[2m]).
+// W^2m and W^4m by squaring (two and four roundings more, ~1e-16): no table look-up in global memory on the
+// critical path of these latency-bound kernels.
+template <int NZ>
+struct TwSin {
+    const double* st;
+    __device__ __forceinline__ void get(int /*pass*/, int s, int p, double2& w1, double2& w2, double2& w4) const {
+        const int m2 = 2 * s * p;
+        w1 = make_double2(st[NZ / 2 - m2], st[m2]);
+        w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * (w1.x * w1.y));
+        w4 = make_double2(w2.x * w2.x - w2.y * w2.y, 2.0 * (w2.x * w2.y));
+    }
+};
+
 // ---- harmonic (Laplace) functions on the fly -------------------------------
 // block constants per sy (inversion_utils.f90:494-503, 529-530)
 struct Hyp { double kl, ef, div, k2if, Q, R; bool lin; };
@@ -176,90 +243,61 @@ __device__ __forceinline__ Hyp make_hyp(const SpecGeom& g, const Grp& r, int sy)
     return h;
 }
 
-// per-thread table for the rows this thread owns: phim, phip for sy = 0, 1 (inversion_utils.f90:505-519)
-// (only phim/phip stay in registers for the whole kernel; exp(-kl zp), exp(-kl zm) are recovered where the
-//  theta functions need them: ep = phim + ef phip, em = phip + ef phim)
-template <int NZ>
-struct HypRows {
-    double phim[3][2], phip[3][2];
-};
-
-template <int NZ>
-__device__ __forceinline__ void hyp_rows(HypRows<NZ>& T, const Hyp (&h)[2], const SpecGeom& g, const Grp& r) {
-    const bool same = (r.k2[0] == r.k2[1]) && !r.g00;
+// phim, phip of the rows this thread owns -> shared planes (inversion_utils.f90:505-519); the caller provides
+// the barrier before other threads read them
+template <int NZ, bool GEN>
+__device__ __forceinline__ void phi_fill(const ZScr<NZ>& sc, const SpecGeom& g, const Grp& r) {
+    constexpr int PST = ZCfg<NZ>::PST;
+    const bool same = GEN && (r.k2[0] == r.k2[1]) && !r.g00;
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) {
-            // never read, but keep every register defined on every path: ptxas 12.9 was seen to emit spill
-            // loads without the matching stores for values that are undefined on some lanes
-            T.phim[it][0] = T.phim[it][1] = T.phip[it][0] = T.phip[it][1] = 0.0;
-            continue;
-        }
-        const double zm = __ldg(&g.zm[z]), zp = __ldg(&g.zp[z]);
+    for (int sy = 0; sy < (GEN ? 2 : 1); ++sy) {
+        const Hyp h = make_hyp(g, r, sy);
 #pragma unroll
-        for (int sy = 0; sy < 2; ++sy) {
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            double pm, pp;
             if (sy == 1 && same) {
-                T.phim[it][1] = T.phim[it][0]; T.phip[it][1] = T.phip[it][0];
-                continue;
-            }
-            if (h[sy].lin) {
-                T.phim[it][sy] = zm / g.Lz;
-                T.phip[it][sy] = zp / g.Lz;
+                pm = sc.phim[z]; pp = sc.phip[z];           // written by this very thread
+            } else if (h.lin) {
+                pm = __ldg(&g.zm[z]) / g.Lz;
+                pp = __ldg(&g.zp[z]) / g.Lz;
             } else {
-                const double ep = exp(-(h[sy].kl * zp));
-                const double em = exp(-(h[sy].kl * zm));
-                T.phim[it][sy] = h[sy].div * (ep - h[sy].ef * em);
-                T.phip[it][sy] = h[sy].div * (em - h[sy].ef * ep);
+                const double ep = exp(-(h.kl * __ldg(&g.zp[z])));
+                const double em = exp(-(h.kl * __ldg(&g.zm[z])));
+                pm = h.div * (ep - h.ef * em);
+                pp = h.div * (em - h.ef * ep);
             }
+            sc.phim[sy * PST + z] = pm;
+            sc.phip[sy * PST + z] = pp;
         }
     }
 }
+template <int NZ, bool GEN>
+__device__ __forceinline__ double phim_of(const ZScr<NZ>& sc, int z, int s) { return sc.phim[sy_of<GEN>(s) * ZCfg<NZ>::PST + z]; }
+template <int NZ, bool GEN>
+__device__ __forceinline__ double phip_of(const ZScr<NZ>& sc, int z, int s) { return sc.phip[sy_of<GEN>(s) * ZCfg<NZ>::PST + z]; }
 
-// thetam, thetap, dthetam, dthetap of one row (inversion_utils.f90:518-541)
-__device__ __forceinline__ void hyp_theta(const Hyp& h, double zm, double zp, double phim,
-                                          double phip, double& thm, double& thp, double& dthm, double& dthp) {
-    if (h.lin) { thm = thp = dthm = dthp = 0.0; return; }
-    const double ep = phim + h.ef * phip, em = phip + h.ef * phim;     // exp(-kl zp), exp(-kl zm)
+// thetam, thetap, dthetam, dthetap of one row (inversion_utils.f90:518-541); exp(-kl zp), exp(-kl zm) are
+// recovered from phim, phip:  ep = phim + ef phip, em = phip + ef phim
+struct Theta { double thm, thp, dthm, dthp; };
+__device__ __forceinline__ Theta hyp_theta(const Hyp& h, double zm, double zp, double phim, double phip) {
+    Theta t;
+    if (h.lin) { t.thm = t.thp = t.dthm = t.dthp = 0.0; return t; }
+    const double ep = phim + h.ef * phip, em = phip + h.ef * phim;
     const double Lm = h.kl * zm;
     const double Lp = h.kl * zp;
     const double dphim = -h.kl * h.div * (ep + h.ef * em);
     const double dphip = h.kl * h.div * (em + h.ef * ep);
-    thm = h.k2if * (h.R * Lm * phip - h.Q * Lp * phim);
-    thp = h.k2if * (h.R * Lp * phim - h.Q * Lm * phip);
-    dthm = -h.k2if * ((h.Q * Lp - 1.0) * dphim - h.R * Lm * dphip);
-    dthp = -h.k2if * ((h.Q * Lm - 1.0) * dphip - h.R * Lp * dphim);
+    t.thm = h.k2if * (h.R * Lm * phip - h.Q * Lp * phim);
+    t.thp = h.k2if * (h.R * Lp * phim - h.Q * Lm * phip);
+    t.dthm = -h.k2if * ((h.Q * Lp - 1.0) * dphim - h.R * Lm * dphip);
+    t.dthp = -h.k2if * ((h.Q * Lm - 1.0) * dphip - h.R * Lp * dphim);
+    return t;
 }
 
 // ---- z transforms on 4-slot shared-memory fields ------------------------------
 enum { XF_DST = 0, XF_DCT = 1 };
-
-// shared scratch of the transforms
-template <int NZ>
-struct ZScr {
-    double* fft;      // [4][2][NZ]
-    double* sintab;   // [NZ/2 + 1]  sin(m pi / NZ)
-    double* wt;       // [64] warp totals of the group scan / sum
-    double* keep;     // [32] block-wide scalars parked between stages (keeps them out of registers)
-};
-template <int NZ>
-__device__ __forceinline__ ZScr<NZ> make_scr(double* base) {
-    ZScr<NZ> s;
-    s.fft = base; s.sintab = base + 8 * NZ; s.wt = s.sintab + ZCfg<NZ>::NSIN; s.keep = s.wt + 64;
-    return s;
-}
-// fill the sine table (once per block; followed by a barrier in the caller)
-template <int NZ>
-__device__ __forceinline__ void scr_init(const ZScr<NZ>& sc, const SpecGeom& g) {
-    const int step = g.ntw / (2 * NZ);                      // tw[m] = exp(2 pi i m / ntw), ntw >= 2 NZ
-    for (int m = threadIdx.x; m <= NZ / 2; m += blockDim.x) sc.sintab[m] = __ldg(&g.tw[m * step]).y;
-}
-template <int NZ>
-__device__ __forceinline__ double sin_j(const ZScr<NZ>& sc, int j) { return sc.sintab[(j <= NZ / 2) ? j : NZ - j]; }
-template <int NZ>
-__device__ __forceinline__ double cos_j(const ZScr<NZ>& sc, int j) {
-    return (j <= NZ / 2) ? sc.sintab[NZ / 2 - j] : -sc.sintab[j - NZ / 2];
-}
 
 // inclusive scan of (a, b) over the TPF consecutive threads of one FFT (u = index inside the FFT)
 template <int TPF>
@@ -296,7 +334,7 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, int u, double* 
     }
 }
 
-// DST-I (rows 1..NZ-1; rows 0 and NZ neither read nor written, stafft.f90:509-513) or DCT-I (rows 0..NZ) of the
+// DST-I (rows 1..NZ-1; rows 0 and NZ keep their values, stafft.f90:509-513) or DCT-I (rows 0..NZ) of the
 // four slots of X0 and, concurrently, of X1 (may be null), scaled sqrt(2/NZ).  Reference algorithm
 // (stafft.f90:410-550) with two columns per complex FFT:
 //   DST: y_j = (x_j - x_{n-j})/2 + sin(j pi/n)(x_j + x_{n-j});  Y = FFT(y);
@@ -304,36 +342,39 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, int u, double* 
 //   DCT: y_0 = (x_0 + x_n)/2, y_j = (x_j + x_{n-j})/2 - sin(j pi/n)(x_j - x_{n-j});
 //        X_1 = x_0/2 - x_n/2 + sum_j x_j cos(j pi/n), X_0 = Y_0, X_{2k} = Re Y_k, X_n = Y_{n/2},
 //        X_{2k+1} = X_{2k-1} - Im Y_k
+// In place: once the pre-processed sequence is in registers, the two column buffers of an FFT serve as the
+// re/im planes of its Stockham exchanges (indices 0..n-1; row n of a column lives at index >= n and is
+// untouched, row 0 of a DST is carried across in a register).
 // The caller must have a barrier between its last write of X0/X1 and this call; ends with a barrier.
 template <int NZ>
-__device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int kind1, const ZScr<NZ>& sc,
-                                       const SpecGeom& g) {
+__device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int kind1, const ZScr<NZ>& sc) {
     constexpr int n = NZ, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
     const int t = threadIdx.x;
     const int fg = t / (2 * TPF), f = (t / TPF) & 1, u = t - (t / TPF) * TPF, fft = 2 * fg + f;
     double* X = fg ? X1 : X0;
     const int kind = fg ? kind1 : kind0;
     const bool act = (X != nullptr);
-    double* xa = (act ? X : X0) + (2 * f) * LC;
+    double* xa = (act ? X : X0) + (2 * f) * LC;     // (inactive threads never dereference these)
     double* xb = xa + LC;
-    double* sre = sc.fft + fft * 2 * n;
-    double* sim = sre + n;
     double* wt = sc.wt + fft * 8;
     const IxSwz ix;
 
     // ---- pre-process: two real sequences -> one complex sequence
     double vr[8], vi[8];
-    double sa = 0.0, sb = 0.0;                 // DCT: X_1 partial sums
+    double sa = 0.0, sb = 0.0;                 // DCT: X_1 partial sums;  DST, u == 0: row 0 carried across
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int j = u + e * TPF;
         double yr = 0.0, yi = 0.0;
         if (act) {
             if (j == 0) {
+                const double a0 = xa[cz(0)], b0 = xb[cz(0)];
                 if (kind == XF_DCT) {
-                    const double a0 = xa[cz(0)], an = xa[cz(n)], b0 = xb[cz(0)], bn = xb[cz(n)];
+                    const double an = xa[cz(n)], bn = xb[cz(n)];
                     yr = 0.5 * (a0 + an); yi = 0.5 * (b0 + bn);
                     sa += 0.5 * (a0 - an); sb += 0.5 * (b0 - bn);
+                } else {
+                    sa = a0; sb = b0;
                 }
             } else {
                 const double aj = xa[cz(j)], an = xa[cz(n - j)], bj = xb[cz(j)], bn = xb[cz(n - j)];
@@ -351,49 +392,66 @@ __device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int ki
         }
         vr[e] = yr; vi[e] = yi;
     }
-    group_sum2<TPF>(sa, sb, u, wt);            // (only meaningful for DCT; executed uniformly)
+    {
+        // DCT: block-wide sums for X_1.  DST: (sa, sb) of thread u == 0 hold row 0 and must survive as they
+        // are, so the sum runs on a copy and is discarded.
+        double ta = (kind == XF_DCT) ? sa : 0.0, tb = (kind == XF_DCT) ? sb : 0.0;
+        group_sum2<TPF>(ta, tb, u, wt);        // executed uniformly (barrier inside when TPF > 32)
+        if (kind == XF_DCT) { sa = ta; sb = tb; }
+    }
+    if (TPF <= 32) __syncthreads();            // every pre-process read is done before the buffers become scratch
 
-    block_cfft<n, false>(vr, vi, u, true, sre, sim, ix, g.tw, g.ntw / n);
+    block_cfft<n, false>(vr, vi, u, act, xa, xb, ix, TwSin<NZ>{sc.sintab});
     __syncthreads();
+    if (act) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int idx = ix(u + e * TPF);
-        sre[idx] = vr[e]; sim[idx] = vi[e];
+        for (int e = 0; e < 8; ++e) {
+            const int idx = ix(u + e * TPF);
+            xa[idx] = vr[e]; xb[idx] = vi[e];
+        }
     }
     __syncthreads();
 
     // ---- post-process: thread u owns k = 4u .. 4u+3, i.e. output rows 8u .. 8u+7
     double oa[4], ob[4], ea[4], eb[4];
+    double nyq_a = 0.0, nyq_b = 0.0;
+    if (act) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int k = 4 * u + c;
-        if (k == 0) {
-            const double p = sre[ix(0)], q = sim[ix(0)];
-            if (kind == XF_DST) { oa[c] = 0.5 * p; ob[c] = 0.5 * q; ea[c] = 0.0; eb[c] = 0.0; }
-            else { oa[c] = sa; ob[c] = sb; ea[c] = p; eb[c] = q; }
-        } else {
-            const int ik = ix(k), im = ix(n - k);
-            const double p = sre[ik], q = sim[ik], r = sre[im], s = sim[im];
-            const double reA = 0.5 * (p + r), imA = 0.5 * (q - s), reB = 0.5 * (q + s), imB = 0.5 * (r - p);
-            if (kind == XF_DST) { oa[c] = reA; ob[c] = reB; ea[c] = -imA; eb[c] = -imB; }
-            else { oa[c] = -imA; ob[c] = -imB; ea[c] = reA; eb[c] = reB; }
+        for (int c = 0; c < 4; ++c) {
+            const int k = 4 * u + c;
+            if (k == 0) {
+                const double p = xa[ix(0)], q = xb[ix(0)];
+                if (kind == XF_DST) { oa[c] = 0.5 * p; ob[c] = 0.5 * q; ea[c] = sa; eb[c] = sb; }
+                else { oa[c] = sa; ob[c] = sb; ea[c] = p; eb[c] = q; }
+            } else {
+                const int ik = ix(k), im = ix(n - k);
+                const double p = xa[ik], q = xb[ik], r = xa[im], s = xb[im];
+                const double reA = 0.5 * (p + r), imA = 0.5 * (q - s), reB = 0.5 * (q + s), imB = 0.5 * (r - p);
+                if (kind == XF_DST) { oa[c] = reA; ob[c] = reB; ea[c] = -imA; eb[c] = -imB; }
+                else { oa[c] = -imA; ob[c] = -imB; ea[c] = reA; eb[c] = reB; }
+            }
         }
+        if (u == 0 && kind == XF_DCT) { nyq_a = xa[ix(n / 2)]; nyq_b = xb[ix(n / 2)]; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { oa[c] = ob[c] = ea[c] = eb[c] = 0.0; }
     }
 #pragma unroll
     for (int c = 1; c < 4; ++c) { oa[c] += oa[c - 1]; ob[c] += ob[c - 1]; }
     double ta = oa[3], tb = ob[3];
     group_scan2<TPF>(ta, tb, u, wt + 4);
+    if (TPF <= 32) __syncthreads();            // every read of the spectrum is done before the rows are written
     const double pa = ta - oa[3], pb = tb - ob[3];      // exclusive prefix of this thread
     const double scl = sqrt(2.0 / (double)n);
-    double nyq_a = 0.0, nyq_b = 0.0;
-    if (u == 0 && kind == XF_DCT) { nyq_a = sre[ix(n / 2)]; nyq_b = sim[ix(n / 2)]; }
     if (act) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int k = 4 * u + c;
             xa[cz(2 * k + 1)] = scl * (oa[c] + pa);
             xb[cz(2 * k + 1)] = scl * (ob[c] + pb);
-            if (k > 0 || kind == XF_DCT) { xa[cz(2 * k)] = scl * ea[c]; xb[cz(2 * k)] = scl * eb[c]; }
+            // row 0 of a DST: the value it had on entry (unscaled)
+            const double se = (k == 0 && kind == XF_DST) ? 1.0 : scl;
+            xa[cz(2 * k)] = se * ea[c]; xb[cz(2 * k)] = se * eb[c];
         }
         if (u == 0 && kind == XF_DCT) { xa[cz(n)] = scl * nyq_a; xb[cz(n)] = scl * nyq_b; }
     }
@@ -403,28 +461,25 @@ __device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int ki
 // ---------------------------------------------------------------------------
 // Operator-mode kernel: one z-operation on one field (drop-in for the public
 // module procedures fftsine, fftcosine, diffx, diffy, central_diffz,
-// field_combine_semi_spectral, field_decompose_semi_spectral).
+// field_combine_semi_spectral, field_decompose_semi_spectral).  General
+// instantiation for every group (this is the host-boundary path, not the hot loop).
 // ---------------------------------------------------------------------------
 enum { ZOP_SINE = 0, ZOP_COSINE, ZOP_COMBINE, ZOP_DECOMPOSE, ZOP_DIFFZ, ZOP_DIFFX, ZOP_DIFFY, ZOP_POISSON };
 
 template <int NZ>
-constexpr size_t zop_smem_bytes() { return (size_t)(ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
+constexpr size_t zop_smem_bytes() { return (size_t)(ZCfg<NZ>::BUF + ZCfg<NZ>::aux(true)) * sizeof(double); }
 
 template <int NZ>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const double* __restrict__ in,
                                                        double* __restrict__ out) {
     PS_SMEM(double, sm);
     constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
+    constexpr bool GEN = true;
     double* X = sm;
-    const ZScr<NZ> scr = make_scr<NZ>(X + BUF);
+    const ZScr<NZ> scr = make_scr<NZ, GEN>(X + BUF);
     scr_init<NZ>(scr, g);
-    const Grp r = make_grp(g, blockIdx.x);
-    Hyp h[2];
-    HypRows<NZ> T;
-    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE) {
-        h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
-        hyp_rows<NZ>(T, h, g, r);
-    }
+    const Grp r = make_grp<GEN>(g, blockIdx.x);
+    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE) phi_fill<NZ, GEN>(scr, g, r);
     if (op == ZOP_DIFFX || op == ZOP_DIFFY) {
 #pragma unroll
         for (int it = 0; it < 3; ++it) {
@@ -443,9 +498,10 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         Row4 x = row_load_g<NZ>(in, r, z);
         if (op == ZOP_DECOMPOSE && z >= 1 && z < NZ) {
             // subtract the harmonic part (inversion_utils.f90:571); boundary rows straight from memory
+            // (phim/phip of this thread's own rows: written by itself above)
             const Row4 x0 = row_load_g<NZ>(in, r, 0), xn = row_load_g<NZ>(in, r, NZ);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) x.v[s] -= x0.v[s] * T.phim[it][s & 1] + xn.v[s] * T.phip[it][s & 1];
+            for (int s = 0; s < 4; ++s) x.v[s] -= x0.v[s] * phim_of<NZ, GEN>(scr, z, s) + xn.v[s] * phip_of<NZ, GEN>(scr, z, s);
         }
         row_store_s<NZ>(X, z, x);
     }
@@ -465,7 +521,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         }
         return;
     }
-    xform2<NZ>(X, (op == ZOP_COSINE || op == ZOP_POISSON) ? XF_DCT : XF_DST, nullptr, XF_DST, scr, g);
+    xform2<NZ>(X, (op == ZOP_COSINE || op == ZOP_POISSON) ? XF_DCT : XF_DST, nullptr, XF_DST, scr);
     if (op == ZOP_POISSON) {
         // pressure Poisson solve between two cosine transforms (fields_derived.f90:125-148):
         // rs <- green * rs with green(kz) = -1/(k^2+l^2+rkz^2), green(0) = -1/(k^2+l^2) (inversion_utils.f90:283-288)
@@ -480,7 +536,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
             row_store_s<NZ>(X, z, x);
         }
         __syncthreads();
-        xform2<NZ>(X, XF_DCT, nullptr, XF_DST, scr, g);
+        xform2<NZ>(X, XF_DCT, nullptr, XF_DST, scr);
     }
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
@@ -490,7 +546,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         if (op == ZOP_SINE && z == NZ) { x.v[0] = x.v[1] = x.v[2] = x.v[3] = 0.0; }     // stafft.f90:546-549
         if (op == ZOP_COMBINE && z >= 1 && z < NZ) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) x.v[s] += X[s * LC + cz(0)] * T.phim[it][s & 1] + X[s * LC + cz(NZ)] * T.phip[it][s & 1];
+            for (int s = 0; s < 4; ++s)
+                x.v[s] += X[s * LC + cz(0)] * phim_of<NZ, GEN>(scr, z, s) + X[s * LC + cz(NZ)] * phip_of<NZ, GEN>(scr, z, s);
         }
         row_store_g<NZ>(out, r, z, x);
     }
@@ -502,7 +559,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
 // the inverse x/y passes that give `vor`), svel.
 // ---------------------------------------------------------------------------
 template <int NZ>
-constexpr size_t v2v_smem_bytes() { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
+constexpr size_t v2v_smem_bytes(bool gen) { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::aux(gen)) * sizeof(double); }
 
 struct V2VArgs {
     double* svor0; double* svor1; double* svor2;         // in/out
@@ -516,6 +573,7 @@ struct V2VArgs {
 // with adding/removing the harmonic part: the kernel applies it once to the mixed-spectral rows (-> new svor)
 // and once to the semi-spectral rows (-> input of the inverse x/y passes) instead of transforming the
 // projected fields again.
+template <bool GEN>
 __device__ __forceinline__ void project_row(Row4& fa, Row4& fb, const Row4& fe, const Grp& r) {
     const Row4 bx = ddx(fb, r), ay = ddy(fa, r);
     Row4 d;
@@ -524,27 +582,24 @@ __device__ __forceinline__ void project_row(Row4& fa, Row4& fb, const Row4& fe, 
     const Row4 ex = ddx(fe, r), ey = ddy(fe, r), dx_ = ddx(d, r), dy_ = ddy(d, r);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        if (r.g00 && s == 0) continue;
-        fa.v[s] = r.k2i[s & 1] * (ex.v[s] + dy_.v[s]);
-        fb.v[s] = r.k2i[s & 1] * (ey.v[s] - dx_.v[s]);
+        if (GEN && r.g00 && s == 0) continue;
+        fa.v[s] = r.k2i[sy_of<GEN>(s)] * (ex.v[s] + dy_.v[s]);
+        fb.v[s] = r.k2i[sy_of<GEN>(s)] * (ey.v[s] - dx_.v[s]);
     }
 }
 
-template <int NZ>
-__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
+template <int NZ, bool GEN>
+__global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
     PS_SMEM(double, sm);
     constexpr int LC = ZCfg<NZ>::LC, BUF = ZCfg<NZ>::BUF;
     double* A = sm;
     double* B = A + BUF;
     double* C = B + BUF;
     double* E = C + BUF;
-    const ZScr<NZ> scr = make_scr<NZ>(E + BUF);
+    const ZScr<NZ> scr = make_scr<NZ, GEN>(E + BUF);
     scr_init<NZ>(scr, g);
-    const Grp r = make_grp(g, blockIdx.x);
-    Hyp h[2];
-    h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
-    HypRows<NZ> T;
-    hyp_rows<NZ>(T, h, g, r);
+    const Grp r = make_grp<GEN>(g, blockIdx.x);
+    phi_fill<NZ, GEN>(scr, g, r);
 
     // stage svor
 #pragma unroll
@@ -560,7 +615,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
     // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; this is also the
     // semi-spectral zeta that feeds the inverse x/y passes (:81).  A (xi) rides along: its sine sum is the
     // interior of combine(xi_old), used by the semi-spectral projection below.
-    xform2<NZ>(C, XF_DST, A, XF_DST, scr, g);
+    xform2<NZ>(C, XF_DST, A, XF_DST, scr);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -568,7 +623,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         Row4 c = row_load_s<NZ>(C, z);
         if (z >= 1 && z < NZ) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) c.v[s] += C[s * LC + cz(0)] * T.phim[it][s & 1] + C[s * LC + cz(NZ)] * T.phip[it][s & 1];
+            for (int s = 0; s < 4; ++s)
+                c.v[s] += C[s * LC + cz(0)] * phim_of<NZ, GEN>(scr, z, s) + C[s * LC + cz(NZ)] * phip_of<NZ, GEN>(scr, z, s);
             row_store_s<NZ>(C, z, c);
         }
         row_store_g<NZ>(a.wsem2, r, z, c);
@@ -593,13 +649,14 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
                 const double* c = C + s * LC;
                 if (z == 0) e.v[s] = e0[s];
                 else if (z == NZ) e.v[s] = en[s];
-                else e.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi - (e0[s] * T.phim[it][s & 1] + en[s] * T.phip[it][s & 1]);
+                else e.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi
+                              - (e0[s] * phim_of<NZ, GEN>(scr, z, s) + en[s] * phip_of<NZ, GEN>(scr, z, s));
             }
             row_store_s<NZ>(E, z, e);
         }
     }
     __syncthreads();
-    xform2<NZ>(E, XF_DST, B, XF_DST, scr, g);
+    xform2<NZ>(E, XF_DST, B, XF_DST, scr);
 
     // Solenoidal projection (:39-76), twice (see project_row):
     //  * semi-spectral rows (combine(xi_old), combine(eta_old), dzeta/dz) -> wsem0, wsem1, the vorticity that the
@@ -617,17 +674,18 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const double* c = C + s * LC;
-                sa.v[s] += A[s * LC + cz(0)] * T.phim[it][s & 1] + A[s * LC + cz(NZ)] * T.phip[it][s & 1];
-                sb.v[s] += B[s * LC + cz(0)] * T.phim[it][s & 1] + B[s * LC + cz(NZ)] * T.phip[it][s & 1];
+                const double pm = phim_of<NZ, GEN>(scr, z, s), pp = phip_of<NZ, GEN>(scr, z, s);
+                sa.v[s] += A[s * LC + cz(0)] * pm + A[s * LC + cz(NZ)] * pp;
+                sb.v[s] += B[s * LC + cz(0)] * pm + B[s * LC + cz(NZ)] * pp;
                 se.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi;
             }
         } else {
             se = fe;            // rows 0, NZ of E still hold the one-sided differences
         }
-        project_row(sa, sb, se, r);
+        project_row<GEN>(sa, sb, se, r);
         row_store_g<NZ>(a.wsem0, r, z, sa);
         row_store_g<NZ>(a.wsem1, r, z, sb);
-        project_row(fa, fb, fe, r);
+        project_row<GEN>(fa, fb, fe, r);
         row_store_g<NZ>(a.svor0, r, z, fa);
         row_store_g<NZ>(a.svor1, r, z, fb);
         const Row4 ay2 = ddy(fa, r), bx2 = ddx(fb, r);
@@ -655,7 +713,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
             const double rk = __ldg(&g.rkz[z]);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const double green = -1.0 / (r.k2[s & 1] + rk * rk);
+                const double green = -1.0 / (r.k2[sy_of<GEN>(s)] + rk * rk);
                 ds.v[s] = green * ds.v[s];
                 as.v[s] = rk * ds.v[s];
             }
@@ -666,7 +724,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         row_store_s<NZ>(A, z, as);
     }
     // horizontally averaged flow from the (0,0) column (:150-165): cosine transform in B slots 0, 1
-    if (r.g00) {
+    if (GEN && r.g00) {
 #pragma unroll
         for (int it = 0; it < 3; ++it) {
             const int z = my_row<NZ>(it);
@@ -683,16 +741,16 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         }
     }
     __syncthreads();
-    xform2<NZ>(A, XF_DCT, E, XF_DST, scr, g);     // (:128-129)
-    if (r.g00) xform2<NZ>(B, XF_DCT, nullptr, XF_DST, scr, g);
+    xform2<NZ>(A, XF_DCT, E, XF_DST, scr);     // (:128-129)
+    if (GEN && r.g00) xform2<NZ>(B, XF_DCT, nullptr, XF_DST, scr);
 
     // w = E + boundary part, dw/dz = es + as (:96-104, :136-139);
     // u = k2l2i (es_x + cs_y), v = k2l2i (es_y - cs_x), (0,0) <- ubar, vbar (:169-213)
-    double d0[4], dn[4];
+    Hyp h[GEN ? 2 : 1];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) { d0[s] = scr.keep[s]; dn[s] = scr.keep[4 + s]; }
+    for (int sy = 0; sy < (GEN ? 2 : 1); ++sy) h[sy] = make_hyp(g, r, sy);
     double a00 = 0.0, a0n = 0.0, b00 = 0.0, b0n = 0.0;
-    if (r.g00) {
+    if (GEN && r.g00) {
         a00 = a.svor0[r.off[0]]; a0n = a.svor0[r.off[0] + NZ];
         b00 = a.svor1[r.off[0]]; b0n = a.svor1[r.off[0] + NZ];
     }
@@ -702,23 +760,26 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
         if (z < 0) continue;
         const Row4 as = row_load_s<NZ>(A, z), ds = row_load_s<NZ>(E, z), cs = row_load_s<NZ>(C, z);
         const double zm = __ldg(&g.zm[z]), zp = __ldg(&g.zp[z]);
+        Theta th[GEN ? 2 : 1];
+#pragma unroll
+        for (int sy = 0; sy < (GEN ? 2 : 1); ++sy)
+            th[sy] = hyp_theta(h[sy], zm, zp, phim_of<NZ, GEN>(scr, z, sy), phip_of<NZ, GEN>(scr, z, sy));
         Row4 es, w;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const int sy = s & 1;
-            double thm, thp, dthm, dthp;
-            hyp_theta(h[sy], zm, zp, T.phim[it][sy], T.phip[it][sy], thm, thp, dthm, dthp);
-            es.v[s] = d0[s] * dthm + dn[s] * dthp + as.v[s];
-            w.v[s] = (z == 0 || z == NZ) ? 0.0 : ds.v[s] + d0[s] * thm + dn[s] * thp;
+            const Theta& q = th[sy_of<GEN>(s)];
+            const double d0 = scr.keep[s], dn = scr.keep[4 + s];
+            es.v[s] = d0 * q.dthm + dn * q.dthp + as.v[s];
+            w.v[s] = (z == 0 || z == NZ) ? 0.0 : ds.v[s] + d0 * q.thm + dn * q.thp;
         }
         const Row4 ex = ddx(es, r), ey = ddy(es, r), cx = ddx(cs, r), cy = ddy(cs, r);
         Row4 u, v;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            u.v[s] = r.k2i[s & 1] * (ex.v[s] + cy.v[s]);
-            v.v[s] = r.k2i[s & 1] * (ey.v[s] - cx.v[s]);
+            u.v[s] = r.k2i[sy_of<GEN>(s)] * (ex.v[s] + cy.v[s]);
+            v.v[s] = r.k2i[sy_of<GEN>(s)] * (ey.v[s] - cx.v[s]);
         }
-        if (r.g00) {
+        if (GEN && r.g00) {
             const double gt = __ldg(&g.gamtop[z]), gb = __ldg(&g.gambot[z]);
             u.v[0] = B[cz(z)] + b0n * gt - b00 * gb;               // ubar (:163)
             v.v[0] = B[LC + cz(z)] - a0n * gt + a00 * gb;          // vbar (:164)
@@ -741,89 +802,127 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_vor2vel_s
 //   svorts = decompose( r_y - q_z,  p_z - r_x,  q_x - p_y )      (three sine transforms).
 // ---------------------------------------------------------------------------
 template <int NZ>
-constexpr size_t src_smem_bytes() { return (size_t)(3 * ZCfg<NZ>::BUF + ZCfg<NZ>::SCR) * sizeof(double); }
+constexpr size_t src_smem_bytes(bool gen) { return (size_t)(4 * ZCfg<NZ>::BUF + ZCfg<NZ>::aux(gen)) * sizeof(double); }
 
 struct SrcArgs {
     const double* r; const double* q; const double* p;   // semi-spectral fluxes
     double* s0; double* s1; double* s2;                  // svorts (mixed spectral)
 };
 
-// semi-spectral curl of one row from the rows z-1, z, z+1 of q, p and row z of r; dz = 1/(2 dz) in the
-// interior, 1/dz with (lo, hi) = (z, z+1) or (z-1, z) at the boundaries (inversion_utils.f90:653-680)
-__device__ __forceinline__ void curl_row(const Row4& fr, const Row4& fq, const Row4& fp, const Row4& qlo,
-                                         const Row4& qhi, const Row4& plo, const Row4& phi, double dz,
-                                         const Grp& r, Row4& s0, Row4& s1, Row4& s2) {
-    const Row4 ry = ddy(fr, r), rx = ddx(fr, r), qx = ddx(fq, r), py = ddy(fp, r);
+// semi-spectral curl of one row, first two components, from row z of r and the rows z-1/z+1 (lo/hi) of q, p;
+// dz = 1/(2 dz) in the interior, 1/dz with (lo, hi) = (z, z+1) or (z-1, z) at the boundaries
+// (inversion_utils.f90:653-680)
+__device__ __forceinline__ void curl01_row(const Row4& fr, const Row4& qlo, const Row4& qhi, const Row4& plo,
+                                           const Row4& phi, double dz, const Grp& r, Row4& s0, Row4& s1) {
+    const Row4 ry = ddy(fr, r), rx = ddx(fr, r);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         s0.v[s] = ry.v[s] - (qhi.v[s] - qlo.v[s]) * dz;      // dr/dy - dq/dz (:341-347)
         s1.v[s] = (phi.v[s] - plo.v[s]) * dz - rx.v[s];      // dp/dz - dr/dx (:353-359)
-        s2.v[s] = qx.v[s] - py.v[s];                         // dq/dx - dp/dy (:363-367)
     }
 }
+// third component from row z of q, p
+__device__ __forceinline__ Row4 curl2_row(const Row4& fq, const Row4& fp, const Grp& r) {
+    const Row4 qx = ddx(fq, r), py = ddy(fp, r);
+    Row4 s2;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) s2.v[s] = qx.v[s] - py.v[s]; // dq/dx - dp/dy (:363-367)
+    return s2;
+}
 
-template <int NZ>
-__global__ void __launch_bounds__(ZCfg<NZ>::NT, (NZ == 512) ? 2 : 1) k_source_spec(SpecGeom g, SrcArgs a) {
+template <int NZ, bool GEN>
+__global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_source_spec(SpecGeom g, SrcArgs a) {
     PS_SMEM(double, sm);
     constexpr int BUF = ZCfg<NZ>::BUF;
-    double* S0 = sm;
-    double* S1 = S0 + BUF;
-    double* S2 = S1 + BUF;
-    const ZScr<NZ> scr = make_scr<NZ>(S2 + BUF);
+    double* R = sm;           // r, then curl component 0
+    double* Q = R + BUF;      // q, then curl component 2
+    double* P = Q + BUF;      // p
+    double* T = P + BUF;      // curl component 1
+    const ZScr<NZ> scr = make_scr<NZ, GEN>(T + BUF);
     scr_init<NZ>(scr, g);
-    const Grp r = make_grp(g, blockIdx.x);
-    Hyp h[2];
-    h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
-    HypRows<NZ> T;
-    hyp_rows<NZ>(T, h, g, r);
+    const Grp r = make_grp<GEN>(g, blockIdx.x);
+    phi_fill<NZ, GEN>(scr, g, r);
 
-    // boundary rows of the curl (every thread: they define the harmonic part that is removed from its rows)
-    Row4 b0[3], bn[3];
-    {
-        const Row4 r0 = row_load_g<NZ>(a.r, r, 0), q0 = row_load_g<NZ>(a.q, r, 0), p0 = row_load_g<NZ>(a.p, r, 0);
-        const Row4 q1 = row_load_g<NZ>(a.q, r, 1), p1 = row_load_g<NZ>(a.p, r, 1);
-        curl_row(r0, q0, p0, q0, q1, p0, p1, g.dzi, r, b0[0], b0[1], b0[2]);
-        const Row4 rn = row_load_g<NZ>(a.r, r, NZ), qn = row_load_g<NZ>(a.q, r, NZ), pn = row_load_g<NZ>(a.p, r, NZ);
-        const Row4 qm = row_load_g<NZ>(a.q, r, NZ - 1), pm = row_load_g<NZ>(a.p, r, NZ - 1);
-        curl_row(rn, qn, pn, qm, qn, pm, pn, g.dzi, r, bn[0], bn[1], bn[2]);
-    }
+    // stage the fluxes (each element is read from memory exactly once)
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        Row4 s[3];
-        if (z == 0) { s[0] = b0[0]; s[1] = b0[1]; s[2] = b0[2]; }
-        else if (z == NZ) { s[0] = bn[0]; s[1] = bn[1]; s[2] = bn[2]; }
-        else {
-            const Row4 fr = row_load_g<NZ>(a.r, r, z), fq = row_load_g<NZ>(a.q, r, z), fp = row_load_g<NZ>(a.p, r, z);
-            const Row4 qlo = row_load_g<NZ>(a.q, r, z - 1), qhi = row_load_g<NZ>(a.q, r, z + 1);
-            const Row4 plo = row_load_g<NZ>(a.p, r, z - 1), phi = row_load_g<NZ>(a.p, r, z + 1);
-            curl_row(fr, fq, fp, qlo, qhi, plo, phi, g.hdzi, r, s[0], s[1], s[2]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    s[c].v[k] -= b0[c].v[k] * T.phim[it][k & 1] + bn[c].v[k] * T.phip[it][k & 1];
-        }
-        row_store_s<NZ>(S0, z, s[0]);
-        row_store_s<NZ>(S1, z, s[1]);
-        row_store_s<NZ>(S2, z, s[2]);
+        row_store_s<NZ>(R, z, row_load_g<NZ>(a.r, r, z));
+        row_store_s<NZ>(Q, z, row_load_g<NZ>(a.q, r, z));
+        row_store_s<NZ>(P, z, row_load_g<NZ>(a.p, r, z));
     }
     __syncthreads();
-    xform2<NZ>(S0, XF_DST, S1, XF_DST, scr, g);
+    // boundary rows of the curl (they define the harmonic part removed from every interior row): one thread
+    // each, parked in shared memory as keep[(c*2 + top)*4 + slot]
+    if (threadIdx.x == 0 || threadIdx.x == ZCfg<NZ>::NT - 1) {
+        const bool top = (threadIdx.x != 0);
+        const int z = top ? NZ : 0, zl = top ? NZ - 1 : 0, zh = top ? NZ : 1;
+        Row4 c0, c1;
+        curl01_row(row_load_s<NZ>(R, z), row_load_s<NZ>(Q, zl), row_load_s<NZ>(Q, zh), row_load_s<NZ>(P, zl),
+                   row_load_s<NZ>(P, zh), g.dzi, r, c0, c1);
+        const Row4 c2 = curl2_row(row_load_s<NZ>(Q, z), row_load_s<NZ>(P, z), r);
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        row_store_g<NZ>(a.s0, r, z, row_load_s<NZ>(S0, z));
-        row_store_g<NZ>(a.s1, r, z, row_load_s<NZ>(S1, z));
+        for (int s = 0; s < 4; ++s) {
+            scr.keep[(0 + top) * 4 + s] = c0.v[s];
+            scr.keep[(2 + top) * 4 + s] = c1.v[s];
+            scr.keep[(4 + top) * 4 + s] = c2.v[s];
+        }
     }
-    xform2<NZ>(S2, XF_DST, nullptr, XF_DST, scr, g);
+    __syncthreads();
+    // components 0, 1 (need the neighbour rows of q, p): R <- s0 in place (row z of r is only read by its
+    // owner), T <- s1
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        row_store_g<NZ>(a.s2, r, z, row_load_s<NZ>(S2, z));
+        Row4 s0, s1;
+        if (z == 0 || z == NZ) {
+            const int top = (z == NZ);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { s0.v[s] = scr.keep[(0 + top) * 4 + s]; s1.v[s] = scr.keep[(2 + top) * 4 + s]; }
+        } else {
+            curl01_row(row_load_s<NZ>(R, z), row_load_s<NZ>(Q, z - 1), row_load_s<NZ>(Q, z + 1),
+                       row_load_s<NZ>(P, z - 1), row_load_s<NZ>(P, z + 1), g.hdzi, r, s0, s1);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double pm = phim_of<NZ, GEN>(scr, z, s), pp = phip_of<NZ, GEN>(scr, z, s);
+                s0.v[s] -= scr.keep[0 + s] * pm + scr.keep[4 + s] * pp;
+                s1.v[s] -= scr.keep[8 + s] * pm + scr.keep[12 + s] * pp;
+            }
+        }
+        row_store_s<NZ>(R, z, s0);
+        row_store_s<NZ>(T, z, s1);
+    }
+    __syncthreads();          // every neighbour row of q, p has been read
+    // component 2 (own rows only): Q <- s2 in place
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        Row4 s2 = curl2_row(row_load_s<NZ>(Q, z), row_load_s<NZ>(P, z), r);
+        if (z >= 1 && z < NZ) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                s2.v[s] -= scr.keep[16 + s] * phim_of<NZ, GEN>(scr, z, s) + scr.keep[20 + s] * phip_of<NZ, GEN>(scr, z, s);
+        }
+        row_store_s<NZ>(Q, z, s2);
+    }
+    __syncthreads();
+    xform2<NZ>(R, XF_DST, T, XF_DST, scr);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        row_store_g<NZ>(a.s0, r, z, row_load_s<NZ>(R, z));
+        row_store_g<NZ>(a.s1, r, z, row_load_s<NZ>(T, z));
+    }
+    xform2<NZ>(Q, XF_DST, nullptr, XF_DST, scr);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        row_store_g<NZ>(a.s2, r, z, row_load_s<NZ>(Q, z));
     }
 }
 

@@ -135,6 +135,26 @@ def test_vor2vel_source_white_noise_64(lib, filtering):
         lib.finalise()
 
 
+@pytest.mark.parametrize("shape", [(16, 16, 512), (8, 16, 256), (16, 8, 128), (8, 8, 1024), (32, 32, 16)])
+def test_vor2vel_source_white_noise_tall(lib, shape):
+    """Column kernels at every nz template the configs use (512: three blocks per SM, in-place transforms; 1024),
+    both instantiations (pairs (a, ny-a) and the (0, ny/2) pair), anisotropic boxes, against the oracle."""
+    nx, ny, nz = shape
+    s = open_grid(lib, nx, ny, nz, [-0.5 * PI, 0.0, -1.0], [PI, 2 * PI, 2.0])
+    try:
+        vor = np.random.default_rng(11).uniform(-1, 1, (3, nx, ny, nz + 1))
+        s.set_vorticity(vor)
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        for name in ("svor", "vor", "svel", "vel"):
+            assert rel(lib.download3(name), getattr(s, name)) < FIELD_TOL, name
+        lib.source()
+        s.source()
+        assert rel(lib.download3("svorts"), s.svorts) < FIELD_TOL
+    finally:
+        lib.finalise()
+
+
 @pytest.mark.parametrize("stepper,n,nsteps", [("cn2", 32, 100), ("impl-diff-rk4", 32, 100), ("cn2", 64, 10)])
 def test_beltrami_trajectory(lib, stepper, n, nsteps):
     """fields every step to 1e-12, dt sequence, and

@@ -6,6 +6,13 @@ o=gpurun_out
 mkdir -p $o
 timeout 600 python -m pytest tests -m gpu -x -q > $o/${tag}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $o/${tag}_pytest.log
 tail -3 $o/${tag}_pytest.log
+if [ -n "$RACE" ]; then
+  timeout 400 compute-sanitizer --tool racecheck --print-limit 20 python tools/race_small.py 8x8x512 8x8x64 16x16x16 > $o/${tag}_racecheck.log 2>&1; echo "racecheck exit $?"
+  tail -4 $o/${tag}_racecheck.log
+fi
+for v in $VARIANTS; do
+  echo "== variant $v"; PS3D_PROBE_LIB=$v timeout 200 python tools/gpu_probe.py 512 2>&1 | tee -a $o/${tag}_variants.log
+done
 timeout 300 python bench.py --steps 10 --warmup 3 > $o/${tag}_bench.json 2> $o/${tag}_bench.err; echo "bench exit $?"
 cat $o/${tag}_bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $o/${tag}_launches.csv \
