@@ -221,7 +221,7 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command (per launch),
     # only quoted for the configuration it was captured on
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01g_ncu_kernels.json")
+    tpath = os.path.join(ROOT, "profiles", "r01j_ncu_kernels.json")
     if os.path.exists(tpath) and n == 512 and world == 1:
         t = json.load(open(tpath)).get(dom if dom in ("vor2vel_columns", "source_columns") else "line_fwd_y")
         if t:
