@@ -106,6 +106,23 @@ int ps3d_cuda_upload(int field_id, int comp, const double* host);
  * horizontal / vertical enstrophy, max horizontal enstrophy (field_diagnostics.f90:128,153,211,248,233) */
 int ps3d_cuda_diagnostics(double out[8]);
 
+/* The 40 scalars of the field-statistics file, update_netcdf_field_diagnostics
+ * (field_diagnostics_netcdf.f90:257-439) together with the values `adapt` hands over through
+ * set_netcdf_field_diagnostic (advance.f90:188-193, 315-321, 366): out[NC_x - 1] with the reference's indices
+ * (field_diagnostics_netcdf.f90:36-75), see the PS3D_NC_* enumerators.  Assumes, like the reference, that the
+ * fields are up to date (vor2vel done) and that adapt has run for the current state; evaluates the horizontal
+ * divergence (fields_derived.f90:161-182) for NC_USDELRMS.  Buoyancy-only entries (BFMAX, RBFMAX, RIMIN) are 0;
+ * ROMIN / ROMAX are min / max zeta divided by f_cor(3) exactly as field_diagnostics.f90:293-320 (f_cor = 0 in the
+ * configurations in scope: +-inf or nan, as in the reference). */
+enum { PS3D_NC_KE = 0, PS3D_NC_EN, PS3D_NC_OMAX, PS3D_NC_ORMS, PS3D_NC_OCHAR, PS3D_NC_OXMEAN, PS3D_NC_OYMEAN,
+       PS3D_NC_OZMEAN, PS3D_NC_KEXY, PS3D_NC_KEZ, PS3D_NC_ENXY, PS3D_NC_ENZ, PS3D_NC_OXMIN, PS3D_NC_OYMIN,
+       PS3D_NC_OZMIN, PS3D_NC_OXMAX, PS3D_NC_OYMAX, PS3D_NC_OZMAX, PS3D_NC_HEMAX, PS3D_NC_GMAX, PS3D_NC_BFMAX,
+       PS3D_NC_UMAX, PS3D_NC_VMAX, PS3D_NC_WMAX, PS3D_NC_USOXMAX, PS3D_NC_LSOXMAX, PS3D_NC_USOYMAX,
+       PS3D_NC_LSOYMAX, PS3D_NC_USOZMAX, PS3D_NC_LSOZMAX, PS3D_NC_USUHMAX, PS3D_NC_USGMAX, PS3D_NC_LSGMAX,
+       PS3D_NC_USZRMS, PS3D_NC_USDELRMS, PS3D_NC_RGMAX, PS3D_NC_RBFMAX, PS3D_NC_RIMIN, PS3D_NC_ROMIN,
+       PS3D_NC_ROMAX, PS3D_NC_COUNT };
+int ps3d_cuda_field_stats(double out[40]);
+
 /* ---- multi-rank transport ----
  * Slab decomposition over `nranks` GPUs of one box: physical fields are split in x (rank r owns planes
  * r*nx/P .. (r+1)*nx/P - 1), spectral fields in ky (rank r owns rows r*ny/P .. of the paired order

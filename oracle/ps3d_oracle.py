@@ -570,6 +570,39 @@ class PS3D:
             self.svor[nc, 0, 0, 0] += self.ini_vor_mean[nc] - savg[nc]
             self.svor[nc, 0, 0, nz] += self.ini_vor_mean[nc] - savg[nc]
 
+    def field_stats(self):
+        """update_netcdf_field_diagnostics (field_diagnostics_netcdf.f90:257-439) plus the values adapt hands
+        over with set_netcdf_field_diagnostic (advance.f90:188-193, 315-321, 366).  Needs vor2vel and adapt for
+        the current state.  Keys: the reference's netCDF variable names, lower case."""
+        nz = self.nz
+        vor, vel = self.vor, self.vel
+        d = self.diag
+        ke = self.get_kinetic_energy()
+        en = self.get_enstrophy()
+        kexy = 0.5 * self._trap(vel[0] ** 2 + vel[1] ** 2) * self.ncelli          # field_diagnostics.f90:128-149
+        enxy = 0.5 * self._trap(vor[0] ** 2 + vor[1] ** 2) * self.ncelli          # :211-229
+        delta = self.horizontal_divergence()
+        nxy = float(self.nx * self.ny)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            romin = np.float64(vor[2].min()) / np.float64(self.f_cor[2])          # :293-304
+            romax = np.float64(vor[2].max()) / np.float64(self.f_cor[2])          # :309-320
+        return dict(
+            ke=ke, en=en, omax=d["vortmax"], orms=d["vortrms"], ochar=d["vorch"],
+            oxmean=d["vormean"][0], oymean=d["vormean"][1], ozmean=d["vormean"][2],
+            kexy=kexy, kez=ke - kexy, enxy=enxy, enz=en - enxy,                   # :153-168, :248-263
+            oxmin=vor[0].min(), oymin=vor[1].min(), ozmin=vor[2].min(),
+            oxmax=vor[0].max(), oymax=vor[1].max(), ozmax=vor[2].max(),
+            hemax=math.sqrt(np.max(vor[0] ** 2 + vor[1] ** 2)),                   # :233-244
+            gmax=d["ggmax"], bfmax=d["bfmax"], umax=d["umax"], vmax=d["vmax"], wmax=d["wmax"],
+            usoxmax=vor[0][..., nz].max(), lsoxmax=vor[0][..., 0].max(),
+            usoymax=vor[1][..., nz].max(), lsoymax=vor[1][..., 0].max(),
+            usozmax=vor[2][..., nz].max(), lsozmax=vor[2][..., 0].max(),
+            usuhmax=math.sqrt(np.max(vel[0][..., nz] ** 2 + vel[1][..., nz] ** 2)),
+            usgmax=d["usggmax"], lsgmax=d["lsggmax"],
+            uszrms=math.sqrt(np.sum(vor[2][..., nz] ** 2) / nxy),
+            usdelrms=math.sqrt(np.sum(delta[..., nz] ** 2) / nxy),
+            rgmax=d["rmv"], rbfmax=0.0, rimin=0.0, romin=float(romin), romax=float(romax))
+
     # ---- fields_derived.f90:67-182 ----
     def pressure(self, dudx, dudy, dvdy, dwdx, dwdy):
         vor = self.vor

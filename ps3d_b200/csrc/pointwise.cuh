@@ -217,6 +217,44 @@ __global__ void k_field_reduce(FieldPtrs f, long long ncol, int nz, int pz, doub
     }
 }
 
+// ---- the remaining scalars of the field-statistics file (field_diagnostics_netcdf.f90:257-439) ------------
+// minima / maxima of the vorticity components (:356-358, :392-394), their maxima on the upper and lower
+// surface (:398-403), max horizontal speed^2 on the upper surface (:404-405), and the sums behind the rms of the
+// upper-surface zeta and horizontal divergence (:301, :305).  Minima are carried as maxima of the negated value
+// so that one max/sum op mask serves the two-stage reduction.
+enum { SQ_NMIN0 = 0, SQ_NMIN1, SQ_NMIN2, SQ_MAX0, SQ_MAX1, SQ_MAX2, SQ_US0, SQ_US1, SQ_US2, SQ_LS0, SQ_LS1, SQ_LS2,
+       SQ_USUH2, SQ_USZ2, SQ_USDEL2, SQ_N };
+constexpr unsigned SQ_OPMASK = (1u << SQ_USZ2 | 1u << SQ_USDEL2) ^ ((1u << SQ_N) - 1u);    // 1 = max, 0 = sum
+
+__global__ void k_field_stats(FieldPtrs f, const double* __restrict__ delta, long long ncol, int nz, int pz,
+                              double* __restrict__ partial) {
+    PS_SMEM(double, red);
+    double acc[SQ_N];
+#pragma unroll
+    for (int q = 0; q < SQ_N; ++q) acc[q] = ((SQ_OPMASK >> q) & 1) ? -1.0e300 : 0.0;
+    const long long n = ncol * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        if (z > nz) continue;
+        const double a = f.vor[0][i], b = f.vor[1][i], c = f.vor[2][i];
+        acc[SQ_NMIN0] = fmax(acc[SQ_NMIN0], -a); acc[SQ_NMIN1] = fmax(acc[SQ_NMIN1], -b); acc[SQ_NMIN2] = fmax(acc[SQ_NMIN2], -c);
+        acc[SQ_MAX0] = fmax(acc[SQ_MAX0], a); acc[SQ_MAX1] = fmax(acc[SQ_MAX1], b); acc[SQ_MAX2] = fmax(acc[SQ_MAX2], c);
+        if (z == nz) {
+            const double u = f.vel[0][i], v = f.vel[1][i], d = delta[i];
+            acc[SQ_US0] = fmax(acc[SQ_US0], a); acc[SQ_US1] = fmax(acc[SQ_US1], b); acc[SQ_US2] = fmax(acc[SQ_US2], c);
+            acc[SQ_USUH2] = fmax(acc[SQ_USUH2], u * u + v * v);
+            acc[SQ_USZ2] += c * c;
+            acc[SQ_USDEL2] += d * d;
+        } else if (z == 0) {
+            acc[SQ_LS0] = fmax(acc[SQ_LS0], a); acc[SQ_LS1] = fmax(acc[SQ_LS1], b); acc[SQ_LS2] = fmax(acc[SQ_LS2], c);
+        }
+    }
+    for (int q = 0; q < SQ_N; ++q) {
+        const double r = block_reduce(acc[q], (SQ_OPMASK >> q) & 1, red);
+        if (threadIdx.x == 0) partial[(long long)blockIdx.x * SQ_N + q] = r;
+    }
+}
+
 // get_char_vorticity (field_diagnostics.f90:501-545): sums over cell-averaged |omega|
 __global__ void k_char_vorticity(FieldPtrs f, long long ncol, int nz, int pz, double vortrms,
                                  double* __restrict__ partial) {

@@ -104,6 +104,8 @@ struct Ctx {
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
+    double last_diag[16] = {};           // diagnostics of the last adapt (advance.f90: set_netcdf_field_diagnostic)
+    bool have_diag = false;
 
     DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[9];
     Transport tr;
@@ -1065,6 +1067,17 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
         diag[PS3D_D_WMAX] = wmax; diag[PS3D_D_USGGMAX] = usggmax; diag[PS3D_D_LSGGMAX] = lsggmax;
         diag[PS3D_D_RMV] = rmv; diag[PS3D_D_DT] = dt; diag[PS3D_D_PREFACTOR] = pref;
     }
+    {
+        const double ncelli = 1.0 / (double)c.ncell;
+        double* d = c.last_diag;
+        d[PS3D_D_VORTMAX] = vortmax; d[PS3D_D_VORTRMS] = vortrms; d[PS3D_D_VORCH] = vorch;
+        d[PS3D_D_VORMEAN_X] = r1[RQ_SUMW0] * ncelli; d[PS3D_D_VORMEAN_Y] = r1[RQ_SUMW1] * ncelli;
+        d[PS3D_D_VORMEAN_Z] = r1[RQ_SUMW2C] * ncelli;
+        d[PS3D_D_BFMAX] = bfmax; d[PS3D_D_GGMAX] = ggmax; d[PS3D_D_UMAX] = umax; d[PS3D_D_VMAX] = vmax;
+        d[PS3D_D_WMAX] = wmax; d[PS3D_D_USGGMAX] = usggmax; d[PS3D_D_LSGGMAX] = lsggmax;
+        d[PS3D_D_RMV] = rmv; d[PS3D_D_DT] = dt; d[PS3D_D_PREFACTOR] = pref;
+        c.have_diag = true;
+    }
     *dt_out = dt;
     if (c.stepper_ready && c.diffusion_ready) do_set_diffusion(c, dt, pref);     // advance.f90:375
 }
@@ -1295,6 +1308,63 @@ int ps3d_cuda_diagnostics(double out[8]) {
     out[5] = 0.5 * c.h_red[RQ_SUMWH] * ncelli;      // get_horizontal_enstrophy (:211)
     out[6] = out[1] - out[5];                       // get_vertical_enstrophy (:248)
     out[7] = std::sqrt(c.h_red[RQ_MAXWH]);          // get_max_horizontal_enstrophy (:233)
+    PS_API_END
+}
+
+int ps3d_cuda_field_stats(double out[40]) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!out) fail(PS3D_ERR_BAD_ARGUMENT, "out is null");
+    if (!c.have_diag) fail(PS3D_ERR_NOT_INITIALISED, "field_stats needs the diagnostics of adapt (advance.f90:188-193, 315-321)");
+    for (int i = 0; i < PS3D_NC_COUNT; ++i) out[i] = 0.0;
+    // summed values (field_diagnostics_netcdf.f90:292-330)
+    field_reduce(c);
+    ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    double r1[RQ_N];
+    for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
+    allreduce_host(c, r1, RQ_N, RQ_OPMASK);
+    const double ncelli = 1.0 / (double)c.ncell;
+    out[PS3D_NC_KE] = 0.5 * r1[RQ_SUMU2] * ncelli;
+    out[PS3D_NC_EN] = 0.5 * r1[RQ_SUMW2] * ncelli;
+    out[PS3D_NC_KEXY] = 0.5 * r1[RQ_SUMUH] * ncelli;
+    out[PS3D_NC_KEZ] = out[PS3D_NC_KE] - out[PS3D_NC_KEXY];
+    out[PS3D_NC_ENXY] = 0.5 * r1[RQ_SUMWH] * ncelli;
+    out[PS3D_NC_ENZ] = out[PS3D_NC_EN] - out[PS3D_NC_ENXY];
+    out[PS3D_NC_HEMAX] = std::sqrt(r1[RQ_MAXWH]);
+    // minima, maxima and the two surface rms values (:301-305, :352-413); delta = u_x + v_y -> W[0]
+    do_delta(c);
+    const long long ncol = (long long)c.nxl * c.ny;
+    PS_LAUNCH((k_field_stats), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              field_ptrs(c), (const double*)c.W[0].p, ncol, c.nz, c.pz, c.partial.p);
+    PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              (const double*)c.partial.p, c.red_blocks, (int)SQ_N, SQ_OPMASK, c.red.p);
+    c.launches += 2;
+    ps_d2h(c.h_red, c.red.p, SQ_N * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    double r2[SQ_N];
+    for (int i = 0; i < SQ_N; ++i) r2[i] = c.h_red[i];
+    allreduce_host(c, r2, SQ_N, SQ_OPMASK);
+    out[PS3D_NC_OXMIN] = -r2[SQ_NMIN0]; out[PS3D_NC_OYMIN] = -r2[SQ_NMIN1]; out[PS3D_NC_OZMIN] = -r2[SQ_NMIN2];
+    out[PS3D_NC_OXMAX] = r2[SQ_MAX0]; out[PS3D_NC_OYMAX] = r2[SQ_MAX1]; out[PS3D_NC_OZMAX] = r2[SQ_MAX2];
+    out[PS3D_NC_USOXMAX] = r2[SQ_US0]; out[PS3D_NC_USOYMAX] = r2[SQ_US1]; out[PS3D_NC_USOZMAX] = r2[SQ_US2];
+    out[PS3D_NC_LSOXMAX] = r2[SQ_LS0]; out[PS3D_NC_LSOYMAX] = r2[SQ_LS1]; out[PS3D_NC_LSOZMAX] = r2[SQ_LS2];
+    out[PS3D_NC_USUHMAX] = std::sqrt(r2[SQ_USUH2]);
+    const double nxy = (double)c.nx * (double)c.ny;
+    out[PS3D_NC_USZRMS] = std::sqrt(r2[SQ_USZ2] / nxy);
+    out[PS3D_NC_USDELRMS] = std::sqrt(r2[SQ_USDEL2] / nxy);
+    const double fcor3 = 0.0;                        // physics.f90 f_cor(3): zero for the configurations in scope
+    out[PS3D_NC_ROMIN] = out[PS3D_NC_OZMIN] / fcor3; // field_diagnostics.f90:297-298
+    out[PS3D_NC_ROMAX] = out[PS3D_NC_OZMAX] / fcor3; // :313-314
+    // handed over by adapt (advance.f90:188-193, 315-321, 366)
+    const double* d = c.last_diag;
+    out[PS3D_NC_OMAX] = d[PS3D_D_VORTMAX]; out[PS3D_NC_ORMS] = d[PS3D_D_VORTRMS]; out[PS3D_NC_OCHAR] = d[PS3D_D_VORCH];
+    out[PS3D_NC_OXMEAN] = d[PS3D_D_VORMEAN_X]; out[PS3D_NC_OYMEAN] = d[PS3D_D_VORMEAN_Y];
+    out[PS3D_NC_OZMEAN] = d[PS3D_D_VORMEAN_Z];
+    out[PS3D_NC_GMAX] = d[PS3D_D_GGMAX]; out[PS3D_NC_BFMAX] = d[PS3D_D_BFMAX];
+    out[PS3D_NC_UMAX] = d[PS3D_D_UMAX]; out[PS3D_NC_VMAX] = d[PS3D_D_VMAX]; out[PS3D_NC_WMAX] = d[PS3D_D_WMAX];
+    out[PS3D_NC_USGMAX] = d[PS3D_D_USGGMAX]; out[PS3D_NC_LSGMAX] = d[PS3D_D_LSGGMAX];
+    out[PS3D_NC_RGMAX] = d[PS3D_D_RMV];
     PS_API_END
 }
 

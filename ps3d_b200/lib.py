@@ -19,11 +19,18 @@ DIAG = ["vortmax", "vortrms", "vorch", "vormean_x", "vormean_y", "vormean_z", "b
 _dp = C.POINTER(C.c_double)
 
 # name -> argtypes; every function returns int except the introspection ones
+# field_diagnostics_netcdf.f90:36-75 (NC_KE = 1 ... NC_ROMAX = 40), in order
+NC_NAMES = ("ke", "en", "omax", "orms", "ochar", "oxmean", "oymean", "ozmean", "kexy", "kez", "enxy", "enz",
+            "oxmin", "oymin", "ozmin", "oxmax", "oymax", "ozmax", "hemax", "gmax", "bfmax", "umax", "vmax", "wmax",
+            "usoxmax", "lsoxmax", "usoymax", "lsoymax", "usozmax", "lsozmax", "usuhmax", "usgmax", "lsgmax",
+            "uszrms", "usdelrms", "rgmax", "rbfmax", "rimin", "romin", "romax")
+
 _SIGNATURES = {
     "ps3d_cuda_init": [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_void_p],
     "ps3d_cuda_init_inversion": [C.c_int],
     "ps3d_cuda_init_diffusion": [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _dp],
     "ps3d_cuda_finalise": [],
+    "ps3d_cuda_field_stats": [_dp],
     "ps3d_cuda_fftxyp2s": [_dp, _dp],
     "ps3d_cuda_fftxys2p": [_dp, _dp],
     "ps3d_cuda_fftsine": [_dp],
@@ -214,6 +221,13 @@ class PS3DLib:
         out = np.zeros(8)
         self._call("ps3d_cuda_diagnostics", _ptr(out))
         return dict(ke=out[0], en=out[1], helicity=out[2], hke=out[3], vke=out[4], hen=out[5], ven=out[6], hemax=out[7])
+
+    def field_stats(self):
+        """The 40 scalars of the field-statistics file (field_diagnostics_netcdf.f90:36-75), keyed by the
+        reference's netCDF names in lower case; needs vor2vel + adapt for the current state."""
+        out = np.zeros(len(NC_NAMES))
+        self._call("ps3d_cuda_field_stats", _ptr(out))
+        return dict(zip(NC_NAMES, out.tolist()))
 
     def kernel_launches(self): return int(self.dll.ps3d_cuda_kernel_launches())
     def last_advance_ms(self): return float(self.dll.ps3d_cuda_last_advance_ms())

@@ -106,6 +106,40 @@ def test_separate_entry_points_equal_advance(grid, stepper):
     assert rel(lib.download3("svor"), s.svor) < TOL
 
 
+def check_field_stats(lib, s):
+    """All 40 scalars of the field-statistics file against the oracle (vor2vel + adapt done on both sides)."""
+    got, want = lib.field_stats(), s.field_stats()
+    assert set(got) == set(want) and len(got) == 40
+    for k, w in want.items():
+        g = got[k]
+        if k in ("romin", "romax"):             # zeta / f_cor(3) with f_cor = 0: the same +-inf / nan as the reference
+            assert (np.isnan(g) and np.isnan(w)) or g == w, k
+        else:
+            assert g == pytest.approx(w, rel=1e-11, abs=1e-15), k
+
+
+def test_field_stats(grid):
+    lib, s, rng = grid
+    vor = rng.uniform(-1, 1, (3, s.nx, s.ny, s.nz + 1))
+    s.set_vorticity(vor)
+    lib.upload_vorticity(vor)
+    lib.vor2vel()
+    with pytest.raises(PS3DError):
+        lib.field_stats()                        # needs the diagnostics of adapt
+    d = lib.diagnostics()
+    lib.init_diffusion(d["ke"], d["en"])
+    lib.stepper_setup("cn2")
+    lib.adapt(0.0, 100.0)
+    s.adapt(0.0, 100.0)
+    check_field_stats(lib, s)
+    # ... and after a step, with the state the time loop leaves behind (write_step, advance.f90:92)
+    t, dt, _ = lib.advance(0.0, 100.0)
+    s.advance(0.0, 100.0, "cn2", literal=True)
+    lib.vor2vel(); lib.adapt(t, 100.0)
+    s.vor2vel(); s.adapt(t, 100.0)
+    check_field_stats(lib, s)
+
+
 def test_error_paths(emu):
     with pytest.raises(PS3DError) as e:
         emu.vor2vel()

@@ -155,6 +155,25 @@ def test_vor2vel_source_white_noise_tall(lib, shape):
         lib.finalise()
 
 
+def test_field_stats_64(lib):
+    """the 40 scalars of the field-statistics file (field_diagnostics_netcdf.f90:257-439)."""
+    from test_emu_kernels import check_field_stats
+    s = open_grid(lib, 64, 64, 64, -0.5 * PI * np.ones(3), PI * np.ones(3))
+    try:
+        vor = np.random.default_rng(5).uniform(-1, 1, (3, 64, 64, 65))
+        s.set_vorticity(vor)
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        d = lib.diagnostics()
+        lib.init_diffusion(d["ke"], d["en"])
+        lib.stepper_setup("cn2")
+        lib.adapt(0.0, 100.0)
+        s.adapt(0.0, 100.0)
+        check_field_stats(lib, s)
+    finally:
+        lib.finalise()
+
+
 @pytest.mark.parametrize("stepper,n,nsteps", [("cn2", 32, 100), ("impl-diff-rk4", 32, 100), ("cn2", 64, 10)])
 def test_beltrami_trajectory(lib, stepper, n, nsteps):
     """fields every step to 1e-12, dt sequence, and
