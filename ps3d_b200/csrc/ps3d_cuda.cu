@@ -16,6 +16,8 @@
 #include "fft_core.cuh"
 #include "line_fft.cuh"
 #include "zcol.cuh"
+#include "line_gen.cuh"
+#include "zcol_gen.cuh"
 #include "pointwise.cuh"
 #include "transport.h"
 
@@ -118,6 +120,11 @@ struct Ctx {
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
     DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
     DevBuf<double2> tw;
+    // lengths that are not a power of two (line_gen.cuh, zcol_gen.cuh): per-axis plan and tables
+    bool gen[3] = {false, false, false};            // x, y, z
+    GenPlan plan[3];
+    DevBuf<double2> gtw[3];                         // [n] exp(2 pi i m / n)
+    DevBuf<double> gsinz, gcosz;                    // [nz+1] sin, cos(pi j / nz)
     DevBuf<int> permy;
     int ntw = 0;
     std::vector<double> h_rkx, h_rky, h_rkz, h_k2l2, h_filt2d;   // host copies ([kx][kyl] local order)
@@ -139,6 +146,7 @@ struct Ctx {
         return g;
     }
     int ngroups() const { return (nx / 2 + 1) * (nyl / 2); }
+    GenZ genz() const { GenZ z; z.plan = plan[2]; z.tw = gtw[2].p; z.sinz = gsinz.p; z.cosz = gcosz.p; return z; }
     // the hot-loop column kernels run as two launches: the fast instantiation on the pairs (a, ny-a), a >= 1,
     // and the general one on the pair (0, ny/2) of the rank that owns ky = 0 (zcol.cuh)
     SpecGeom geom_fast() const { SpecGeom g = geom(); g.ap0 = (rank == 0) ? 1 : 0; g.npf = nyl / 2 - g.ap0; return g; }
@@ -181,6 +189,22 @@ static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntil
     } else {
         if (pro == PRO_DIFF) { allow_smem(k_line_inv<N, PRO_DIFF>, sm); PS_LAUNCH((k_line_inv<N, PRO_DIFF>), grid, block, sm, stream, a); }
         else { allow_smem(k_line_inv<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_inv<N, PRO_PLAIN>), grid, block, sm, stream, a); }
+    }
+    ++c.launches;
+}
+
+// line lengths that are not a power of two (coverage path, one rank)
+static void launch_line_gen(Ctx& c, int axis, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream) {
+    GenLine gl;
+    gl.plan = c.plan[axis]; gl.tw = c.gtw[axis].p;
+    const size_t sm = line_gen_smem_bytes(gl.plan.n);
+    const dim3 grid(std::min(ntiles, 4 * c.num_sms)), block(GEN_THREADS);
+    if (!inv) {
+        if (pro == PRO_CROSS) { allow_smem(k_line_gen_fwd<PRO_CROSS>, sm); PS_LAUNCH((k_line_gen_fwd<PRO_CROSS>), grid, block, sm, stream, a, gl); }
+        else { allow_smem(k_line_gen_fwd<PRO_PLAIN>, sm); PS_LAUNCH((k_line_gen_fwd<PRO_PLAIN>), grid, block, sm, stream, a, gl); }
+    } else {
+        if (pro == PRO_DIFF) { allow_smem(k_line_gen_inv<PRO_DIFF>, sm); PS_LAUNCH((k_line_gen_inv<PRO_DIFF>), grid, block, sm, stream, a, gl); }
+        else { allow_smem(k_line_gen_inv<PRO_PLAIN>, sm); PS_LAUNCH((k_line_gen_inv<PRO_PLAIN>), grid, block, sm, stream, a, gl); }
     }
     ++c.launches;
 }
@@ -243,7 +267,8 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.scale = 1.0 / std::sqrt((double)n);
     a.twscale = c.ntw / n;
     a.ntiles = nouter * a.nzc;
-    launch_line(c, n, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
+    if (c.gen[s.axis]) launch_line_gen(c, s.axis, s.inv, s.pro, a, a.ntiles, c.stream);
+    else launch_line(c, n, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
 }
 
 // ---- slab exchange: P equal contiguous blocks, block d of `send` goes to rank d and lands as block
@@ -476,6 +501,13 @@ static void launch_zop_n(Ctx& c, int op, const double* in, double* out) {
     ++c.launches;
 }
 static void launch_zop(Ctx& c, int op, const double* in, double* out) {
+    if (c.gen[2]) {
+        const size_t sm = gen_col_smem_bytes(1, c.nz);
+        allow_smem(k_zop_gen, sm);
+        PS_LAUNCH((k_zop_gen), dim3(c.ngroups()), dim3(GEN_COL_THREADS), sm, c.stream, c.geom(), c.genz(), op, in, out);
+        ++c.launches;
+        return;
+    }
     switch (c.nz) {
 #define X(NN) case NN: launch_zop_n<NN>(c, op, in, out); break;
         PS_FOR_Z_SIZES(X)
@@ -501,6 +533,13 @@ static void launch_v2v_n(Ctx& c, const V2VArgs& a) {
     }
 }
 static void launch_v2v(Ctx& c, const V2VArgs& a) {
+    if (c.gen[2]) {
+        const size_t sm = gen_col_smem_bytes(4, c.nz);
+        allow_smem(k_vor2vel_gen, sm);
+        PS_LAUNCH((k_vor2vel_gen), dim3(c.ngroups()), dim3(GEN_COL_THREADS), sm, c.stream, c.geom(), c.genz(), a);
+        ++c.launches;
+        return;
+    }
     switch (c.nz) {
 #define X(NN) case NN: launch_v2v_n<NN>(c, a); break;
         PS_FOR_Z_SIZES(X)
@@ -526,6 +565,13 @@ static void launch_src_n(Ctx& c, const SrcArgs& a) {
     }
 }
 static void launch_src(Ctx& c, const SrcArgs& a) {
+    if (c.gen[2]) {
+        const size_t sm = gen_col_smem_bytes(4, c.nz);
+        allow_smem(k_source_gen, sm);
+        PS_LAUNCH((k_source_gen), dim3(c.ngroups()), dim3(GEN_COL_THREADS), sm, c.stream, c.geom(), c.genz(), a);
+        ++c.launches;
+        return;
+    }
     switch (c.nz) {
 #define X(NN) case NN: launch_src_n<NN>(c, a); break;
         PS_FOR_Z_SIZES(X)
@@ -566,9 +612,27 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
                     const void* nccl_id) {
     if (g_ctx) fail(PS3D_ERR_BAD_ARGUMENT, "ps3d_cuda_init called twice without ps3d_cuda_finalise");
     if (!lower || !extent) fail(PS3D_ERR_BAD_ARGUMENT, "null lower/extent");
-    if (!pow2(nx) || !pow2(ny) || !pow2(nz) || nx < 8 || ny < 8 || nz < 8 || nx > 1024 || ny > 1024 || nz > 1024)
-        fail(PS3D_ERR_UNSUPPORTED_SIZE,
-             "grid %dx%dx%d: this build supports power-of-two nx, ny, nz in 8..1024", nx, ny, nz);
+    // Powers of two in 8..1024 run through the register-blocked kernels; other even lengths with prime factors
+    // 2, 3, 5 only (the lengths factorisen accepts, stafft.f90:128-187) through the mixed-radix coverage kernels
+    // (one rank, shared-memory limits: nx, ny <= 896, nz <= 1200).
+    bool gen_axis[3];
+    GenPlan gplan[3];
+    {
+        const int nn[3] = {nx, ny, nz};
+        const int lim[3] = {896, 896, 1200};
+        for (int i = 0; i < 3; ++i) {
+            const bool fast = pow2(nn[i]) && nn[i] >= 8 && nn[i] <= 1024;
+            gen_axis[i] = !fast;
+            if (fast) continue;
+            if (nn[i] < 6 || (nn[i] & 1) || nn[i] > lim[i] || !gen_plan_make(nn[i], gplan[i]))
+                fail(PS3D_ERR_UNSUPPORTED_SIZE,
+                     "grid %dx%dx%d: supported are powers of two in 8..1024 and even lengths 2^a 3^b 5^c (nx, ny <= 896, "
+                     "nz <= 1200)", nx, ny, nz);
+            if (nranks > 1)
+                fail(PS3D_ERR_UNSUPPORTED_SIZE, "grid %dx%dx%d: lengths that are not a power of two run on one rank only",
+                     nx, ny, nz);
+        }
+    }
     if (nranks < 1 || rank < 0 || rank >= nranks || nx % nranks || (ny / 2) % nranks)
         fail(PS3D_ERR_BAD_ARGUMENT, "bad rank layout %d/%d for %dx%d", rank, nranks, nx, ny);
     for (int i = 0; i < 3; ++i)
@@ -646,8 +710,30 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
 #endif
     ps_stream_t s = c->stream;
 
-    // twiddles: exp(2 pi i m / ntw), ntw = max(nx, ny, 2 nz)
-    c->ntw = std::max(std::max(nx, ny), 2 * nz);
+    for (int i = 0; i < 3; ++i) {
+        c->gen[i] = gen_axis[i];
+        if (!gen_axis[i]) continue;
+        c->plan[i] = gplan[i];
+        const int n = gplan[i].n;
+        const long double pi_l = 3.14159265358979323846264338327950288L;
+        std::vector<double2> tw(n);
+        for (int m = 0; m < n; ++m) {
+            const long double ang = 2.0L * pi_l * (long double)m / (long double)n;
+            tw[m] = make_double2((double)cosl(ang), (double)sinl(ang));
+        }
+        c->gtw[i].upload(tw, c->stream);
+        if (i == 2) {
+            std::vector<double> sn(n + 1), cs(n + 1);
+            for (int j = 0; j <= n; ++j) {
+                const long double ang = pi_l * (long double)j / (long double)n;
+                sn[j] = (double)sinl(ang); cs[j] = (double)cosl(ang);
+            }
+            sn[0] = 0.0; sn[n] = 0.0; cs[n / 2] = 0.0;
+            c->gsinz.upload(sn, c->stream); c->gcosz.upload(cs, c->stream);
+        }
+    }
+    // twiddles of the power-of-two kernels: exp(2 pi i m / ntw), ntw = max(nx, ny, 2 nz) over the power-of-two axes
+    c->ntw = std::max(std::max(gen_axis[0] ? 16 : nx, gen_axis[1] ? 16 : ny), gen_axis[2] ? 16 : 2 * nz);
     {
         std::vector<double2> tw(c->ntw);
         for (int m = 0; m < c->ntw; ++m) {
@@ -825,6 +911,8 @@ static void do_finalise() {
                                  &c->wz, &c->ini_mean, &c->partial, &c->red};
     for (auto* b : singles) b->release();
     c->tw.release(); c->permy.release();
+    for (int i = 0; i < 3; ++i) c->gtw[i].release();
+    c->gsinz.release(); c->gcosz.release();
 #ifndef PS3D_EMU
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -140,12 +140,51 @@ def test_field_stats(grid):
     check_field_stats(lib, s)
 
 
+@pytest.mark.parametrize("shape", [(24, 20, 12), (6, 6, 6), (16, 30, 16), (16, 16, 50)])
+def test_non_power_of_two_grids(emu, shape):
+    """Lengths 2^a 3^b 5^c that are not powers of two (stafft.f90:128-187 factorisen; radix 3 / 5 / 6 kernels
+    :561-1757): mixed-radix coverage kernels (gen_fft.cuh, line_gen.cuh, zcol_gen.cuh), any mix of axes."""
+    nx, ny, nz = shape
+    lower = np.array([-0.5 * math.pi, 0.0, -1.0])
+    extent = np.array([math.pi, 2 * math.pi, 2.0])
+    emu.init(nx, ny, nz, lower, extent)
+    try:
+        emu.init_inversion("Hou & Li")
+        s = O.PS3D(nx, ny, nz, lower, extent)
+        rng = np.random.default_rng(3)
+        f = rng.uniform(-1, 1, (nx, ny, nz + 1))
+        fs = emu.fftxyp2s(f)
+        assert rel(fs, s.fftxyp2s(f)) < TOL
+        assert rel(emu.fftxys2p(fs), f) < TOL
+        assert rel(emu.fftsine(f), s.fftsine(f)) < TOL
+        assert rel(emu.fftcosine(f), s.fftcosine(f)) < TOL
+        assert rel(emu.diffx(f), s.diffx(f)) < TOL
+        assert rel(emu.diffy(f), s.diffy(f)) < TOL
+        assert rel(emu.field_combine_physical(f), s.field_combine_physical(f)) < TOL
+        assert rel(emu.field_decompose_physical(f), s.field_decompose_physical(f)) < TOL
+        vor = rng.uniform(-1, 1, (3, nx, ny, nz + 1))
+        s.set_vorticity(vor)
+        emu.upload_vorticity(vor)
+        emu.vor2vel()
+        for name in ("svor", "vor", "svel", "vel"):
+            assert rel(emu.download3(name), getattr(s, name)) < TOL, name
+        d = emu.diagnostics()
+        emu.init_diffusion(d["ke"], d["en"])
+        emu.stepper_setup("cn2")
+        t, dt, _ = emu.advance(0.0, 100.0)
+        to, dto = s.advance(0.0, 100.0, "cn2", literal=True)
+        assert dt == pytest.approx(dto, rel=1e-13)
+        assert rel(emu.download3("svor"), s.svor) < TOL
+    finally:
+        emu.finalise()
+
+
 def test_error_paths(emu):
     with pytest.raises(PS3DError) as e:
         emu.vor2vel()
     assert e.value.status == 1
     with pytest.raises(PS3DError) as e:
-        emu.init(24, 32, 32, np.zeros(3), np.ones(3))       # stafft.f90:87-95 analogue
+        emu.init(28, 32, 32, np.zeros(3), np.ones(3))       # a factor 7: stafft.f90:87-95
     assert e.value.status == 3
     with pytest.raises(PS3DError) as e:
         emu.init(32, 32, 32, np.zeros(3), np.array([1.0, 0.0, 1.0]))   # sta2dfft.f90:67-74

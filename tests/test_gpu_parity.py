@@ -155,6 +155,43 @@ def test_vor2vel_source_white_noise_tall(lib, shape):
         lib.finalise()
 
 
+@pytest.mark.parametrize("shape", [(48, 40, 36), (96, 96, 96), (12, 24, 384), (384, 12, 24), (16, 640, 10)])
+def test_non_power_of_two_grids(lib, shape):
+    """the lengths factorisen accepts beyond powers of two (radix 3 / 5 / 6, stafft.f90:128-187,
+    561-1757) through the mixed-radix coverage kernels; operators, vor2vel, source and one cn2 step."""
+    nx, ny, nz = shape
+    s = open_grid(lib, nx, ny, nz, [-0.5 * PI, 0.0, -1.0], [PI, 2 * PI, 2.0])
+    try:
+        rng = np.random.default_rng(3)
+        f = rng.uniform(-1, 1, (nx, ny, nz + 1))
+        fs = lib.fftxyp2s(f)
+        assert rel(fs, s.fftxyp2s(f)) < FIELD_TOL
+        assert rel(lib.fftxys2p(fs), f) < FIELD_TOL
+        assert rel(lib.fftsine(f), s.fftsine(f)) < FIELD_TOL
+        assert rel(lib.fftcosine(f), s.fftcosine(f)) < FIELD_TOL
+        assert rel(lib.diffx(f), s.diffx(f)) < FIELD_TOL
+        assert rel(lib.diffy(f), s.diffy(f)) < FIELD_TOL
+        assert rel(lib.field_decompose_physical(f), s.field_decompose_physical(f)) < FIELD_TOL
+        vor = rng.uniform(-1, 1, (3, nx, ny, nz + 1))
+        s.set_vorticity(vor)
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        for name in ("svor", "vor", "svel", "vel"):
+            assert rel(lib.download3(name), getattr(s, name)) < FIELD_TOL, name
+        lib.source()
+        s.source()
+        assert rel(lib.download3("svorts"), s.svorts) < FIELD_TOL
+        d = lib.diagnostics()
+        lib.init_diffusion(d["ke"], d["en"])
+        lib.stepper_setup("cn2")
+        t, dt, _ = lib.advance(0.0, 100.0)
+        to, dto = s.advance(0.0, 100.0, "cn2", literal=True)
+        assert dt == pytest.approx(dto, rel=1e-11)
+        assert rel(lib.download3("svor"), s.svor) < FIELD_TOL
+    finally:
+        lib.finalise()
+
+
 def test_field_stats_64(lib):
     """the 40 scalars of the field-statistics file (field_diagnostics_netcdf.f90:257-439)."""
     from test_emu_kernels import check_field_stats
