@@ -44,11 +44,15 @@ struct IxSwz {
 template <int NF>
 struct IxIlv {
     int f;
+    // (NF = 4, the 8-z tiles of N = 1024: a quarter-warp is two element indices x 4 FFTs = two 64-byte half rows;
+    //  they collide (2-way) only in the stride-8 scatter of the first pass, i = 8 u + j.  A swizzle that avoids it
+    //  costs more in index registers -- the kernel is at its 64-register cap -- than the conflict does.)
+    __device__ __forceinline__ int at(int i) const { return NF * i + f; }
     __device__ __forceinline__ void put(double* sre, double*, int i, double re, double im) const {
-        reinterpret_cast<double2*>(sre)[NF * i + f] = make_double2(re, im);
+        reinterpret_cast<double2*>(sre)[at(i)] = make_double2(re, im);
     }
     __device__ __forceinline__ void get(const double* sre, const double*, int i, double& re, double& im) const {
-        const double2 c = reinterpret_cast<const double2*>(sre)[NF * i + f];
+        const double2 c = reinterpret_cast<const double2*>(sre)[at(i)];
         re = c.x; im = c.y;
     }
 };

@@ -23,6 +23,12 @@ namespace ps3d {
 enum { PRO_PLAIN = 0, PRO_DIFF = 1, PRO_CROSS = 2 };
 constexpr int LINE_ZC = 16;            // z values per tile row (pz is a multiple of this)
 constexpr int LINE_NF = LINE_ZC / 2;   // complex FFTs per tile
+// N = 1024: tiles of 8 z (64-byte rows, 4 complex FFTs, 512 threads, 64 KB of scratch) so that two blocks fit an
+// SM like at N = 512; a 16-z tile would need 128 KB and 1024 threads, one block per SM, with nothing to overlap
+// its load and store phases
+__host__ __device__ constexpr int line_zc(int n) { return n >= 1024 ? 8 : LINE_ZC; }
+__host__ __device__ constexpr int line_nf(int n) { return line_zc(n) / 2; }
+__host__ __device__ constexpr int line_threads(int n) { return line_nf(n) * n / 8; }
 
 // Row k of a line -> (destination block d, offset in doubles from the tile base), computed arithmetically
 // and branch-free so that the unrolled global accesses of a tile can all be issued back to back.
@@ -97,12 +103,13 @@ __device__ __forceinline__ double* row_dst(const LineArgs& a, int k) {
 }
 
 template <int N, int PRO>
-__global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_fwd(LineArgs a) {
+__global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024 / line_threads(N) : 1) k_line_fwd(LineArgs a) {
     PS_SMEM(double, sm);
-    const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
+    constexpr int ZC = line_zc(N), NF = line_nf(N);
+    const int t = threadIdx.x, f = t & (NF - 1), u = t / NF;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
-    const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
+    const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * ZC + 2 * f;
     const int ul = tile_local(u);
     double vr[8], vi[8];
 #pragma unroll
@@ -119,14 +126,14 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
         }
     }
     double* sre = sm;
-    double* sim = sm + LINE_NF * N;
-    const IxIlv<LINE_NF> ix{f};
+    double* sim = sm + NF * N;
+    const IxIlv<NF> ix{f};
     block_cfft<N, false>(vr, vi, u, true, sre, sim, ix, TwGlobal{a.tw, a.twscale});
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; ++e) ix.put(sre, sim, u + e * (N / 8), vr[e], vi[e]);
     __syncthreads();
-    const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * LINE_ZC + 2 * f;
+    const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * ZC + 2 * f;
     const double sc = a.scale, hs = 0.5 * a.scale;
 #pragma unroll(PRO == PRO_CROSS ? 2 : 4)
     for (int e = 0; e < 4; ++e) {
@@ -152,15 +159,16 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
 }
 
 template <int N, int PRO>
-__global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_line_inv(LineArgs a) {
+__global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024 / line_threads(N) : 1) k_line_inv(LineArgs a) {
     PS_SMEM(double, sm);
-    const int t = threadIdx.x, f = t & (LINE_NF - 1), u = t / LINE_NF;
+    constexpr int ZC = line_zc(N), NF = line_nf(N);
+    const int t = threadIdx.x, f = t & (NF - 1), u = t / NF;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
-    const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC + 2 * f;
+    const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * ZC + 2 * f;
     double* sre = sm;
-    double* sim = sm + LINE_NF * N;
-    const IxIlv<LINE_NF> ix{f};
+    double* sim = sm + NF * N;
+    const IxIlv<NF> ix{f};
     // rows k and N-k (k = 0: rows 0 and N/2); all eight loads are issued before the first use
     double2 xa[4], xb[4];
 #pragma unroll
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
     fft_gather<N>(vr, vi, u, sre, sim, ix);
     __syncthreads();
     block_cfft<N, true>(vr, vi, u, true, sre, sim, ix, TwGlobal{a.tw, a.twscale});
-    const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * LINE_ZC + 2 * f;
+    const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * ZC + 2 * f;
     const double sc = a.scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
@@ -209,6 +217,6 @@ __global__ void __launch_bounds__(N, (N >= 64 && N <= 1024) ? 1024 / N : 1) k_li
 }
 
 template <int N>
-constexpr size_t line_smem_bytes() { return (size_t)LINE_NF * 2 * N * sizeof(double); }
+constexpr size_t line_smem_bytes() { return (size_t)line_nf(N) * 2 * N * sizeof(double); }
 
 }  // namespace ps3d

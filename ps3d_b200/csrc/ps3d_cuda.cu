@@ -182,7 +182,7 @@ static void allow_smem(K, size_t) {}
 template <int N>
 static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
     const size_t sm = line_smem_bytes<N>();
-    const dim3 grid(max_ctas > 0 ? std::min(ntiles, max_ctas) : ntiles), block(N);
+    const dim3 grid(max_ctas > 0 ? std::min(ntiles, max_ctas) : ntiles), block(line_threads(N));
     if (!inv) {
         if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS>), grid, block, sm, stream, a); }
         else { allow_smem(k_line_fwd<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN>), grid, block, sm, stream, a); }
@@ -234,7 +234,9 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.in0 = s.in[0]; a.in1 = s.in[1]; a.in2 = s.in[2]; a.in3 = s.in[3];
     a.add1 = s.add1; a.add3 = s.add3;
     a.out = s.out;
-    a.nzc = (s.nzc < 0) ? c.pz / LINE_ZC : s.nzc;
+    const int nline = (s.axis == 1) ? c.ny : c.nx;
+    const int zcl = c.gen[s.axis] ? LINE_ZC : line_zc(nline);     // z values per tile of this sweep's kernel
+    a.nzc = (s.nzc < 0) ? c.pz / zcl : s.nzc;
     a.zc0 = s.zc0; a.in_zc0 = s.in_zc0; a.out_zc0 = s.out_zc0; a.final_store = s.final_store;
     const long long ipz = s.in_pitch ? s.in_pitch : c.pz, opz = s.out_pitch ? s.out_pitch : c.pz;
     a.tw = c.tw.p;
@@ -376,7 +378,8 @@ static void setup_p2p(Ctx& c) {
 // forward (fftxyp2s): first = y sweep, second = x sweep; inverse (fftxys2p): first = x, second = y.
 static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
     if (c.nranks == 1) {
-        const int nzc = c.pz / LINE_ZC, G = c.l2_chunks;
+        // (the L2-blocked variant assumes 16-z tiles on both axes)
+        const int nzc = c.pz / LINE_ZC, G = (line_zc(c.nx) == LINE_ZC && line_zc(c.ny) == LINE_ZC && !c.gen[0] && !c.gen[1]) ? c.l2_chunks : 0;
         if (G <= 0 || G >= nzc) {
             for (int i = 0; i < n; ++i) {
                 first[i].out = c.W[5].p;
