@@ -98,7 +98,7 @@ def run_reference(args):
     sample = f"Beltrami {n}^3 cn2 steps (bounded sample of the 512^3 workload), NumPy/SciPy port of the reference algorithm"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Beltrami {args.n}^3 cn2 (examples/beltrami_512.config)", "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},

@@ -95,6 +95,14 @@ def main():
         for k in ("vortmax", "vortrms", "vorch", "ggmax", "umax", "usggmax", "lsggmax"):
             errs[k] = max(errs.get(k, 0.0), abs(diag[k] - ref.diag[k]) / abs(ref.diag[k]))
     errs["svor_after"] = rel(lib.download3("svor"), ref.svor[:, :, kys])
+    # the 40 field statistics (reduced over the ranks inside the library) for the state after the last step
+    lib.vor2vel(); lib.adapt(t, 100.0)
+    ref.vor2vel(); ref.adapt(tr, 100.0)
+    got, want = lib.field_stats(), ref.field_stats()
+    for k, w in want.items():
+        if k in ("romin", "romax"):
+            continue
+        errs["stat_" + k] = abs(got[k] - w) / max(abs(w), 1e-3)
     n_a2a, sent = lib.comm_stats()
     lib.finalise()
     worst = max(errs.values())
