@@ -179,6 +179,42 @@ def test_non_power_of_two_grids(emu, shape):
         emu.finalise()
 
 
+def check_reference_z_known_answers(lib, nz_deriv):
+    """The reference's analytic z tests through the C ABI: unit-tests/test_diffz_1..4.f90 (central_diffz) and
+    tests/test_deriv.f90 (fftsine -> * rkz -> fftcosine), with the reference's tolerances."""
+    from test_oracle_known_answers import deriv_via_sine_series, grid as ogrid
+    PI = math.pi
+    cases = [((32, 32, 32), [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], lambda x, y, z: z + 0 * x * y, lambda x, y, z: 1.0 + 0 * z, 1e-14),
+             ((16, 32, 32), [0.0, -0.5 * PI, 0.0], [PI, 2 * PI, 2 * PI], lambda x, y, z: z * np.cos(2 * x) * np.sin(y),
+              lambda x, y, z: np.cos(2 * x) * np.sin(y) + 0 * z, 2e-14),
+             ((16, 32, 32), [0.0, -0.5 * PI, 0.0], [PI, 2 * PI, 2 * PI], lambda x, y, z: 6 * z + 3 * np.cos(2 * x) * np.sin(y) * z,
+              lambda x, y, z: 6 + 3 * np.cos(2 * x) * np.sin(y) + 0 * z, 2e-13),
+             ((32, 32, 32), [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], lambda x, y, z: 1 - 3 * z ** 2 + 0 * x * y, lambda x, y, z: -6 * z + 0 * x * y, 1e-1)]
+    for (nx, ny, nz), lower, extent, f, dfdz, atol in cases:
+        lib.init(nx, ny, nz, np.asarray(lower, float), np.asarray(extent, float))
+        try:
+            lib.init_inversion("Hou & Li")
+            x, y, z = ogrid(O.PS3D(nx, ny, nz, lower, extent))
+            assert np.max(np.abs(lib.central_diffz(f(x, y, z)) - dfdz(x, y, z))) < atol
+        finally:
+            lib.finalise()
+    nz = nz_deriv
+    lib.init(8, 8, nz, np.zeros(3), np.ones(3))
+    try:
+        lib.init_inversion("Hou & Li")
+        col = lambda v: np.broadcast_to(v, (8, 8, nz + 1)).copy()
+        d, exact = deriv_via_sine_series(nz, lambda a: lib.fftsine(col(a))[3, 5], lambda v: lib.fftcosine(col(v))[3, 5])
+        assert np.max(np.abs(d - exact)) < 3.01 / nz
+        want, _ = deriv_via_sine_series(nz, lambda a: np.concatenate(([0.0], O.dst(a[1:].copy(), nz))), lambda v: O.dct(v, nz))
+        assert np.max(np.abs(d - want)) < 1e-12
+    finally:
+        lib.finalise()
+
+
+def test_reference_z_known_answers(emu):
+    check_reference_z_known_answers(emu, 64)
+
+
 def test_error_paths(emu):
     with pytest.raises(PS3DError) as e:
         emu.vor2vel()

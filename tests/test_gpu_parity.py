@@ -192,6 +192,12 @@ def test_non_power_of_two_grids(lib, shape):
         lib.finalise()
 
 
+def test_reference_z_known_answers(lib):
+    """unit-tests/test_diffz_1..4.f90 and tests/test_deriv.f90 (nz = 1024 as in the reference) through the C ABI."""
+    from test_emu_kernels import check_reference_z_known_answers
+    check_reference_z_known_answers(lib, 1024)
+
+
 def test_field_stats_64(lib):
     """the 40 scalars of the field-statistics file (field_diagnostics_netcdf.f90:257-439)."""
     from test_emu_kernels import check_field_stats

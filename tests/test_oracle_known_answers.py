@@ -147,6 +147,41 @@ def test_diffz():
     assert np.max(np.abs(s.central_diffz(f) - np.cos(2 * x) * np.sin(y))) < 2e-14
 
 
+def test_diffz_3_4():
+    """unit-tests/test_diffz_3.f90:52-63 (6z + 3 cos(kx) sin(ly) z, atol 2e-13) and test_diffz_4.f90 (1 - 3z^2 ->
+    -6z with the one-sided boundary rows, atol 1e-1)."""
+    s = O.PS3D(16, 32, 32, [0.0, -0.5 * PI, 0.0], [PI, 2 * PI, 2 * PI])
+    x, y, z = grid(s)
+    f = 6 * z + 3 * np.cos(2 * x) * np.sin(y) * z
+    assert np.max(np.abs(s.central_diffz(f) - (6 + 3 * np.cos(2 * x) * np.sin(y)))) < 2e-13
+    s = O.PS3D(32, 32, 32, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
+    x, y, z = grid(s)
+    assert np.max(np.abs(s.central_diffz(1 - 3 * z ** 2 + 0 * x * y) + 6 * z)) < 1e-1
+
+
+def deriv_via_sine_series(nz, dst_fn, dct_fn):
+    """tests/test_deriv.f90:33-62: d/dz of phi = 1 - 2 z^3 on [0, 1] from the sine series of phi - phi_lin
+    (dst -> * rkz -> dct, + slope of phi_lin); returns (spectral derivative, exact derivative)."""
+    z = np.arange(nz + 1) / nz
+    a = (1 - 2 * z ** 3) - (1 - 2 * z)
+    w = dst_fn(a)                                   # rows 1..nz-1 transformed, row nz -> 0
+    rkz = PI * np.arange(nz + 1)                    # deriv1d.f90:17-22 with Lz = 1
+    d = dct_fn(rkz * w) - 2.0
+    return d, -6 * z ** 2
+
+
+@pytest.mark.parametrize("nz", [64, 1024])
+def test_deriv(nz):
+    """tests/test_deriv.f90 (prints the errors, no tolerance): the decomposition-based derivative converges like
+    3/nz in the max norm (2.93e-3 at the reference's nz = 1024)."""
+    def dst_fn(a):
+        out = np.zeros(nz + 1)
+        out[1:] = O.dst(a[1:].copy(), nz)
+        return out
+    d, exact = deriv_via_sine_series(nz, dst_fn, lambda v: O.dct(v, nz))
+    assert np.max(np.abs(d - exact)) < 3.01 / nz
+
+
 def test_implicit_rk():
     """unit-tests/test_implicit_rk.f90:64-94: S = D = 1, exact solution
     q E + (1 - E) S / D with E = exp(-dt D); atol 1e-12 at dt = 0.0125."""
