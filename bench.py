@@ -114,6 +114,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--grid", "--n", dest="n", type=int, default=512, help="grid size (nx = ny = nz)")
+    ap.add_argument("--nz", type=int, default=0, help="vertical cells if different from --grid (dev runs)")
     ap.add_argument("--stepper", default="cn2")
     ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -149,9 +150,10 @@ def main():
         box = [torch.cuda.nccl.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         nccl_id = box[0]
-    solver = host.Solver(lib, n, n, n, lower, extent, stepper=args.stepper, rank=rank, nranks=world, nccl_id=nccl_id)
+    nzz = args.nz or n
+    solver = host.Solver(lib, n, n, nzz, lower, extent, stepper=args.stepper, rank=rank, nranks=world, nccl_id=nccl_id)
     nxl = n // world
-    vor_np = host.beltrami_vorticity(n, n, n, lower, extent, x0=rank * nxl, x1=(rank + 1) * nxl)
+    vor_np = host.beltrami_vorticity(n, n, nzz, lower, extent, x0=rank * nxl, x1=(rank + 1) * nxl)
     vor_pinned = torch.from_numpy(vor_np).pin_memory()
     vor_host = vor_pinned.numpy()
     solver.setup_fields(vor_host)
@@ -202,7 +204,7 @@ def main():
 
     # ---- per-kernel device times (CUDA events on the library's stream), roofline of the dominant one ----
     peak, peak_src = peaks()
-    N = n * n * (n + 1) // world                           # array elements per field on this rank
+    N = n * n * (nzz + 1) // world                         # array elements per field on this rank
     kinfo = [("line_fwd_y", 16), ("line_fwd_x", 16), ("line_inv_x", 16), ("line_inv_y", 16),
              ("vor2vel_columns", 8 * 16), ("source_columns", 5 * 16)]
     kernels = {}
@@ -229,8 +231,8 @@ def main():
     roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBs"], "peak": peak, "unit": "GB/s",
             "frac": kernels[dom]["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"]}
-    step_bytes = SWEEPS[args.stepper] * 16 * n * n * (n + 1)   # whole job, peak = P x one GPU
-    value = n ** 3 / (ms_step * 1e-3)                      # whole job: the grid is split over the ranks
+    step_bytes = SWEEPS[args.stepper] * 16 * n * n * (nzz + 1)   # whole job, peak = P x one GPU
+    value = n * n * nzz / (ms_step * 1e-3)                      # whole job: the grid is split over the ranks
     n_a2a, sent = lib.comm_stats()
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -245,7 +247,7 @@ def main():
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                           "peak": peak * world, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / (peak * world)},
         "kernels": kernels, "step_share_ms": share,
-        "e2e": {"value": n ** 3 / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+        "e2e": {"value": n * n * nzz / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                 "d2h_bytes_per_step": (16 + 8) * 8, "ms_per_step": e2e_sec * 1e3},
         "comm": {"alltoalls_total": int(n_a2a), "bytes_sent_per_rank_total": sent},
         "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps * 1e3, "clocks": clocks,

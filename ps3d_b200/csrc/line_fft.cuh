@@ -72,6 +72,7 @@ struct LineArgs {
     int in_zc0, out_zc0;      // z-chunk held at offset 0 of the input / output array (0 for full arrays; = zc0 for
                               // the compact, L2-resident intermediate of a chunked 2-D FFT)
     int final_store;          // 1: streaming stores (result leaves the cache), 0: keep in L2 for the next sweep
+    int scatter_fence;        // peer-memory scatter: system-scope fence before the block retires
     const double* kdiff;      // DIFF: wavenumber per k = 0..N/2 (0 at k = 0 and N/2)
     double scale;             // 1/sqrt(N)
     const double2* tw;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024
     }
     __syncthreads();          // scratch is reused by the next tile of a persistent launch
     }
-    if (a.out_map.self >= 0) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
+    if (a.out_map.self >= 0 && a.scatter_fence) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
 }
 
 template <int N, int PRO>
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024
         st2f(a.final_store, row_dst(a, u + e * (N / 8)) + obase, vr[e] * sc, vi[e] * sc);
     __syncthreads();          // scratch is reused by the next tile of a persistent launch
     }
-    if (a.out_map.self >= 0) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
+    if (a.out_map.self >= 0 && a.scatter_fence) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
 }
 
 template <int N>

@@ -103,6 +103,8 @@ struct Ctx {
     int red_blocks = RED_BLOCKS;         // blocks of the two-stage reductions: fixed per grid size -> deterministic sums
     int num_sms = 148;
     int p2p_ctas_per_sm = -1;            // PS3D_P2P_CTAS: blocks per SM of the persistent scatter sweeps (0 = full grid, -1 = auto)
+    int scatter_fence = 1;               // PS3D_NO_SCATTER_FENCE=1: rely on kernel completion for the visibility of peer stores
+    int fuse_update = 1;                 // PS3D_NO_FUSED_UPDATE=1: cn2 update as a separate kernel after the source kernel
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
     double last_advance_ms = 0.0;
@@ -238,6 +240,7 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     const int zcl = c.gen[s.axis] ? LINE_ZC : line_zc(nline);     // z values per tile of this sweep's kernel
     a.nzc = (s.nzc < 0) ? c.pz / zcl : s.nzc;
     a.zc0 = s.zc0; a.in_zc0 = s.in_zc0; a.out_zc0 = s.out_zc0; a.final_store = s.final_store;
+    a.scatter_fence = c.scatter_fence;
     const long long ipz = s.in_pitch ? s.in_pitch : c.pz, opz = s.out_pitch ? s.out_pitch : c.pz;
     a.tw = c.tw.p;
     int n, nouter;
@@ -658,6 +661,8 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
+    c->fuse_update = getenv("PS3D_NO_FUSED_UPDATE") ? 0 : 1;
+    c->scatter_fence = getenv("PS3D_NO_SCATTER_FENCE") ? 0 : 1;
     c->p2p_ctas_per_sm = getenv("PS3D_P2P_CTAS") ? atoi(getenv("PS3D_P2P_CTAS")) : -1;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
     c->rank = rank; c->nranks = nranks;
@@ -951,7 +956,12 @@ static void do_vor2vel(Ctx& c) {
     fft2d_batch(c, 6, f, g);
 }
 
-static void do_source(Ctx& c) {
+static StepArgs step_args(Ctx& c);
+static void vor_mean(Ctx& c, int mode);
+
+// upd < 0: svorts only.  upd = 0 / 1 (cn2, power-of-two nz): the Crank-Nicolson update of cn2.f90:120-135 /
+// :162-173 rides on the last stage of the source kernel, svorts is not stored (see SrcArgs)
+static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0) {
     const double fc[3] = {0.0, 0.0, 0.0};    // physics.f90 f_cor: zero for the configurations in scope
     const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
     const double *xi = c.vor[0].p, *eta = c.vor[1].p, *zeta = c.vor[2].p;
@@ -965,7 +975,12 @@ static void do_source(Ctx& c) {
     SrcArgs a;
     a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
     a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
+    a.upd = upd; a.c1 = dt2;
+    const StepArgs st = step_args(c);
+    for (int i = 0; i < 3; ++i) { a.svor[i] = st.svor[i]; a.vortsm[i] = st.wa[i]; }
+    a.f2d = st.f2d; a.filtz = st.filtz; a.vd = st.vd;
     launch_src(c, a);
+    if (upd >= 0) vor_mean(c, 1);
 }
 
 static void vor_mean(Ctx& c, int mode) {
@@ -1050,15 +1065,23 @@ static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 /
     ++c.launches;
 }
 
-static void do_step(Ctx& c, double* t, double dt) {
+// the cn2 update can ride on the source kernel (power-of-two nz; PS3D_NO_FUSED_UPDATE=1 keeps it separate)
+static bool cn2_fused(const Ctx& c) { return c.stepper == PS3D_STEPPER_CN2 && !c.gen[2] && c.fuse_update; }
+
+// first_update_done: the source call before this step already carried the first update (ps3d_cuda_advance)
+static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false) {
     if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
     if (c.stepper == PS3D_STEPPER_CN2) {
         const double dt2 = 0.5 * dt;                       // cn2.f90:101
-        cn2_update(c, dt2, 0);                             // :120-137
+        if (!first_update_done) cn2_update(c, dt2, 0);     // :120-137
         for (int iter = 0; iter < 2; ++iter) {             // niter = 2 (:34, :143-177)
             do_vor2vel(c);
-            do_source(c);
-            cn2_update(c, dt2, 1);
+            if (cn2_fused(c)) {
+                do_source(c, 1, dt2);
+            } else {
+                do_source(c);
+                cn2_update(c, dt2, 1);
+            }
         }
         *t += dt;
     } else {
@@ -1327,8 +1350,13 @@ int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, i
     double dt = 0.0;
     do_vor2vel(c);                                     // advance.f90:85
     do_adapt(c, *t, t_limit, alpha, pretype_id, win, &dt, diag_out);   // :88
-    do_source(c);                                      // :95
-    do_step(c, t, dt);                                 // :102
+    if (cn2_fused(c)) {
+        do_source(c, 0, 0.5 * dt);                     // :95 + the first update of cn2_step (cn2.f90:120-137)
+        do_step(c, t, dt, true);                       // :102
+    } else {
+        do_source(c);                                  // :95
+        do_step(c, t, dt);                             // :102
+    }
 #ifndef PS3D_EMU
     PS_CUDA_TRY(cudaEventRecord(c.ev1, c.stream));
     PS_CUDA_TRY(cudaEventSynchronize(c.ev1));
@@ -1504,6 +1532,9 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
                 SrcArgs a;
                 a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
                 a.s0 = c.W[3].p; a.s1 = c.W[4].p; a.s2 = c.W[5].p;
+                a.upd = -1; a.c1 = 0.0;
+                for (int i = 0; i < 3; ++i) { a.svor[i] = nullptr; a.vortsm[i] = nullptr; }
+                a.f2d = a.filtz = a.vd = nullptr;
                 launch_src(c, a);
                 break;
             }

@@ -41,6 +41,19 @@ void set_error(const char* fmt, ...);
 
 struct DeviceError {};
 
+// 8-byte asynchronous copy global -> shared (LDGSTS) and the wait for this thread's outstanding copies; the
+// test-only emulator copies at once
+#ifdef PS3D_EMU
+inline void ps_cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+inline void ps_cp_async_wait() {}
+#else
+__device__ __forceinline__ void ps_cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ps_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
 #ifdef PS3D_EMU
 typedef int ps_stream_t;
 #define PS_LAUNCH(kernel, grid, block, smem, stream, ...) \

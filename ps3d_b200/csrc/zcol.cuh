@@ -807,6 +807,16 @@ constexpr size_t src_smem_bytes(bool gen) { return (size_t)(4 * ZCfg<NZ>::BUF + 
 struct SrcArgs {
     const double* r; const double* q; const double* p;   // semi-spectral fluxes
     double* s0; double* s1; double* s2;                  // svorts (mixed spectral)
+    // Crank-Nicolson update folded into the last stage (cn2.f90:120-135, 162-173 with the combine -> vdiss ->
+    // decompose pairs collapsed, see k_cn2_update): upd < 0: store svorts;  upd = 0: vortsm = svor + c1 S,
+    // svor = fac (vortsm + c1 S);  upd = 1: svor = fac (vortsm + c1 S).  svorts is then not stored at all.
+    int upd;
+    double c1;                    // dt/2
+    double* svor[3];
+    double* vortsm[3];
+    const double* f2d;            // vdiss * filt2d per column
+    const double* filtz;          // z part of the filter, [nz+1]
+    const double* vd;             // vdiss per column: the (0,0) column has filt = 1 (inversion_utils.f90:275-277)
 };
 
 // semi-spectral curl of one row, first two components, from row z of r and the rows z-1/z+1 (lo/hi) of q, p;
@@ -828,6 +838,47 @@ __device__ __forceinline__ Row4 curl2_row(const Row4& fq, const Row4& fp, const 
 #pragma unroll
     for (int s = 0; s < 4; ++s) s2.v[s] = qx.v[s] - py.v[s]; // dq/dx - dp/dy (:363-367)
     return s2;
+}
+
+// prefetch of the rows this thread owns of one 4-slot field into a column buffer (asynchronous copies; the same
+// thread reads them back after ps_cp_async_wait, so no barrier is involved)
+template <int NZ>
+__device__ __forceinline__ void rows_prefetch(double* buf, const double* __restrict__ src, const Grp& r) {
+    constexpr int LC = ZCfg<NZ>::LC;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        const int zz = cz(z);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (s < 2 || !r.dupx) ps_cp_async8(buf + s * LC + zz, src + r.off[s] + z);
+    }
+}
+
+// last stage of the source kernel for one component: svorts row -> memory, or the Crank-Nicolson update with it
+template <int NZ, bool GEN>
+__device__ __forceinline__ void src_finish(const SrcArgs& a, int comp, const double* S, const double* X, double* sv_out,
+                                           const SpecGeom& g, const Grp& r, const double (&f2)[4]) {
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const int z = my_row<NZ>(it);
+        if (z < 0) continue;
+        const Row4 sr = row_load_s<NZ>(S, z);
+        if (a.upd < 0) { row_store_g<NZ>(sv_out, r, z, sr); continue; }
+        const Row4 x = row_load_s<NZ>(X, z);             // svor (upd = 0) or vortsm (upd = 1), prefetched
+        const double fz = __ldg(&a.filtz[z]);
+        Row4 sm, out;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            double fac = f2[s] * fz;
+            if (GEN && r.g00 && s == 0) fac = f2[s];      // (0,0): vdiss only
+            sm.v[s] = (a.upd == 0) ? x.v[s] + a.c1 * sr.v[s] : x.v[s];
+            out.v[s] = fac * (sm.v[s] + a.c1 * sr.v[s]);
+        }
+        if (a.upd == 0) row_store_g<NZ>(a.vortsm[comp], r, z, sm);
+        row_store_g<NZ>(a.svor[comp], r, z, out);
+    }
 }
 
 template <int NZ, bool GEN>
@@ -909,21 +960,29 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_source
         row_store_s<NZ>(Q, z, s2);
     }
     __syncthreads();
-    xform2<NZ>(R, XF_DST, T, XF_DST, scr);
+    // per-slot factor of the update: vdiss * filt2d of the column ((0,0): vdiss, filt = 1)
+    double f2[4] = {0.0, 0.0, 0.0, 0.0};
+    if (a.upd >= 0) {
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        row_store_g<NZ>(a.s0, r, z, row_load_s<NZ>(R, z));
-        row_store_g<NZ>(a.s1, r, z, row_load_s<NZ>(T, z));
+        for (int s = 0; s < 4; ++s) {
+            const long long col = r.off[s] / g.pz;
+            f2[s] = (GEN && r.g00 && s == 0) ? __ldg(&a.vd[0]) : __ldg(&a.f2d[col]);
+        }
     }
+    const double* x0 = (a.upd == 0) ? a.svor[0] : a.vortsm[0];
+    const double* x1 = (a.upd == 0) ? a.svor[1] : a.vortsm[1];
+    const double* x2 = (a.upd == 0) ? a.svor[2] : a.vortsm[2];
+    // component 2 first (the half-filled transform round); its update operand lands in P, free since the curl
+    if (a.upd >= 0) rows_prefetch<NZ>(P, x2, r);
     xform2<NZ>(Q, XF_DST, nullptr, XF_DST, scr);
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        row_store_g<NZ>(a.s2, r, z, row_load_s<NZ>(Q, z));
-    }
+    if (a.upd >= 0) ps_cp_async_wait();
+    src_finish<NZ, GEN>(a, 2, Q, P, a.s2, g, r, f2);
+    // components 0, 1: operands into P and Q (this thread only ever touches its own rows of them from here on)
+    if (a.upd >= 0) { rows_prefetch<NZ>(P, x0, r); rows_prefetch<NZ>(Q, x1, r); }
+    xform2<NZ>(R, XF_DST, T, XF_DST, scr);
+    if (a.upd >= 0) ps_cp_async_wait();
+    src_finish<NZ, GEN>(a, 0, R, P, a.s0, g, r, f2);
+    src_finish<NZ, GEN>(a, 1, T, Q, a.s1, g, r, f2);
 }
 
 }  // namespace ps3d
