@@ -26,9 +26,9 @@ constexpr int LINE_NF = LINE_ZC / 2;   // complex FFTs per tile
 // N = 1024: tiles of 8 z (64-byte rows, 4 complex FFTs, 512 threads, 64 KB of scratch) so that two blocks fit an
 // SM like at N = 512; a 16-z tile would need 128 KB and 1024 threads, one block per SM, with nothing to overlap
 // its load and store phases
+// Sweeps that scatter their rows into peer memory keep 16-z tiles at every N: 128-byte stores over NVLink.
 __host__ __device__ constexpr int line_zc(int n) { return n >= 1024 ? 8 : LINE_ZC; }
-__host__ __device__ constexpr int line_nf(int n) { return line_zc(n) / 2; }
-__host__ __device__ constexpr int line_threads(int n) { return line_nf(n) * n / 8; }
+__host__ __device__ constexpr int line_threads(int n, int zc) { return (zc / 2) * n / 8; }
 
 // Row k of a line -> (destination block d, offset in doubles from the tile base), computed arithmetically
 // and branch-free so that the unrolled global accesses of a tile can all be issued back to back.
@@ -103,10 +103,10 @@ __device__ __forceinline__ double* row_dst(const LineArgs& a, int k) {
     return a.outp[d & 7] + off;
 }
 
-template <int N, int PRO>
-__global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024 / line_threads(N) : 1) k_line_fwd(LineArgs a) {
+template <int N, int PRO, int ZC = line_zc(N)>
+__global__ void __launch_bounds__(line_threads(N, ZC), (N >= 64 && N <= 1024) ? 1024 / line_threads(N, ZC) : 1) k_line_fwd(LineArgs a) {
     PS_SMEM(double, sm);
-    constexpr int ZC = line_zc(N), NF = line_nf(N);
+    constexpr int NF = ZC / 2;
     const int t = threadIdx.x, f = t & (NF - 1), u = t / NF;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
@@ -159,10 +159,10 @@ __global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024
     if (a.out_map.self >= 0 && a.scatter_fence) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
 }
 
-template <int N, int PRO>
-__global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024 / line_threads(N) : 1) k_line_inv(LineArgs a) {
+template <int N, int PRO, int ZC = line_zc(N)>
+__global__ void __launch_bounds__(line_threads(N, ZC), (N >= 64 && N <= 1024) ? 1024 / line_threads(N, ZC) : 1) k_line_inv(LineArgs a) {
     PS_SMEM(double, sm);
-    constexpr int ZC = line_zc(N), NF = line_nf(N);
+    constexpr int NF = ZC / 2;
     const int t = threadIdx.x, f = t & (NF - 1), u = t / NF;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(line_threads(N), (N >= 64 && N <= 1024) ? 1024
     if (a.out_map.self >= 0 && a.scatter_fence) __threadfence_system();     // peer-memory scatter: stores visible to the owner GPU
 }
 
-template <int N>
-constexpr size_t line_smem_bytes() { return (size_t)line_nf(N) * 2 * N * sizeof(double); }
+template <int N, int ZC = line_zc(N)>
+constexpr size_t line_smem_bytes() { return (size_t)(ZC / 2) * 2 * N * sizeof(double); }
 
 }  // namespace ps3d

@@ -181,18 +181,27 @@ static void allow_smem(K, size_t) {}
 #define PS_FOR_LINE_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
 #define PS_FOR_Z_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
 
-template <int N>
-static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
-    const size_t sm = line_smem_bytes<N>();
-    const dim3 grid(max_ctas > 0 ? std::min(ntiles, max_ctas) : ntiles), block(line_threads(N));
+template <int N, int ZC>
+static void launch_line_nz(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
+    const size_t sm = line_smem_bytes<N, ZC>();
+    const dim3 grid(max_ctas > 0 ? std::min(ntiles, max_ctas) : ntiles), block(line_threads(N, ZC));
     if (!inv) {
-        if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS>), grid, block, sm, stream, a); }
-        else { allow_smem(k_line_fwd<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN>), grid, block, sm, stream, a); }
+        if (pro == PRO_CROSS) { allow_smem(k_line_fwd<N, PRO_CROSS, ZC>, sm); PS_LAUNCH((k_line_fwd<N, PRO_CROSS, ZC>), grid, block, sm, stream, a); }
+        else { allow_smem(k_line_fwd<N, PRO_PLAIN, ZC>, sm); PS_LAUNCH((k_line_fwd<N, PRO_PLAIN, ZC>), grid, block, sm, stream, a); }
     } else {
-        if (pro == PRO_DIFF) { allow_smem(k_line_inv<N, PRO_DIFF>, sm); PS_LAUNCH((k_line_inv<N, PRO_DIFF>), grid, block, sm, stream, a); }
-        else { allow_smem(k_line_inv<N, PRO_PLAIN>, sm); PS_LAUNCH((k_line_inv<N, PRO_PLAIN>), grid, block, sm, stream, a); }
+        if (pro == PRO_DIFF) { allow_smem(k_line_inv<N, PRO_DIFF, ZC>, sm); PS_LAUNCH((k_line_inv<N, PRO_DIFF, ZC>), grid, block, sm, stream, a); }
+        else { allow_smem(k_line_inv<N, PRO_PLAIN, ZC>, sm); PS_LAUNCH((k_line_inv<N, PRO_PLAIN, ZC>), grid, block, sm, stream, a); }
     }
     ++c.launches;
+}
+
+// z values per tile of the sweep kernel for line length n: line_zc(n), except 16 for peer-memory scatter sweeps
+static int sweep_zc(int n, bool scatter) { return scatter ? LINE_ZC : line_zc(n); }
+
+template <int N>
+static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
+    if (line_zc(N) != LINE_ZC && a.out_map.self >= 0) launch_line_nz<N, LINE_ZC>(c, inv, pro, a, ntiles, stream, max_ctas);
+    else launch_line_nz<N, line_zc(N)>(c, inv, pro, a, ntiles, stream, max_ctas);
 }
 
 // line lengths that are not a power of two (coverage path, one rank)
@@ -237,7 +246,7 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.add1 = s.add1; a.add3 = s.add3;
     a.out = s.out;
     const int nline = (s.axis == 1) ? c.ny : c.nx;
-    const int zcl = c.gen[s.axis] ? LINE_ZC : line_zc(nline);     // z values per tile of this sweep's kernel
+    const int zcl = c.gen[s.axis] ? LINE_ZC : sweep_zc(nline, s.scatter >= 0);     // z values per tile of this sweep's kernel
     a.nzc = (s.nzc < 0) ? c.pz / zcl : s.nzc;
     a.zc0 = s.zc0; a.in_zc0 = s.in_zc0; a.out_zc0 = s.out_zc0; a.final_store = s.final_store;
     a.scatter_fence = c.scatter_fence;
@@ -428,9 +437,10 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
             first[i].out = t2[i & 1];
             first[i].scatter = i & 1;
             first[i].on_comm_stream = true;
-            // measured (512^3 cn2): 2 GPUs 44.8 ms with two persistent blocks per SM vs 45.9 full grid; 8 GPUs 14.9 ms
-            // full grid vs 15.4 persistent -> persistent only for the large per-rank blocks of P = 2
-            first[i].max_ctas = (c.p2p_ctas_per_sm >= 0 ? c.p2p_ctas_per_sm : (c.nranks <= 2 ? 2 : 0)) * c.num_sms;
+            // persistent launch, two blocks per SM: the system-scope fence that ends a scatter sweep is then paid once
+            // per block instead of once per tile (measured, 512^3 cn2 on 4 GPUs: full grid 27.4 ms/step, persistent
+            // 22.6, full grid without the fence 22.2)
+            first[i].max_ctas = (c.p2p_ctas_per_sm >= 0 ? c.p2p_ctas_per_sm : 2) * c.num_sms;
             run_sweep(c, first[i]);
             ++c.tr.n_alltoall;
             c.tr.bytes_sent += (double)c.nxl * c.nyl * c.pz * 8.0 * (c.nranks - 1);
