@@ -206,7 +206,8 @@ def check_reference_z_known_answers(lib, nz_deriv):
         d, exact = deriv_via_sine_series(nz, lambda a: lib.fftsine(col(a))[3, 5], lambda v: lib.fftcosine(col(v))[3, 5])
         assert np.max(np.abs(d - exact)) < 3.01 / nz
         want, _ = deriv_via_sine_series(nz, lambda a: np.concatenate(([0.0], O.dst(a[1:].copy(), nz))), lambda v: O.dct(v, nz))
-        assert np.max(np.abs(d - want)) < 1e-12
+        # round-off of the two transforms is amplified by the largest wavenumber pi nz (deriv1d.f90:17-22)
+        assert np.max(np.abs(d - want)) < 1e-12 * math.pi * nz
     finally:
         lib.finalise()
 
