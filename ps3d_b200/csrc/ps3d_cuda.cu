@@ -110,6 +110,7 @@ struct Ctx {
     double last_advance_ms = 0.0;
     double last_diag[16] = {};           // diagnostics of the last adapt (advance.f90: set_netcdf_field_diagnostic)
     bool have_diag = false;
+    bool svorts_stale = false;           // the last source call carried the cn2 update and did not store svorts
 
     DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[9];
     Transport tr;
@@ -990,6 +991,7 @@ static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0) {
     for (int i = 0; i < 3; ++i) { a.svor[i] = st.svor[i]; a.vortsm[i] = st.wa[i]; }
     a.f2d = st.f2d; a.filtz = st.filtz; a.vd = st.vd;
     launch_src(c, a);
+    c.svorts_stale = (upd >= 0);
     if (upd >= 0) vor_mean(c, 1);
 }
 
@@ -1404,6 +1406,9 @@ int ps3d_cuda_download(int field_id, int comp, double* host) {
     bool spectral = false;
     DevBuf<double>* f = field_by_id(c, field_id, spectral);
     if (!f || comp < 0 || comp > 2) fail(PS3D_ERR_BAD_ARGUMENT, "bad field id %d / component %d", field_id, comp);
+    // the time loop does not keep svorts when the update rides on the source kernel: re-evaluate the last tendency
+    // from vel, vor (still those of the last source call) when somebody asks for it
+    if (field_id == PS3D_F_SVORTS && c.svorts_stale) do_source(c);
     to_host(c, f[comp].p, host, spectral);
     PS_API_END
 }
