@@ -126,6 +126,14 @@ enum { PS3D_NC_KE = 0, PS3D_NC_EN, PS3D_NC_OMAX, PS3D_NC_ORMS, PS3D_NC_OCHAR, PS
        PS3D_NC_ROMAX, PS3D_NC_COUNT };
 int ps3d_cuda_field_stats(double out[40]);
 
+/* Kinetic-energy spectrum of the current velocity field, the computation of the post-processing program genspec
+ * (genspec.f90:55-127): fftxyp2s of u, v, w, cosine transform of u, v and sine transform of w in z, shells
+ * m = int(nint(|k|) / dk) with dk = kmax / sqrt((nx/2)^2 + (ny/2)^2 + nz^2), spec(m) = sum |u_k|^2 * 4/3 pi dk^3
+ * ((m+1)^3 - m^3) / num(m), normalised so that sum(spec) dk = kinetic energy.  nbins = kmax + 1 values are written
+ * to spec and num (bins with num = 0 are left 0 where the reference prints a warning); with spec == NULL only
+ * *nbins and *dk are returned.  Needs vor2vel for the current state. */
+int ps3d_cuda_genspec(int nmax, double* spec, double* num, int* nbins, double* dk);
+
 /* ---- multi-rank transport ----
  * Slab decomposition over `nranks` GPUs of one box: physical fields are split in x (rank r owns planes
  * r*nx/P .. (r+1)*nx/P - 1), spectral fields in ky (rank r owns rows r*ny/P .. of the paired order

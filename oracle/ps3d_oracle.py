@@ -603,6 +603,33 @@ class PS3D:
             usdelrms=math.sqrt(np.sum(delta[..., nz] ** 2) / nxy),
             rgmax=d["rmv"], rbfmax=0.0, rimin=0.0, romin=float(romin), romax=float(romax))
 
+    def genspec(self):
+        """genspec.f90:55-127: kinetic-energy spectrum of `vel` (needs vor2vel).  Returns (spec, num, dk);
+        empty bins keep spec = 0 (the reference prints a warning, :118-119).  `kmag` as intended by :74-81 (the
+        reference allocates it for a single x index, :34)."""
+        nz = self.nz
+        ke = self.get_kinetic_energy()
+        s = [self.fftxyp2s(self.vel[nc]) for nc in range(3)]
+        s[0] = dct(s[0], nz)
+        s[1] = dct(s[1], nz)
+        w = np.array(s[2])
+        w[..., 1:] = dst(np.ascontiguousarray(w[..., 1:]), nz)
+        s[2] = w
+        kmag = np.floor(np.sqrt(self.rkx[:, None, None] ** 2 + self.rky[None, :, None] ** 2
+                                + self.rkz[None, None, :] ** 2) + 0.5)                     # nint
+        kmax = int(kmag.max())
+        dk = kmax / math.sqrt((0.5 * self.nx) ** 2 + (0.5 * self.ny) ** 2 + float(nz) ** 2)
+        m = (kmag * (1.0 / dk)).astype(np.int64)
+        e = s[0] ** 2 + s[1] ** 2 + s[2] ** 2
+        spec = np.bincount(m.ravel(), weights=e.ravel(), minlength=kmax + 1).astype(np.float64)
+        num = np.bincount(m.ravel(), minlength=kmax + 1).astype(np.float64)
+        prefactor = 4.0 / 3.0 * math.pi * dk ** 3
+        mm = np.arange(kmax + 1, dtype=np.float64)
+        ok = num > 0
+        spec[ok] = spec[ok] * prefactor * ((mm[ok] + 1) ** 3 - mm[ok] ** 3) / num[ok]
+        spec *= ke / np.sum(spec * dk)
+        return spec, num, dk
+
     # ---- fields_derived.f90:67-182 ----
     def pressure(self, dudx, dudy, dvdy, dwdx, dwdy):
         vor = self.vor

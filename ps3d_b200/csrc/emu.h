@@ -92,6 +92,12 @@ template <class T> static inline T __ldcs(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline void __threadfence_system() {}
+static inline double atomicAdd(double* p, double v) {
+    double old;
+#pragma omp atomic capture
+    { old = *p; *p += v; }
+    return old;
+}
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 
 #ifdef PS3D_EMU_IMPL

@@ -255,6 +255,28 @@ __global__ void k_field_stats(FieldPtrs f, const double* __restrict__ delta, lon
     }
 }
 
+// ---- kinetic-energy spectrum (genspec.f90:64-106) ---------------------------------------------------------
+// u, v (cosine series in z) and w (sine series) fully spectral; bin m = int(nint(|k|) / dk) collects
+// |u|^2 + |v|^2 + |w|^2 and a count.  k2l2 is the [nx/2+1][nyl] table of rkx^2 + rky^2 (rkx(kx) = rkx(nx-kx)).
+__global__ void k_spec_bin(const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                           const double* __restrict__ k2l2, const double* __restrict__ rkz, int nx, int nyl, int nz,
+                           int pz, double dki, double* spec, double* num) {
+    const long long n = (long long)nx * nyl * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        if (z > nz) continue;
+        const long long col = i / pz;
+        const int kx = (int)(col / nyl), kyl = (int)(col - (long long)kx * nyl);
+        const int b = (kx <= nx - kx) ? kx : nx - kx;
+        const double rk = __ldg(&rkz[z]);
+        const double kmag = floor(sqrt(__ldg(&k2l2[(long long)b * nyl + kyl]) + rk * rk) + 0.5);    // nint (:79)
+        const int m = (int)(kmag * dki);                                                            // :100
+        const double a = u[i], bb = v[i], c = w[i];
+        atomicAdd(&spec[m], a * a + bb * bb + c * c);
+        atomicAdd(&num[m], 1.0);
+    }
+}
+
 // get_char_vorticity (field_diagnostics.f90:501-545): sums over cell-averaged |omega|
 __global__ void k_char_vorticity(FieldPtrs f, long long ncol, int nz, int pz, double vortrms,
                                  double* __restrict__ partial) {

@@ -1502,6 +1502,56 @@ int ps3d_cuda_field_stats(double out[40]) {
     PS_API_END
 }
 
+int ps3d_cuda_genspec(int nmax, double* spec, double* num, int* nbins, double* dk_out) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!nbins || !dk_out) fail(PS3D_ERR_BAD_ARGUMENT, "nbins / dk is null");
+    // kmax = maxval(nint(|k|)) (genspec.f90:74-84): |k| is largest at the Nyquist wavenumbers
+    const double kx = c.h_rkx[c.nx / 2], ky = c.h_rky[c.ny / 2], kz = c.h_rkz[c.nz];
+    const int kmax = (int)std::floor(std::sqrt(kx * kx + ky * ky + kz * kz) + 0.5);
+    const double dk = (double)kmax / std::sqrt(0.25 * (double)c.nx * c.nx + 0.25 * (double)c.ny * c.ny + (double)c.nz * c.nz);   // :97
+    *nbins = kmax + 1; *dk_out = dk;
+    if (!spec) return PS3D_OK;
+    if (!num || nmax < kmax + 1) fail(PS3D_ERR_BAD_ARGUMENT, "genspec needs room for %d bins", kmax + 1);
+    // kinetic energy of the current state (:62)
+    field_reduce(c);
+    ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    double r1[RQ_N];
+    for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
+    allreduce_host(c, r1, RQ_N, RQ_OPMASK);
+    const double ke = 0.5 * r1[RQ_SUMU2] / (double)c.ncell;
+    // fully spectral velocity (:64-73) -> W[0..2]
+    for (int i = 0; i < 3; ++i) {
+        fft2d_fwd(c, c.vel[i].p, c.W[i].p);
+        launch_zop(c, i < 2 ? ZOP_COSINE : ZOP_SINE, c.W[i].p, c.W[i].p);
+    }
+    DevBuf<double> bins;
+    bins.alloc((size_t)2 * (kmax + 1));           // zero-initialised: spec, num
+    PS_LAUNCH((k_spec_bin), dim3(stream_blocks((size_t)c.nx * c.nyl * c.pz)), dim3(256), 0, c.stream,
+              (const double*)c.W[0].p, (const double*)c.W[1].p, (const double*)c.W[2].p, (const double*)c.k2l2.p,
+              (const double*)c.rkz.p, c.nx, c.nyl, c.nz, c.pz, 1.0 / dk, bins.p, bins.p + (kmax + 1));
+    ++c.launches;
+    std::vector<double> h((size_t)2 * (kmax + 1));
+    ps_d2h(h.data(), bins.p, h.size() * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    bins.release();
+    for (size_t o = 0; o < h.size(); o += 32) allreduce_host(c, h.data() + o, (int)std::min<size_t>(32, h.size() - o), 0u);   // :108-109
+    const double pi = std::acos(-1.0);
+    const double prefactor = 4.0 / 3.0 * pi * dk * dk * dk;                                     // :111
+    double total = 0.0;
+    for (int m = 0; m <= kmax; ++m) {
+        const double cnt = h[(size_t)kmax + 1 + m];
+        num[m] = cnt;
+        const double m0 = (double)m, m1 = (double)(m + 1);
+        spec[m] = (cnt > 0.0) ? h[m] * prefactor * (m1 * m1 * m1 - m0 * m0 * m0) / cnt : h[m];  // :114-120
+        total += spec[m] * dk;
+    }
+    const double snorm = ke / total;                                                            // :123
+    for (int m = 0; m <= kmax; ++m) spec[m] *= snorm;
+    PS_API_END
+}
+
 int ps3d_cuda_set_transport(ps3d_alltoall_fn alltoall, ps3d_allreduce_fn allreduce, void* user) {
     PS_API_BEGIN
     Ctx& c = ctx();

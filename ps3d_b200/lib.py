@@ -31,6 +31,7 @@ _SIGNATURES = {
     "ps3d_cuda_init_diffusion": [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _dp],
     "ps3d_cuda_finalise": [],
     "ps3d_cuda_field_stats": [_dp],
+    "ps3d_cuda_genspec": [C.c_int, _dp, _dp, C.POINTER(C.c_int), _dp],
     "ps3d_cuda_fftxyp2s": [_dp, _dp],
     "ps3d_cuda_fftxys2p": [_dp, _dp],
     "ps3d_cuda_fftsine": [_dp],
@@ -228,6 +229,15 @@ class PS3DLib:
         out = np.zeros(len(NC_NAMES))
         self._call("ps3d_cuda_field_stats", _ptr(out))
         return dict(zip(NC_NAMES, out.tolist()))
+
+    def genspec(self):
+        """Kinetic-energy spectrum of the current velocity (genspec.f90): returns (spec, num, dk)."""
+        nb = C.c_int(0)
+        dk = np.zeros(1)
+        self._call("ps3d_cuda_genspec", 0, None, None, C.byref(nb), _ptr(dk))
+        spec, num = np.zeros(nb.value), np.zeros(nb.value)
+        self._call("ps3d_cuda_genspec", nb.value, _ptr(spec), _ptr(num), C.byref(nb), _ptr(dk))
+        return spec, num, float(dk[0])
 
     def kernel_launches(self): return int(self.dll.ps3d_cuda_kernel_launches())
     def last_advance_ms(self): return float(self.dll.ps3d_cuda_last_advance_ms())

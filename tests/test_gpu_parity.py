@@ -198,6 +198,20 @@ def test_reference_z_known_answers(lib):
     check_reference_z_known_answers(lib, 1024)
 
 
+def test_genspec_64(lib):
+    """the kinetic-energy spectrum of genspec.f90 as a device reduction."""
+    from test_emu_kernels import check_genspec
+    s = open_grid(lib, 64, 64, 64, -0.5 * PI * np.ones(3), PI * np.ones(3))
+    try:
+        vor = np.random.default_rng(9).uniform(-1, 1, (3, 64, 64, 65))
+        s.set_vorticity(vor)
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        check_genspec(lib, s)
+    finally:
+        lib.finalise()
+
+
 def test_field_stats_64(lib):
     """the 40 scalars of the field-statistics file (field_diagnostics_netcdf.f90:257-439)."""
     from test_emu_kernels import check_field_stats
