@@ -1,4 +1,4 @@
-"""Dev tool: small vor2vel + source + one cn2 step per nz template, meant to run under
+"""Test harness (dev): small vor2vel + source + one cn2 step per nz template, meant to run under
 `compute-sanitizer --tool racecheck` (shared-memory hazards of the in-place column transforms) and
 `--tool memcheck`; checks the result against the oracle as well."""
 import math

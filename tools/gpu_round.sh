@@ -7,7 +7,7 @@ mkdir -p $o
 timeout 600 python -m pytest tests -m gpu -x -q > $o/${tag}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $o/${tag}_pytest.log
 tail -3 $o/${tag}_pytest.log
 if [ -n "$RACE" ]; then
-  timeout 400 compute-sanitizer --tool racecheck --print-limit 20 python tools/race_small.py 8x8x512 8x8x64 16x16x16 > $o/${tag}_racecheck.log 2>&1; echo "racecheck exit $?"
+  timeout 400 compute-sanitizer --tool racecheck --print-limit 20 python tests/race_small.py 8x8x512 8x8x64 16x16x16 > $o/${tag}_racecheck.log 2>&1; echo "racecheck exit $?"
   tail -4 $o/${tag}_racecheck.log
 fi
 for v in $VARIANTS; do
