@@ -62,8 +62,8 @@ const char* ps3d_cuda_last_error(void);
  * GPUs of one box; nccl_id: 128-byte ncclUniqueId shared by all ranks (NULL
  * when nranks == 1).
  * Grid sizes: powers of two in 8..1024 per axis (tuned kernels, any nranks dividing nx and ny/2); other even
- * lengths 2^a 3^b 5^c -- what factorisen accepts, stafft.f90:128-187 -- with nx, ny <= 896, nz <= 1200 on one
- * rank (coverage kernels); anything else returns PS3D_ERR_UNSUPPORTED_SIZE. */
+ * lengths 2^a 3^b 5^c -- what factorisen accepts, stafft.f90:128-187 -- with nx, ny <= 896, nz <= 1200
+ * (coverage kernels); anything else returns PS3D_ERR_UNSUPPORTED_SIZE. */
 int ps3d_cuda_init(int nx, int ny, int nz, const double lower[3], const double extent[3],
                    int rank, int nranks, const void* nccl_id);
 /* init_inversion (inversion_utils.f90:222) */

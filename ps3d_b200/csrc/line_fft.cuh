@@ -42,6 +42,7 @@ struct RowMap {
     long long stride;
     long long nb;          // doubles per block (nxl * nyl * pz)
     int paired, n, logblk, self;
+    int blk;               // rows per block (= 2^logblk when that is a power of two; the mixed-radix kernels divide by it)
 };
 __device__ __forceinline__ long long row_off(const RowMap& m, int k, int& d) {
     const int h = m.n >> 1;
@@ -55,6 +56,19 @@ __device__ __forceinline__ long long row_off(const RowMap& m, int k, int& d) {
     return (long long)blk * m.nb + (long long)kl * m.stride;
 }
 __device__ __forceinline__ long long row_off(const RowMap& m, int k) { int d; return row_off(m, k, d); }
+// the same map with a block size that need not be a power of two (line_gen.cuh)
+__device__ __forceinline__ long long row_off_div(const RowMap& m, int k, int& d) {
+    const int h = m.n >> 1;
+    int kq = (k < h) ? 2 * k : 2 * (m.n - k) + 1;
+    kq = (k == 0) ? 0 : kq;
+    kq = (k == h) ? 1 : kq;
+    const int kp = m.paired ? kq : k;
+    d = kp / m.blk;
+    const int kl = kp - d * m.blk;
+    const int blk = (m.self < 0) ? d : m.self;
+    return (long long)blk * m.nb + (long long)kl * m.stride;
+}
+__device__ __forceinline__ long long row_off_div(const RowMap& m, int k) { int d; return row_off_div(m, k, d); }
 
 struct LineArgs {
     const double* in0;        // PLAIN/DIFF: the field.  CROSS: a
@@ -100,6 +114,11 @@ __device__ __forceinline__ void st2f(int fin, double* p, double x, double y) {
 __device__ __forceinline__ double* row_dst(const LineArgs& a, int k) {
     int d;
     const long long off = row_off(a.out_map, k, d);
+    return a.outp[d & 7] + off;
+}
+__device__ __forceinline__ double* row_dst_div(const LineArgs& a, int k) {
+    int d;
+    const long long off = row_off_div(a.out_map, k, d);
     return a.outp[d & 7] + off;
 }
 

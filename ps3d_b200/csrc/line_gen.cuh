@@ -2,7 +2,7 @@
 // the same two-real-lines-per-complex-FFT packing, prologues (diffx/diffy, cross products) and output packing as
 // line_fft.cuh (reference sta3dfft.f90:136-260, 304-377; stafft.f90:55-58), with the mixed-radix transform of
 // gen_fft.cuh looping through shared memory instead of the register-blocked radix-8 passes.  Coverage path for
-// the grids the reference's factorisen accepts; one rank only.
+// the grids the reference's factorisen accepts (slab blocks of any size: the row maps divide instead of shifting).
 #pragma once
 
 #include "gen_fft.cuh"
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_line_gen_fwd(LineArgs a, GenLin
         const long long ibase = (long long)o * a.in_os + (zc - a.in_zc0) * LINE_ZC;
         for (int w = threadIdx.x; w < LINE_NF * n; w += blockDim.x) {
             const int f = w & (LINE_NF - 1), row = w / LINE_NF;
-            const long long off = ibase + 2 * f + row_off(a.in_map, row);
+            const long long off = ibase + 2 * f + row_off_div(a.in_map, row);
             double2 v;
             if (PRO == PRO_CROSS) {
                 const double2 x0 = ld2(a.in0 + off), x1 = ld2(a.in1 + off), x2 = ld2(a.in2 + off), x3 = ld2(a.in3 + off);
@@ -51,19 +51,20 @@ __global__ void __launch_bounds__(GEN_THREADS) k_line_gen_fwd(LineArgs a, GenLin
             const long long ob = obase + 2 * f;
             if (k == 0) {
                 const double2 c0 = C[f];
-                st2f(a.final_store, row_dst(a, 0) + ob, c0.x * sc, c0.y * sc);
+                st2f(a.final_store, row_dst_div(a, 0) + ob, c0.x * sc, c0.y * sc);
             } else if (k == h) {
                 const double2 ch = C[h * LINE_NF + f];
-                st2f(a.final_store, row_dst(a, h) + ob, ch.x * sc, ch.y * sc);
+                st2f(a.final_store, row_dst_div(a, h) + ob, ch.x * sc, ch.y * sc);
             } else {
                 const double2 ck = C[k * LINE_NF + f], cm = C[(n - k) * LINE_NF + f];
                 // A_k = (C_k + conj C_{n-k})/2, B_k = (C_k - conj C_{n-k})/(2i)
-                st2f(a.final_store, row_dst(a, k) + ob, (ck.x + cm.x) * hs, (ck.y + cm.y) * hs);       // Re A, Re B
-                st2f(a.final_store, row_dst(a, n - k) + ob, (ck.y - cm.y) * hs, (cm.x - ck.x) * hs);   // Im A, Im B
+                st2f(a.final_store, row_dst_div(a, k) + ob, (ck.x + cm.x) * hs, (ck.y + cm.y) * hs);       // Re A, Re B
+                st2f(a.final_store, row_dst_div(a, n - k) + ob, (ck.y - cm.y) * hs, (cm.x - ck.x) * hs);   // Im A, Im B
             }
         }
         __syncthreads();          // the buffers are reused by the next tile
     }
+    if (a.out_map.self >= 0 && a.scatter_fence) __threadfence_system();     // peer-memory scatter (see line_fft.cuh)
 }
 
 template <int PRO>
@@ -81,11 +82,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k_line_gen_inv(LineArgs a, GenLin
             const long long ib = ibase + 2 * f;
             if (k == 0 || k == h) {
                 // real DC / Nyquist terms of both lines; d/dx: kappa = 0 there (sta3dfft.f90:321-335)
-                double2 c = ld2(a.in0 + ib + row_off(a.in_map, k));
+                double2 c = ld2(a.in0 + ib + row_off_div(a.in_map, k));
                 if (PRO == PRO_DIFF) c = make_double2(0.0, 0.0);
                 A[k * LINE_NF + f] = c;
             } else {
-                const double2 xa = ld2(a.in0 + ib + row_off(a.in_map, k)), xb = ld2(a.in0 + ib + row_off(a.in_map, n - k));
+                const double2 xa = ld2(a.in0 + ib + row_off_div(a.in_map, k)), xb = ld2(a.in0 + ib + row_off_div(a.in_map, n - k));
                 double Ar = xa.x, Ai = xb.x, Br = xa.y, Bi = xb.y;
                 if (PRO == PRO_DIFF) {
                     // d/dx: X_k -> i kappa X_k (sta3dfft.f90:325-329)
@@ -105,10 +106,11 @@ __global__ void __launch_bounds__(GEN_THREADS) k_line_gen_inv(LineArgs a, GenLin
         for (int w = threadIdx.x; w < LINE_NF * n; w += blockDim.x) {
             const int f = w & (LINE_NF - 1), row = w / LINE_NF;
             const double2 c = C[w];
-            st2f(a.final_store, row_dst(a, row) + obase + 2 * f, c.x * sc, c.y * sc);
+            st2f(a.final_store, row_dst_div(a, row) + obase + 2 * f, c.x * sc, c.y * sc);
         }
         __syncthreads();
     }
+    if (a.out_map.self >= 0 && a.scatter_fence) __threadfence_system();
 }
 
 }  // namespace ps3d

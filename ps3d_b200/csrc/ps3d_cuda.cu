@@ -206,11 +206,11 @@ static void launch_line_n(Ctx& c, bool inv, int pro, const LineArgs& a, int ntil
 }
 
 // line lengths that are not a power of two (coverage path, one rank)
-static void launch_line_gen(Ctx& c, int axis, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream) {
+static void launch_line_gen(Ctx& c, int axis, bool inv, int pro, const LineArgs& a, int ntiles, ps_stream_t stream, int max_ctas) {
     GenLine gl;
     gl.plan = c.plan[axis]; gl.tw = c.gtw[axis].p;
     const size_t sm = line_gen_smem_bytes(gl.plan.n);
-    const dim3 grid(std::min(ntiles, 4 * c.num_sms)), block(GEN_THREADS);
+    const dim3 grid(std::min(ntiles, max_ctas > 0 ? max_ctas : 4 * c.num_sms)), block(GEN_THREADS);
     if (!inv) {
         if (pro == PRO_CROSS) { allow_smem(k_line_gen_fwd<PRO_CROSS>, sm); PS_LAUNCH((k_line_gen_fwd<PRO_CROSS>), grid, block, sm, stream, a, gl); }
         else { allow_smem(k_line_gen_fwd<PRO_PLAIN>, sm); PS_LAUNCH((k_line_gen_fwd<PRO_PLAIN>), grid, block, sm, stream, a, gl); }
@@ -265,24 +265,24 @@ static void run_sweep(Ctx& c, const Sweep& s) {
         // physical side [xl][y][pz]; spectral side: P blocks [d][xl][kyl][pz] (== [kx][kyl][pz] after the exchange)
         a.in_os = (s.inv ? (long long)c.nyl : (long long)c.ny) * ipz;
         a.out_os = (s.inv ? (long long)c.ny : (long long)c.nyl) * opz;
-        const RowMap phys_in{ipz, 0, 0, n, 30, -1}, phys_out{opz, 0, 0, n, 30, -1};
-        const RowMap spec_in{ipz, nbi, 1, n, lognyl, -1};
-        const RowMap spec_out{opz, nbo, 1, n, lognyl, self};
+        const RowMap phys_in{ipz, 0, 0, n, 30, -1, 1 << 30}, phys_out{opz, 0, 0, n, 30, -1, 1 << 30};
+        const RowMap spec_in{ipz, nbi, 1, n, lognyl, -1, c.nyl};
+        const RowMap spec_out{opz, nbo, 1, n, lognyl, self, c.nyl};
         a.in_map = s.inv ? spec_in : phys_in;
         a.out_map = s.inv ? phys_out : spec_out;
         a.kdiff = c.kyline.p;
     } else {
         n = c.nx; nouter = c.nyl;
         a.in_os = ipz; a.out_os = opz;
-        const RowMap xin{(long long)c.nyl * ipz, 0, 0, n, 30, -1};
-        const RowMap xout{(long long)c.nyl * opz, nbo, 0, n, lognxl, self};      // block d = x / nxl
+        const RowMap xin{(long long)c.nyl * ipz, 0, 0, n, 30, -1, 1 << 30};
+        const RowMap xout{(long long)c.nyl * opz, nbo, 0, n, lognxl, self, c.nxl};      // block d = x / nxl
         a.in_map = xin; a.out_map = xout;
         a.kdiff = c.kxl.p;
     }
     a.scale = 1.0 / std::sqrt((double)n);
     a.twscale = c.ntw / n;
     a.ntiles = nouter * a.nzc;
-    if (c.gen[s.axis]) launch_line_gen(c, s.axis, s.inv, s.pro, a, a.ntiles, c.stream);
+    if (c.gen[s.axis]) launch_line_gen(c, s.axis, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
     else launch_line(c, n, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
 }
 
@@ -631,7 +631,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     if (!lower || !extent) fail(PS3D_ERR_BAD_ARGUMENT, "null lower/extent");
     // Powers of two in 8..1024 run through the register-blocked kernels; other even lengths with prime factors
     // 2, 3, 5 only (the lengths factorisen accepts, stafft.f90:128-187) through the mixed-radix coverage kernels
-    // (one rank, shared-memory limits: nx, ny <= 896, nz <= 1200).
+    // (shared-memory limits: nx, ny <= 896, nz <= 1200).
     bool gen_axis[3];
     GenPlan gplan[3];
     {
@@ -645,9 +645,6 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
                 fail(PS3D_ERR_UNSUPPORTED_SIZE,
                      "grid %dx%dx%d: supported are powers of two in 8..1024 and even lengths 2^a 3^b 5^c (nx, ny <= 896, "
                      "nz <= 1200)", nx, ny, nz);
-            if (nranks > 1)
-                fail(PS3D_ERR_UNSUPPORTED_SIZE, "grid %dx%dx%d: lengths that are not a power of two run on one rank only",
-                     nx, ny, nz);
         }
     }
     if (nranks < 1 || rank < 0 || rank >= nranks || nx % nranks || (ny / 2) % nranks)
