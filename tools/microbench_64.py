@@ -29,7 +29,7 @@ alg = [16, 16, 16, 16, 8 * 16, 5 * 16]
 for w, name in enumerate(names):
     lib.time_kernel(w, 5)
     ms = lib.time_kernel(w, 50)
-    out["resident_kernels"][name] = {"ms": ms, "alg_GBs": alg[w] * N / (ms * 1e-3) / 1e9}
+    out["resident_kernels"][name] = {"ms": ms, "alg_GBs": (alg[w] * N / (ms * 1e-3) / 1e9) if ms > 0 else None}
 
 
 def wall(fn, reps=20):
