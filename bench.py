@@ -74,7 +74,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(n, steps, warmup):
+def cpu_reference_run(n, steps, warmup, stepper="cn2"):
     """Reference algorithm on the host cores.  Preferred: oracle/ps3d_ref.cpp, the C++/OpenMP restatement with the
     reference's sweep structure (four transposes per 2-D FFT, reversed copies in diffx/diffy, stored N-sized tables,
     literal combine/decompose pairs in the stepper), all cores; fallback: the NumPy/SciPy oracle.
@@ -91,10 +91,10 @@ def cpu_reference_run(n, steps, warmup):
     if r is not None:
         r.set_vorticity(host.beltrami_vorticity(n, n, n, lower, extent))
         for _ in range(warmup):
-            r.advance()
+            r.advance(stepper=stepper)
         t0 = time.perf_counter()
         for _ in range(steps):
-            r.advance()
+            r.advance(stepper=stepper)
         dt = time.perf_counter() - t0
         threads = r.threads
         r.close()
@@ -104,10 +104,10 @@ def cpu_reference_run(n, steps, warmup):
     s = O.beltrami_setup(n)
     t = 0.0
     for _ in range(warmup):
-        t, _ = s.advance(t, 100.0, "cn2", literal=True)
+        t, _ = s.advance(t, 100.0, stepper, literal=True)
     t0 = time.perf_counter()
     for _ in range(steps):
-        t, _ = s.advance(t, 100.0, "cn2", literal=True)
+        t, _ = s.advance(t, 100.0, stepper, literal=True)
     dt = time.perf_counter() - t0
     return n ** 3 * steps / dt, dt / steps, "NumPy/SciPy port of the reference algorithm (literal steppers), scipy.fft on all cores"
 
@@ -117,14 +117,14 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.ref_n
-    val, sec, how = cpu_reference_run(n, args.steps, args.warmup)
+    val, sec, how = cpu_reference_run(n, args.steps, args.warmup, args.stepper)
     cores = os.cpu_count()
-    sample = f"Beltrami {n}^3 cn2 steps (bounded sample of the 512^3 workload), {how}"
+    sample = f"Beltrami {n}^3 {args.stepper} steps (bounded sample of the {args.n}^3 workload), {how}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Beltrami {args.n}^3 cn2 (examples/beltrami_512.config)", "sample": sample},
+        "config": {"workload": f"Beltrami {args.n}^3 {args.stepper} (examples/beltrami_512.config)", "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -279,9 +279,9 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        val, sec, how = cpu_reference_run(args.ref_n, 3, 1)
+        val, sec, how = cpu_reference_run(args.ref_n, 3, 1, args.stepper)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"Beltrami {args.ref_n}^3 cn2, 3 steps after 1 warm-up, {how}"}
+                               "sample": f"Beltrami {args.ref_n}^3 {args.stepper}, 3 steps after 1 warm-up, {how}"}
     solver.close()
     if rank == 0:
         print(json.dumps(out))

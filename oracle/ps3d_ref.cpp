@@ -542,7 +542,7 @@ static double max_abs_eig(double s11, double s12, double s13, double s22, double
 }
 
 // ---- advance.f90:109-410 adapt (pretype 'vorch') ----------------------------------------------------------------
-static double adapt(Ref& r, double t, double t_limit, double alpha) {
+static double adapt(Ref& r, double t, double t_limit, double alpha, int stepper) {
     const size_t N = r.N;
     const int nz = r.nz, nzp = r.nzp;
     const double small = 1.0e-12, cflmax = 0.8;
@@ -579,9 +579,14 @@ static double adapt(Ref& r, double t, double t_limit, double alpha) {
     const double dtcfl = cflmax * std::min(r.dx[0] / (umax + small), std::min(r.dx[1] / (vmax + small), r.dx[2] / (wmax + small)));
     const double bfmax = 0.0;
     const double dt = std::min(std::min(alpha / (gg + small), alpha / (bfmax + small)), std::min(dtcfl, t_limit - t));
-    // cn2_set_diffusion (cn2.f90:40-79) with the 'vorch' prefactor
-    const double dfac = (r.nnu == 1) ? dt : r.vorch * dt;
-    for (size_t c = 0; c < r.NC; ++c) r.vdiss[c] = 1.0 / (1.0 + dfac * r.vhdis[c]);
+    if (stepper == 0) {
+        // cn2_set_diffusion (cn2.f90:40-79) with the 'vorch' prefactor
+        const double dfac = (r.nnu == 1) ? dt : r.vorch * dt;
+        for (size_t c = 0; c < r.NC; ++c) r.vdiss[c] = 1.0 / (1.0 + dfac * r.vhdis[c]);
+    } else {
+        // impl_rk4_set_diffusion (impl_rk4.f90:37-55)
+        for (size_t c = 0; c < r.NC; ++c) r.vdiss[c] = 0.5 * r.vorch * dt * r.vhdis[c];
+    }
     return dt;
 }
 
@@ -600,10 +605,60 @@ static void cn2_update(Ref& r, double dt2) {
     }
     adjust_vorticity_mean(r);
 }
-static double advance(Ref& r, double* t, double t_limit, double alpha) {      // advance.f90:77-104
+// impl_rk4.f90:212-364: q <- decompose(fac(ky,kx) * combine(q)), literally
+static void cmd(const Ref& r, vec& q, const vec& fac) {
+    combine_semi_spectral(r, q.data());
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)r.N; ++i) q[i] *= fac[i / r.nzp];
+    decompose_semi_spectral(r, q.data());
+}
+static void rk4_step(Ref& r, double* t, double dt) {                           // impl_rk4.f90:76-207
+    const double dt2 = 0.5 * dt, dt3 = dt / 3.0, dt6 = dt / 6.0;
+    const size_t N = r.N;
+    vec epq(r.NC), emq(r.NC), q(N);
+    for (size_t c = 0; c < r.NC; ++c) { const double e = std::exp(r.vdiss[c]); emq[c] = 1.0 / e; epq[c] = e * r.filt[c * r.nzp]; }
+    vec svori[3], svorf[3];
+    for (int nc = 0; nc < 3; ++nc) {                                           // substep one
+        svori[nc] = r.svor[nc]; svorf[nc].resize(N);
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)N; ++i) {
+            r.svorts[nc][i] *= r.filt[(i / r.nzp) * r.nzp];
+            q[i] = svori[nc][i] + dt2 * r.svorts[nc][i];
+            svorf[nc][i] = svori[nc][i] + dt6 * r.svorts[nc][i];
+        }
+        cmd(r, q, emq);
+        r.svor[nc] = q;
+    }
+    vor2vel(r); vorticity_tendency(r);
+    *t += dt2;
+    auto substep = [&](double c1, double c2, bool last) {
+        for (int nc = 0; nc < 3; ++nc) {
+            cmd(r, r.svorts[nc], epq);
+            const vec& base = last ? svorf[nc] : svori[nc];
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < (long long)N; ++i) {
+                q[i] = base[i] + c1 * r.svorts[nc][i];
+                if (!last) svorf[nc][i] += c2 * r.svorts[nc][i];
+            }
+            cmd(r, q, emq);
+            r.svor[nc] = q;
+        }
+    };
+    substep(dt2, dt3, false);                                                  // substep two
+    vor2vel(r); vorticity_tendency(r);
+    *t += dt2;
+    for (size_t c = 0; c < r.NC; ++c) emq[c] *= emq[c];
+    substep(dt, dt3, false);                                                   // substep three
+    vor2vel(r); vorticity_tendency(r);
+    for (size_t c = 0; c < r.NC; ++c) epq[c] *= epq[c];
+    substep(dt6, 0.0, true);                                                   // substep four
+    adjust_vorticity_mean(r);
+}
+static double advance(Ref& r, double* t, double t_limit, double alpha, int stepper) {      // advance.f90:77-104
     vor2vel(r);
-    const double dt = adapt(r, *t, t_limit, alpha);
+    const double dt = adapt(r, *t, t_limit, alpha, stepper);
     vorticity_tendency(r);
+    if (stepper != 0) { rk4_step(r, t, dt); return dt; }
     const double dt2 = 0.5 * dt;
     for (int nc = 0; nc < 3; ++nc)
 #pragma omp parallel for schedule(static)
@@ -661,7 +716,10 @@ void ps3d_ref_set_vorticity(void* h, const double* vor, int nnu, double prediss,
     for (size_t c = 0; c < r.NC; ++c) r.vhdis[c] = (nnu == 1) ? vis * r.k2l2[c] : vis * std::pow(r.k2l2[c], nnu);
     if (ke_en) { ke_en[0] = ke; ke_en[1] = en; }
 }
-double ps3d_ref_advance(void* h, double* t, double t_limit, double alpha) { return advance(*static_cast<Ref*>(h), t, t_limit, alpha); }
+// stepper: 0 cn2, 1 impl-diff-rk4
+double ps3d_ref_advance(void* h, double* t, double t_limit, double alpha, int stepper) {
+    return advance(*static_cast<Ref*>(h), t, t_limit, alpha, stepper);
+}
 
 // field: 0 svor, 1 vor, 2 vel, 3 svel, 4 svorts  -> out[3][nx][ny][nz+1]
 void ps3d_ref_get(void* h, int field, double* out) {

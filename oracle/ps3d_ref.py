@@ -19,7 +19,7 @@ def _p(a):
 
 
 class RefSolver:
-    """One-rank solver state of the restatement (power-of-two grids, cn2, pretype 'vorch', Kolmogorov scaling)."""
+    """One-rank solver state of the restatement (power-of-two grids, cn2 / impl-diff-rk4, pretype 'vorch', Kolmogorov scaling)."""
 
     def __init__(self, nx, ny, nz, lower, extent, filtering="Hou & Li", path=LIB_PATH):
         if not os.path.exists(path):
@@ -31,7 +31,7 @@ class RefSolver:
         d.ps3d_ref_destroy.argtypes = [C.c_void_p]
         d.ps3d_ref_set_vorticity.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, _dp]
         d.ps3d_ref_advance.restype = C.c_double
-        d.ps3d_ref_advance.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double]
+        d.ps3d_ref_advance.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, C.c_int]
         d.ps3d_ref_get.argtypes = [C.c_void_p, C.c_int, _dp]
         d.ps3d_ref_op.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         d.ps3d_ref_diag.argtypes = [C.c_void_p, _dp]
@@ -53,8 +53,8 @@ class RefSolver:
         self.dll.ps3d_ref_set_vorticity(self.h, _p(v), nnu, prediss, _p(out))
         return float(out[0]), float(out[1])
 
-    def advance(self, time_limit=100.0, alpha=0.1):
-        dt = self.dll.ps3d_ref_advance(self.h, _p(self.t), time_limit, alpha)
+    def advance(self, time_limit=100.0, alpha=0.1, stepper="cn2"):
+        dt = self.dll.ps3d_ref_advance(self.h, _p(self.t), time_limit, alpha, 0 if stepper == "cn2" else 1)
         return float(self.t[0]), float(dt)
 
     def get(self, name):

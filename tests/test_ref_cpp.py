@@ -16,8 +16,9 @@ def rel(a, b):
     return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
 
 
-@pytest.mark.parametrize("shape,filtering", [((16, 32, 8), "Hou & Li"), ((32, 16, 32), "2/3-rule")])
-def test_cpp_restatement_matches_numpy_oracle(shape, filtering):
+@pytest.mark.parametrize("shape,filtering,stepper", [((16, 32, 8), "Hou & Li", "cn2"), ((32, 16, 32), "2/3-rule", "cn2"),
+                                                     ((16, 16, 16), "Hou & Li", "impl-diff-rk4")])
+def test_cpp_restatement_matches_numpy_oracle(shape, filtering, stepper):
     G.build_ref()
     nx, ny, nz = shape
     lower = np.array([-0.5 * PI, 0.0, -1.0])
@@ -38,13 +39,14 @@ def test_cpp_restatement_matches_numpy_oracle(shape, filtering):
             assert rel(r.get(name), getattr(s, name)) < 1e-13, name
         t0 = 0.0
         for _ in range(2):
-            t, dt = r.advance()
-            t0, dt0 = s.advance(t0, 100.0, "cn2", literal=True)
+            t, dt = r.advance(stepper=stepper)
+            t0, dt0 = s.advance(t0, 100.0, stepper, literal=True)
             assert dt == pytest.approx(dt0, rel=1e-12) and t == pytest.approx(t0, rel=1e-12)
             assert r.diag()["vorch"] == pytest.approx(s.diag["vorch"], rel=1e-12)
             assert r.diag()["ggmax"] == pytest.approx(s.diag["ggmax"], rel=1e-12)
             assert rel(r.get("svor"), s.svor) < 1e-12
-            assert rel(r.get("svorts"), s.svorts) < 1e-11
+            if stepper == "cn2":
+                assert rel(r.get("svorts"), s.svorts) < 1e-11
     finally:
         r.close()
 
