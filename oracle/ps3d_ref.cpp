@@ -716,6 +716,7 @@ void ps3d_ref_set_vorticity(void* h, const double* vor, int nnu, double prediss,
     for (size_t c = 0; c < r.NC; ++c) r.vhdis[c] = (nnu == 1) ? vis * r.k2l2[c] : vis * std::pow(r.k2l2[c], nnu);
     if (ke_en) { ke_en[0] = ke; ke_en[1] = en; }
 }
+void ps3d_ref_vor2vel(void* h) { vor2vel(*static_cast<Ref*>(h)); }
 // stepper: 0 cn2, 1 impl-diff-rk4
 double ps3d_ref_advance(void* h, double* t, double t_limit, double alpha, int stepper) {
     return advance(*static_cast<Ref*>(h), t, t_limit, alpha, stepper);

@@ -33,6 +33,7 @@ class RefSolver:
         d.ps3d_ref_advance.restype = C.c_double
         d.ps3d_ref_advance.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, C.c_int]
         d.ps3d_ref_get.argtypes = [C.c_void_p, C.c_int, _dp]
+        d.ps3d_ref_vor2vel.argtypes = [C.c_void_p]
         d.ps3d_ref_op.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         d.ps3d_ref_diag.argtypes = [C.c_void_p, _dp]
         d.ps3d_ref_set_threads.argtypes = [C.c_int]
@@ -56,6 +57,9 @@ class RefSolver:
     def advance(self, time_limit=100.0, alpha=0.1, stepper="cn2"):
         dt = self.dll.ps3d_ref_advance(self.h, _p(self.t), time_limit, alpha, 0 if stepper == "cn2" else 1)
         return float(self.t[0]), float(dt)
+
+    def vor2vel(self):
+        self.dll.ps3d_ref_vor2vel(self.h)
 
     def get(self, name):
         out = np.empty((3,) + self.shape)
