@@ -55,12 +55,14 @@ enum { PS3D_D_VORTMAX = 0, PS3D_D_VORTRMS, PS3D_D_VORCH, PS3D_D_VORMEAN_X, PS3D_
        PS3D_D_BFMAX, PS3D_D_GGMAX, PS3D_D_UMAX, PS3D_D_VMAX, PS3D_D_WMAX, PS3D_D_USGGMAX, PS3D_D_LSGGMAX,
        PS3D_D_RMV, PS3D_D_DT, PS3D_D_PREFACTOR };
 
+#define PS3D_MAX_RANKS 8   /* one NVSwitch box: peer-memory tables are sized for it */
+
 const char* ps3d_cuda_last_error(void);
 
 /* mpi_layout_init (mpi_layout.f90:53) + update_parameters (parameters.f90:61) +
  * initialise_fft (sta3dfft.f90:53).  rank/nranks: slab decomposition over the
- * GPUs of one box; nccl_id: 128-byte ncclUniqueId shared by all ranks (NULL
- * when nranks == 1).
+ * GPUs of one box (nranks <= PS3D_MAX_RANKS, else PS3D_ERR_BAD_ARGUMENT); nccl_id:
+ * 128-byte ncclUniqueId shared by all ranks (NULL when nranks == 1).
  * Grid sizes: powers of two in 8..1024 per axis (tuned kernels, any nranks dividing nx and ny/2); other even
  * lengths 2^a 3^b 5^c -- what factorisen accepts, stafft.f90:128-187 -- with nx, ny <= 896, nz <= 1200
  * (coverage kernels); anything else returns PS3D_ERR_UNSUPPORTED_SIZE. */

@@ -621,10 +621,14 @@ class PS3D:
         dk = kmax / math.sqrt((0.5 * self.nx) ** 2 + (0.5 * self.ny) ** 2 + float(nz) ** 2)
         m = (kmag * (1.0 / dk)).astype(np.int64)
         e = s[0] ** 2 + s[1] ** 2 + s[2] ** 2
-        spec = np.bincount(m.ravel(), weights=e.ravel(), minlength=kmax + 1).astype(np.float64)
-        num = np.bincount(m.ravel(), minlength=kmax + 1).astype(np.float64)
+        # the reference allocates spec(0:kmax) (:86-87) but int(kmag / dk) exceeds kmax when dk < 1 (boxes larger
+        # than pi (2, 2, 1)): a latent out-of-bounds write there; bins here cover the largest reachable index
+        nb = max(kmax, int(kmax * (1.0 / dk))) + 1
+        spec = np.bincount(m.ravel(), weights=e.ravel(), minlength=nb).astype(np.float64)
+        num = np.bincount(m.ravel(), minlength=nb).astype(np.float64)
+        assert len(spec) == nb
         prefactor = 4.0 / 3.0 * math.pi * dk ** 3
-        mm = np.arange(kmax + 1, dtype=np.float64)
+        mm = np.arange(nb, dtype=np.float64)
         ok = num > 0
         spec[ok] = spec[ok] * prefactor * ((mm[ok] + 1) ** 3 - mm[ok] ** 3) / num[ok]
         spec *= ke / np.sum(spec * dk)

@@ -260,7 +260,7 @@ __global__ void k_field_stats(FieldPtrs f, const double* __restrict__ delta, lon
 // |u|^2 + |v|^2 + |w|^2 and a count.  k2l2 is the [nx/2+1][nyl] table of rkx^2 + rky^2 (rkx(kx) = rkx(nx-kx)).
 __global__ void k_spec_bin(const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                            const double* __restrict__ k2l2, const double* __restrict__ rkz, int nx, int nyl, int nz,
-                           int pz, double dki, double* spec, double* num) {
+                           int pz, double dki, int nb, double* spec, double* num) {
     const long long n = (long long)nx * nyl * pz;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(i % pz);
@@ -271,6 +271,7 @@ __global__ void k_spec_bin(const double* __restrict__ u, const double* __restric
         const double rk = __ldg(&rkz[z]);
         const double kmag = floor(sqrt(__ldg(&k2l2[(long long)b * nyl + kyl]) + rk * rk) + 0.5);    // nint (:79)
         const int m = (int)(kmag * dki);                                                            // :100
+        if (m >= nb) continue;              // cannot happen with the host's bin count; never write out of bounds
         const double a = u[i], bb = v[i], c = w[i];
         atomicAdd(&spec[m], a * a + bb * bb + c * c);
         atomicAdd(&num[m], 1.0);

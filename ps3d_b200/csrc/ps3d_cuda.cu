@@ -65,7 +65,8 @@ struct RollingMean {   // utils/rolling_mean.f90:36-69
     int inew = 1, iold = 1, length = 0;
     double sma = 0.0;
     bool filled = false;
-    void alloc(int n) { if (history.empty()) history.assign(n, 0.0); length = n; }
+    // allocated once (advance.f90: rollmean%alloc in the stepper set-up); the window cannot change afterwards
+    bool alloc(int n) { if (history.empty()) { history.assign(n, 0.0); length = n; } return n == length; }
     double get_next(double vnew) {
         if (filled) {
             const double vold = history[iold - 1];
@@ -107,6 +108,8 @@ struct Ctx {
     int fuse_update = 1;                 // PS3D_NO_FUSED_UPDATE=1: cn2 update as a separate kernel after the source kernel
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
+    double rk4_dfac = 0.0;               // impl-diff-rk4: 0.5 * pref * dt of the last set_diffusion (vdiss = rk4_dfac * vhdis)
+    bool rk4_dfac_set = false;
     double last_advance_ms = 0.0;
     double last_diag[16] = {};           // diagnostics of the last adapt (advance.f90: set_netcdf_field_diagnostic)
     bool have_diag = false;
@@ -393,7 +396,7 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
     if (c.nranks == 1) {
         // (the L2-blocked variant assumes 16-z tiles on both axes)
         const int nzc = c.pz / LINE_ZC, G = (line_zc(c.nx) == LINE_ZC && line_zc(c.ny) == LINE_ZC && !c.gen[0] && !c.gen[1]) ? c.l2_chunks : 0;
-        if (G <= 0 || G >= nzc) {
+        if (G <= 0 || 2 * G > nzc) {       // the two ping-pong intermediates of 16 G levels must fit the work field
             for (int i = 0; i < n; ++i) {
                 first[i].out = c.W[5].p;
                 run_sweep(c, first[i]);
@@ -649,6 +652,8 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     }
     if (nranks < 1 || rank < 0 || rank >= nranks || nx % nranks || (ny / 2) % nranks)
         fail(PS3D_ERR_BAD_ARGUMENT, "bad rank layout %d/%d for %dx%d", rank, nranks, nx, ny);
+    if (nranks > PS3D_MAX_RANKS)
+        fail(PS3D_ERR_BAD_ARGUMENT, "nranks = %d: at most %d ranks (the GPUs of one NVSwitch box; peer tables are fixed-size)", nranks, PS3D_MAX_RANKS);
     for (int i = 0; i < 3; ++i)
         if (!(extent[i] > 0.0)) fail(PS3D_ERR_BAD_ARGUMENT, "domain extent must be positive (sta2dfft.f90:59-74)");
 #ifndef PS3D_EMU
@@ -1022,11 +1027,20 @@ static void do_set_diffusion(Ctx& c, double dt, double pref) {
         const double dfac = (c.nnu == 1) ? dt : pref * dt;          // cn2.f90:50-56
         PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 0, dfac, (const double*)c.vhdis.p,
                   (const double*)c.filt2d.p, c.fac1.p, c.fac2.p, ncol);
+        ++c.launches;
     } else {
-        const double dfac = 0.5 * pref * dt;                         // impl_rk4.f90:43
-        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 1, dfac, (const double*)c.vhdis.p,
-                  (const double*)c.filt2d.p, c.fac1.p, c.fac2.p, ncol);
+        // impl_rk4.f90:43-47: vdiss = dfac * vhdis is the persistent state; emq / epq are rebuilt from it at the start
+        // of every impl_rk4_step (:87-89) because the step squares them in place (:151, :185)
+        c.rk4_dfac = 0.5 * pref * dt;
+        c.rk4_dfac_set = true;
     }
+}
+
+static void rk4_factors(Ctx& c) {                               // impl_rk4.f90:87-89
+    if (!c.rk4_dfac_set) fail(PS3D_ERR_NOT_INITIALISED, "set_diffusion has not been called");
+    const long long ncol = (long long)c.nx * c.nyl;
+    PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 1, c.rk4_dfac, (const double*)c.vhdis.p,
+              (const double*)c.filt2d.p, c.fac1.p, c.fac2.p, ncol);
     ++c.launches;
 }
 
@@ -1095,6 +1109,7 @@ static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false
         *t += dt;
     } else {
         const double dt2 = 0.5 * dt, dt3 = dt / 3.0, dt6 = dt / 6.0;   // impl_rk4.f90:82-84
+        rk4_factors(c);                                    // epq, emq (:87-89)
         // substep one filters the source with filt(0,:,:) (:227-229)
         rk4_update(c, 1, dt2, dt6, c.filt2d.p);
         do_vor2vel(c);
@@ -1168,7 +1183,8 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     const double dtcfl = cflmax * std::min(std::min(c.dx[0] / (umax + small), c.dx[1] / (vmax + small)),
                                            c.dx[2] / (wmax + small));
     const double dt = std::min(std::min(alpha / (ggmax + small), alpha / (bfmax + small)), std::min(dtcfl, t_limit - t));
-    c.rollmean.alloc(win);
+    if (!c.rollmean.alloc(win))
+        fail(PS3D_ERR_BAD_ARGUMENT, "roll_mean_win_size changed from %d to %d (rolling_mean.f90: allocated once)", c.rollmean.length, win);
     const double rmv = c.rollmean.get_next(ggmax);
     double pref;
     switch (pretype) {                                             // advance.f90:385-408
@@ -1507,9 +1523,13 @@ int ps3d_cuda_genspec(int nmax, double* spec, double* num, int* nbins, double* d
     const double kx = c.h_rkx[c.nx / 2], ky = c.h_rky[c.ny / 2], kz = c.h_rkz[c.nz];
     const int kmax = (int)std::floor(std::sqrt(kx * kx + ky * ky + kz * kz) + 0.5);
     const double dk = (double)kmax / std::sqrt(0.25 * (double)c.nx * c.nx + 0.25 * (double)c.ny * c.ny + (double)c.nz * c.nz);   // :97
-    *nbins = kmax + 1; *dk_out = dk;
+    // The reference allocates spec(0:kmax) (:86-87) but bins with m = int(kmag / dk) (:100), which exceeds kmax
+    // whenever dk < 1, i.e. for any box larger than pi (2, 2, 1): a latent out-of-bounds write there.  Here the
+    // bins cover the largest reachable index, and the kernel checks it.
+    const int nb = std::max(kmax, (int)((double)kmax * (1.0 / dk))) + 1;
+    *nbins = nb; *dk_out = dk;
     if (!spec) return PS3D_OK;
-    if (!num || nmax < kmax + 1) fail(PS3D_ERR_BAD_ARGUMENT, "genspec needs room for %d bins", kmax + 1);
+    if (!num || nmax < nb) fail(PS3D_ERR_BAD_ARGUMENT, "genspec needs room for %d bins", nb);
     // kinetic energy of the current state (:62)
     field_reduce(c);
     ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
@@ -1524,12 +1544,13 @@ int ps3d_cuda_genspec(int nmax, double* spec, double* num, int* nbins, double* d
         launch_zop(c, i < 2 ? ZOP_COSINE : ZOP_SINE, c.W[i].p, c.W[i].p);
     }
     DevBuf<double> bins;
-    bins.alloc((size_t)2 * (kmax + 1));           // zero-initialised: spec, num
+    bins.alloc((size_t)2 * nb);
+    ps_memset(bins.p, 0, (size_t)2 * nb * sizeof(double), c.stream);
     PS_LAUNCH((k_spec_bin), dim3(stream_blocks((size_t)c.nx * c.nyl * c.pz)), dim3(256), 0, c.stream,
               (const double*)c.W[0].p, (const double*)c.W[1].p, (const double*)c.W[2].p, (const double*)c.k2l2.p,
-              (const double*)c.rkz.p, c.nx, c.nyl, c.nz, c.pz, 1.0 / dk, bins.p, bins.p + (kmax + 1));
+              (const double*)c.rkz.p, c.nx, c.nyl, c.nz, c.pz, 1.0 / dk, nb, bins.p, bins.p + nb);
     ++c.launches;
-    std::vector<double> h((size_t)2 * (kmax + 1));
+    std::vector<double> h((size_t)2 * nb);
     ps_d2h(h.data(), bins.p, h.size() * sizeof(double), c.stream);
     ps_sync(c.stream);
     bins.release();
@@ -1537,15 +1558,15 @@ int ps3d_cuda_genspec(int nmax, double* spec, double* num, int* nbins, double* d
     const double pi = std::acos(-1.0);
     const double prefactor = 4.0 / 3.0 * pi * dk * dk * dk;                                     // :111
     double total = 0.0;
-    for (int m = 0; m <= kmax; ++m) {
-        const double cnt = h[(size_t)kmax + 1 + m];
+    for (int m = 0; m < nb; ++m) {
+        const double cnt = h[(size_t)nb + m];
         num[m] = cnt;
         const double m0 = (double)m, m1 = (double)(m + 1);
         spec[m] = (cnt > 0.0) ? h[m] * prefactor * (m1 * m1 * m1 - m0 * m0 * m0) / cnt : h[m];  // :114-120
         total += spec[m] * dk;
     }
     const double snorm = ke / total;                                                            // :123
-    for (int m = 0; m <= kmax; ++m) spec[m] *= snorm;
+    for (int m = 0; m < nb; ++m) spec[m] *= snorm;
     PS_API_END
 }
 

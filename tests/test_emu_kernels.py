@@ -210,8 +210,22 @@ def check_reference_z_known_answers(lib, nz_deriv):
         d, exact = deriv_via_sine_series(nz, lambda a: lib.fftsine(col(a))[3, 5], lambda v: lib.fftcosine(col(v))[3, 5])
         assert np.max(np.abs(d - exact)) < 3.01 / nz
         want, _ = deriv_via_sine_series(nz, lambda a: np.concatenate(([0.0], O.dst(a[1:].copy(), nz))), lambda v: O.dct(v, nz))
-        # round-off of the two transforms is amplified by the largest wavenumber pi nz (deriv1d.f90:17-22)
-        assert np.max(np.abs(d - want)) < 1e-12 * math.pi * nz
+        # The derivative is cosine(rkz * sine(f)): absolute round-off of the sine coefficients (~1e-16 x their largest
+        # partial sum, uniform in kz) is amplified by rkz <= pi nz.  Two bars, both tied to the reference: relative
+        # to the magnitude the transforms carry, max |rkz * w| (deriv1d.f90:17-22), and the round-off floor of the
+        # reference's OWN arithmetic for this very test (literal stafft.f90 dst -> rkz -> dct, oracle/stafft_lit.c:
+        # 1.7e-10 at nz = 1024, 2.7e-13 at nz = 64).  The CUDA transforms must be at least as accurate as the Fortran.
+        import __graft_entry__ as G
+        G.build_stafft_lit()
+        from oracle.stafft_lit import Stafft
+        S = Stafft(nz)
+        lit, _ = deriv_via_sine_series(nz, lambda a: np.concatenate(([0.0], S.dst(a[1:].copy()))), lambda v: S.dct(v))
+        z = np.arange(nz + 1) / nz
+        w = np.concatenate(([0.0], O.dst(((1 - 2 * z ** 3) - (1 - 2 * z))[1:].copy(), nz)))
+        amp = float(np.max(np.abs(math.pi * np.arange(nz + 1) * w)))
+        floor = float(np.max(np.abs(lit - want)))
+        err = float(np.max(np.abs(d - want)))
+        assert err < max(1e-12 * amp, floor), (err, amp, floor)
     finally:
         lib.finalise()
 
@@ -249,3 +263,75 @@ def test_error_paths(emu):
     with pytest.raises(PS3DError) as e:
         emu.init(32, 32, 32, np.zeros(3), np.array([1.0, 0.0, 1.0]))   # sta2dfft.f90:67-74
     assert e.value.status == 2
+
+
+def test_genspec_large_box(emu):
+    """on a box larger than pi (2, 2, 1) the shell index int(kmag / dk) exceeds kmax (the reference
+    allocates spec(0:kmax), genspec.f90:86-100: latent overflow).  Every point must land in a bin and the bins
+    must integrate to the kinetic energy."""
+    n = 16
+    lower, extent = -math.pi * np.ones(3), 2 * math.pi * np.ones(3)
+    emu.init(n, n, n, lower, extent)
+    try:
+        emu.init_inversion("Hou & Li")
+        s = O.PS3D(n, n, n, lower, extent)
+        vor = np.random.default_rng(2).uniform(-1, 1, (3, n, n, n + 1))
+        s.set_vorticity(vor)
+        emu.upload_vorticity(vor)
+        emu.vor2vel()
+        spec, num, dk = emu.genspec()
+        assert dk < 1.0 and len(num) > int(round(math.sqrt(3 * (n / 2) ** 2))) + 1
+        assert np.sum(num) == n * n * (n + 1)
+        check_genspec(emu, s)
+        # the state next to the bins is intact: a second vor2vel reproduces the oracle's second vor2vel
+        emu.vor2vel()
+        s.vor2vel()
+        assert rel(emu.download3("vel"), s.vel) < TOL
+    finally:
+        emu.finalise()
+
+
+def test_rk4_two_steps_without_new_diffusion(grid):
+    """ps3d_cuda_step is the drop-in for bstep%step; impl_rk4_step rebuilds epq / emq from vdiss at every
+    call (impl_rk4.f90:87-89), so two steps after ONE set_diffusion must not see squared factors."""
+    lib, s, rng = grid
+    vor = rng.uniform(-1, 1, (3, s.nx, s.ny, s.nz + 1))
+    s.set_vorticity(vor)
+    lib.upload_vorticity(vor)
+    lib.vor2vel()
+    d = lib.diagnostics()
+    lib.init_diffusion(d["ke"], d["en"])
+    lib.stepper_setup("impl-diff-rk4")
+    dt, _ = lib.adapt(0.0, 100.0)
+    dto, pref = s.adapt(0.0, 100.0)              # (set_vorticity has run the oracle's vor2vel)
+    s.rk4_set_diffusion(dto, pref)
+    t = to = 0.0
+    for i in range(2):
+        lib.source()
+        t = lib.step(t, dt)
+        s.source()
+        to = s.rk4_step(to, dto, literal=True)
+        assert rel(lib.download3("svor"), s.svor) < TOL, i
+        lib.vor2vel()
+        s.vor2vel()
+
+
+def test_rank_limit_and_window_change(emu):
+    with pytest.raises(PS3DError) as e:
+        emu.init(32, 32, 8, np.zeros(3), np.ones(3), rank=0, nranks=16)
+    assert e.value.status == 2
+    emu.init(8, 8, 8, np.zeros(3), np.ones(3))
+    try:
+        emu.init_inversion("Hou & Li")
+        vor = np.random.default_rng(1).uniform(-1, 1, (3, 8, 8, 9))
+        emu.upload_vorticity(vor)
+        emu.vor2vel()
+        d = emu.diagnostics()
+        emu.init_diffusion(d["ke"], d["en"])
+        emu.stepper_setup("cn2")
+        emu.adapt(0.0, 100.0, win=4)
+        with pytest.raises(PS3DError) as e:
+            emu.adapt(0.0, 100.0, win=64)          # rolling_mean.f90: the window is allocated once
+        assert e.value.status == 2
+    finally:
+        emu.finalise()

@@ -34,7 +34,10 @@ def open_grid(lib, nx, ny, nz, lower, extent, filtering="Hou & Li"):
     return O.PS3D(nx, ny, nz, lower, extent, filtering)
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 64), (16, 32, 8), (128, 64, 32), (8, 8, 8), (16, 16, 1024), (1024, 8, 16)])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (16, 32, 8), (128, 64, 32), (8, 8, 8), (16, 16, 1024), (1024, 8, 16),
+                                   # the kernel instantiations of the benchmarked configurations (k_line_*<512>, <256> on
+                                   # both axes, full-width nz = 512 columns)
+                                   (512, 512, 8), (512, 8, 16), (8, 512, 16), (256, 256, 16), (64, 64, 512)])
 def test_operators_white_noise(lib, shape):
     """isolated transforms on a white-noise field (all modes populated)."""
     nx, ny, nz = shape
@@ -135,7 +138,8 @@ def test_vor2vel_source_white_noise_64(lib, filtering):
         lib.finalise()
 
 
-@pytest.mark.parametrize("shape", [(16, 16, 512), (8, 16, 256), (16, 8, 128), (8, 8, 1024), (32, 32, 16)])
+@pytest.mark.parametrize("shape", [(16, 16, 512), (8, 16, 256), (16, 8, 128), (8, 8, 1024), (32, 32, 16),
+                                   (512, 512, 8), (512, 8, 16), (8, 512, 16), (256, 256, 16), (64, 64, 512)])
 def test_vor2vel_source_white_noise_tall(lib, shape):
     """Column kernels at every nz template the configs use (512: three blocks per SM, in-place transforms; 1024),
     both instantiations (pairs (a, ny-a) and the (0, ny/2) pair), anisotropic boxes, against the oracle."""
@@ -340,6 +344,74 @@ def test_full_size_properties_256(lib):
         assert rel(dd[..., 1:n], f[..., 1:n]) < FIELD_TOL and np.all(dd[..., n] == 0.0)
         assert rel(lib.fftcosine(lib.fftcosine(f)), f) < FIELD_TOL
         assert rel(lib.field_decompose_semi_spectral(lib.field_combine_semi_spectral(f)), f) < FIELD_TOL
+    finally:
+        lib.finalise()
+
+
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_config3_256_steps_match_oracle(lib, stepper):
+    """BASELINE config 3 (Beltrami 256^3, full time stepping) against the oracle (literal steppers): dt to 1e-11 and
+    the spectral vorticity to 1e-12 of its max-norm after each of the first steps."""
+    from ps3d_b200 import host
+    n, nsteps = 256, 2
+    ref = O.beltrami_setup(n)
+    s = host.beltrami_solver(lib, n, stepper=stepper)
+    try:
+        t = 0.0
+        for i in range(nsteps):
+            dt, diag = s.advance()
+            t, dto = ref.advance(t, 100.0, stepper, literal=True)
+            assert dt == pytest.approx(dto, rel=1e-11), i
+            for k in ("vortmax", "vortrms", "vorch", "ggmax", "umax", "vmax", "wmax"):
+                assert diag[k] == pytest.approx(ref.diag[k], rel=1e-10), (i, k)
+            assert rel(lib.download3("svor"), ref.svor) < FIELD_TOL, i
+        d = lib.diagnostics()         # of the vel / vor of the last vor2vel inside the step
+        lib.vor2vel()
+        ref.vor2vel()
+        d = lib.diagnostics()
+        assert d["ke"] == pytest.approx(ref.get_kinetic_energy(), rel=DIAG_TOL)
+        assert d["en"] == pytest.approx(ref.get_enstrophy(), rel=DIAG_TOL)
+        assert d["helicity"] == pytest.approx(ref.get_helicity(), rel=DIAG_TOL)
+    finally:
+        s.close()
+
+
+def test_config4_512_analytic_known_answers(lib):
+    """BASELINE config 4 grid (512^3) through the C ABI against analytic answers: unit-tests/test_vor2vel_1.f90
+    (Beltrami k = l = 2, m = 1: velocity = vorticity / alpha) and test_diffx.f90 / test_diffy.f90
+    (cos 4x -> -4 sin 4x, 1e-12), the reference's own known-answer tests at the benchmark size."""
+    n = 512
+    lower, extent = -0.5 * PI * np.ones(3), PI * np.ones(3)
+    lib.init(n, n, n, lower, extent)
+    lib.init_inversion("Hou & Li")
+    try:
+        from ps3d_b200 import host
+        vor = host.beltrami_vorticity(n, n, n, lower, extent)
+        alpha = 3.0
+        lib.upload_vorticity(vor)
+        lib.vor2vel()
+        vor /= alpha                                   # analytic velocity (beltrami.f90:162-181, test_vor2vel_1.f90:75-94)
+        err = 0.0
+        for c in range(3):
+            err = max(err, float(np.max(np.abs(lib.download("vel", c) - vor[c]))))
+        del vor
+        assert err < 1e-13, err                        # reference bar at 32^3: 1e-14 (test_vor2vel_1.f90:99)
+        # diffx / diffy on a box of [-pi, pi]^3 need a second init
+    finally:
+        lib.finalise()
+    lib.init(n, n, n, -PI * np.ones(3), 2 * PI * np.ones(3))
+    lib.init_inversion("Hou & Li")
+    try:
+        x = (-PI + (2 * PI / n) * np.arange(n))
+        f = np.empty((n, n, n + 1))
+        f[:] = np.cos(4 * x)[:, None, None]
+        out = lib.fftxys2p(lib.diffx(lib.fftxyp2s(f)))
+        f[:] = (-4 * np.sin(4 * x))[:, None, None]
+        assert np.max(np.abs(out - f)) < 1e-12
+        f[:] = np.cos(4 * x)[None, :, None]
+        out = lib.fftxys2p(lib.diffy(lib.fftxyp2s(f)))
+        f[:] = (-4 * np.sin(4 * x))[None, :, None]
+        assert np.max(np.abs(out - f)) < 1e-12
     finally:
         lib.finalise()
 
