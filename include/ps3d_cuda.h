@@ -154,6 +154,9 @@ int ps3d_cuda_comm_stats(long long* n_alltoall, double* bytes_sent);
 /* ---- introspection for benchmarks ---- */
 /* number of kernels this library has launched since init */
 long long ps3d_cuda_kernel_launches(void);
+/* how many of them were TMA-staged line sweeps (line_tma.cuh; 0 when PS3D_LINE_TMA=0 or the driver refused the
+ * tensor maps and the register-staged sweeps of line_fft.cuh ran instead) */
+long long ps3d_cuda_tma_launches(void);
 /* time the last ps3d_cuda_advance spent on the device (CUDA events), milliseconds */
 double ps3d_cuda_last_advance_ms(void);
 /* run `reps` back-to-back launches of one hot kernel on resident data and return the

@@ -204,10 +204,14 @@ __host__ __device__ constexpr bool is_pow2(int n) { return n > 0 && (n & (n - 1)
 // `active` false for threads that own no FFT: they neither read nor write the
 // scratch).  sre/sim: this FFT's scratch line (N doubles each for IxSwz).  The
 // scratch must not be in use by other threads when the call is entered.
-template <int N, bool INV, class IX, class TW>
+// Barrier over the threads that share the exchange scratch: the whole block (default), or a named barrier over
+// one group of a block that runs several independent FFT groups (line_tma.cuh).
+struct BarBlock { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+
+template <int N, bool INV, class IX, class TW, class BAR = BarBlock>
 __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int u, bool active,
                                            double* __restrict__ sre, double* __restrict__ sim, const IX& ix,
-                                           const TW& tws) {
+                                           const TW& tws, const BAR& bar = BAR()) {
     static_assert(is_pow2(N) && N >= 8, "power-of-two lengths >= 8 only");
     int s = 1;
     constexpr int L = (N == 8) ? 3 : (N == 16) ? 4 : (N == 32) ? 5 : (N == 64) ? 6 : (N == 128) ? 7 :
@@ -220,9 +224,9 @@ __device__ __forceinline__ void block_cfft(double (&vr)[8], double (&vi)[8], int
         if (active) fft_pass<N, 8, INV>(vr, vi, u, s, pass, tws);
         const bool last = (pass == N8 - 1) && (TAIL == 1);
         if (!last) {
-            if (pass > 0) __syncthreads();               // WAR: everyone has gathered
+            if (pass > 0) bar();                         // WAR: everyone has gathered
             if (active) fft_scatter<N, 8>(vr, vi, u, s, sre, sim, ix);
-            __syncthreads();
+            bar();
             if (active) fft_gather<N>(vr, vi, u, sre, sim, ix);
         }
         s *= 8;

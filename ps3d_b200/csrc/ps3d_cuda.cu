@@ -7,6 +7,7 @@
 //   adapt         <- stepper/advance.f90:109-410, utils/rolling_mean.f90:36-69
 //   steppers      <- stepper/cn2.f90:40-181, stepper/impl_rk4.f90:37-207
 #include <cstdarg>
+#include <map>
 #include <vector>
 #include <algorithm>
 #include <cmath>
@@ -15,6 +16,7 @@
 #include "rt.h"
 #include "fft_core.cuh"
 #include "line_fft.cuh"
+#include "line_tma.cuh"
 #include "zcol.cuh"
 #include "line_gen.cuh"
 #include "zcol_gen.cuh"
@@ -108,6 +110,13 @@ struct Ctx {
     int fuse_update = 1;                 // PS3D_NO_FUSED_UPDATE=1: cn2 update as a separate kernel after the source kernel
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
+#ifndef PS3D_EMU
+    // TMA-staged line sweeps (line_tma.cuh): PS3D_LINE_TMA=0 falls back to the register-staged sweeps of line_fft.cuh
+    int line_tma = 1;
+    void* encode_tiled = nullptr;                      // cuTensorMapEncodeTiled through the runtime's driver entry point
+    std::map<std::pair<const void*, int>, CUtensorMap> tmaps;    // (input array, sweep kind) -> tensor map
+    long long tma_launches = 0;
+#endif
     double rk4_dfac = 0.0;               // impl-diff-rk4: 0.5 * pref * dt of the last set_diffusion (vdiss = rk4_dfac * vhdis)
     bool rk4_dfac_set = false;
     double last_advance_ms = 0.0;
@@ -233,6 +242,61 @@ static void launch_line(Ctx& c, int n, bool inv, int pro, const LineArgs& a, int
     }
 }
 
+#ifndef PS3D_EMU
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor map of a sweep input (line_tma.cuh).  kind 0: y sweep over a physical array [xl][y][pz]; 1: y sweep over
+// slab blocks [d][xl][kyl][pz] (one rank: one block, kyl = ny); 2: x sweep over [x][kyl][pz].  Returns null (and
+// switches the TMA path off) if the driver refuses the descriptor.
+static const CUtensorMap* sweep_tmap(Ctx& c, const double* base, int kind, int zc, TmaArgs& ta) {
+    const int n = (kind == 2) ? c.nx : c.ny;
+    const int blkrows = (kind == 1) ? c.nyl : n;
+    const int rpo = std::min(256, (kind == 2) ? n : blkrows);
+    ta.mode = (kind == 2) ? 1 : 0;
+    ta.rows_per_op = rpo; ta.nops = n / rpo; ta.blkrows = blkrows;
+    auto key = std::make_pair((const void*)base, kind);
+    auto it = c.tmaps.find(key);
+    if (it != c.tmaps.end()) return &it->second;
+    cuuint64_t dim[4], str[3];
+    cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+    const cuuint64_t rowb = (cuuint64_t)c.pz * 8;
+    dim[0] = c.pz;
+    if (kind == 2) {
+        dim[1] = c.nyl; dim[2] = c.nx; dim[3] = 1;
+        str[0] = rowb; str[1] = rowb * c.nyl; str[2] = rowb * c.nyl * c.nx;
+        box[0] = zc; box[1] = 1; box[2] = rpo; box[3] = 1;
+    } else {
+        const int nblk = n / blkrows;
+        dim[1] = blkrows; dim[2] = c.nxl; dim[3] = nblk;
+        str[0] = rowb; str[1] = rowb * blkrows; str[2] = rowb * blkrows * c.nxl;
+        box[0] = zc; box[1] = rpo; box[2] = 1; box[3] = 1;
+    }
+    alignas(64) CUtensorMap tm;
+    const CUresult rc = ((EncodeTiledFn)c.encode_tiled)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dim, str, box, es,
+                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        fprintf(stderr, "libps3d_cuda: cuTensorMapEncodeTiled failed (%d) for sweep kind %d: register-staged sweeps from here on\n", (int)rc, kind);
+        c.line_tma = 0;
+        return nullptr;
+    }
+    return &c.tmaps.emplace(key, tm).first->second;
+}
+
+template <int N, int ZC>
+static void launch_line_tma_n(Ctx& c, bool inv, int pro, const LineArgs& a, const TmaArgs& ta, const CUtensorMap& tm, int nctas,
+                              ps_stream_t stream) {
+    const size_t sm = line_tma_smem_bytes<N, ZC>();
+    const dim3 grid(nctas), block(1024);
+    if (!inv) { allow_smem(k_line_tma<N, false, PRO_PLAIN, ZC>, sm); PS_LAUNCH((k_line_tma<N, false, PRO_PLAIN, ZC>), grid, block, sm, stream, a, ta, tm); }
+    else if (pro == PRO_DIFF) { allow_smem(k_line_tma<N, true, PRO_DIFF, ZC>, sm); PS_LAUNCH((k_line_tma<N, true, PRO_DIFF, ZC>), grid, block, sm, stream, a, ta, tm); }
+    else { allow_smem(k_line_tma<N, true, PRO_PLAIN, ZC>, sm); PS_LAUNCH((k_line_tma<N, true, PRO_PLAIN, ZC>), grid, block, sm, stream, a, ta, tm); }
+    ++c.launches; ++c.tma_launches;
+}
+#endif
+
 // one x or y sweep.  axis: 0 = x, 1 = y.
 struct Sweep { int axis; bool inv; int pro; const double* in[4]; double add1, add3; double* out;
                int scatter = -1;      // >= 0: store straight into the peers' receive buffer `scatter` (peer memory)
@@ -285,6 +349,26 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.scale = 1.0 / std::sqrt((double)n);
     a.twscale = c.ntw / n;
     a.ntiles = nouter * a.nzc;
+#ifndef PS3D_EMU
+    // TMA-staged sweep (line_tma.cuh): whole arrays, plain or derivative prologue, tiles of at most 64 KB
+    if (c.line_tma && !c.gen[s.axis] && s.pro != PRO_CROSS && s.nzc < 0 && !s.in_pitch && !s.out_pitch && n >= 128 &&
+        (long long)n * zcl * 8 <= 65536) {
+        TmaArgs ta;
+        const int kind = (s.axis == 0) ? 2 : (s.inv ? 1 : 0);
+        const CUtensorMap* tm = sweep_tmap(c, s.in[0], kind, zcl, ta);
+        if (tm) {
+            const int nctas = std::min(a.ntiles, s.max_ctas > 0 ? std::min(s.max_ctas, c.num_sms) : c.num_sms);
+            ps_stream_t st = s.on_comm_stream ? c.comm_stream : c.stream;
+            switch (n) {
+                case 128: launch_line_tma_n<128, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
+                case 256: launch_line_tma_n<256, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
+                case 512: launch_line_tma_n<512, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
+                case 1024: launch_line_tma_n<1024, 8>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
+                default: break;
+            }
+        }
+    }
+#endif
     if (c.gen[s.axis]) launch_line_gen(c, s.axis, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
     else launch_line(c, n, s.inv, s.pro, a, a.ntiles, s.on_comm_stream ? c.comm_stream : c.stream, s.max_ctas);
 }
@@ -698,6 +782,21 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
         PS_CUDA_TRY(cudaGetDevice(&dev));
         PS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
         c->num_sms = prop.multiProcessorCount;
+    }
+    {
+        // cuTensorMapEncodeTiled without linking libcuda: the runtime hands out the driver entry point.
+        // Default: on for one rank (with several ranks the scatter sweeps and the second sweeps of neighbouring
+        // fields share the SMs, which one 192 KB block per SM does not allow); PS3D_LINE_TMA=0/1 overrides.
+        const char* e = getenv("PS3D_LINE_TMA");
+        c->line_tma = e ? atoi(e) : (nranks == 1 ? 1 : 0);
+        cudaDriverEntryPointQueryResult qr;
+        void* fn = nullptr;
+        if (c->line_tma && (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+                            qr != cudaDriverEntryPointSuccess || !fn)) {
+            (void)cudaGetLastError();
+            c->line_tma = 0;
+        }
+        c->encode_tiled = fn;
     }
     PS_CUDA_TRY(cudaEventCreate(&c->ev0));
     PS_CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -1586,6 +1685,13 @@ int ps3d_cuda_comm_stats(long long* n_alltoall, double* bytes_sent) {
 }
 
 long long ps3d_cuda_kernel_launches(void) { return g_ctx ? g_ctx->launches : 0; }
+long long ps3d_cuda_tma_launches(void) {
+#ifndef PS3D_EMU
+    return g_ctx ? g_ctx->tma_launches : 0;
+#else
+    return 0;
+#endif
+}
 double ps3d_cuda_last_advance_ms(void) { return g_ctx ? g_ctx->last_advance_ms : 0.0; }
 
 int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {

@@ -62,7 +62,7 @@ ALLTOALL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _dp, C.c_int, C.c_int, C.c_void_p)
 SPECTRAL_FIELDS = ("svor", "svel", "svorts")
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ps3d_cuda_last_error", "ps3d_cuda_kernel_launches",
-                                               "ps3d_cuda_last_advance_ms"])
+                                               "ps3d_cuda_tma_launches", "ps3d_cuda_last_advance_ms"])
 
 
 class PS3DError(RuntimeError):
@@ -95,6 +95,7 @@ class PS3DLib:
             fn.restype = C.c_int
         self.dll.ps3d_cuda_last_error.restype = C.c_char_p
         self.dll.ps3d_cuda_kernel_launches.restype = C.c_longlong
+        self.dll.ps3d_cuda_tma_launches.restype = C.c_longlong
         self.dll.ps3d_cuda_last_advance_ms.restype = C.c_double
         self.shape = self.spec_shape = None
 
@@ -240,6 +241,7 @@ class PS3DLib:
         return spec, num, float(dk[0])
 
     def kernel_launches(self): return int(self.dll.ps3d_cuda_kernel_launches())
+    def tma_launches(self): return int(self.dll.ps3d_cuda_tma_launches())
     def last_advance_ms(self): return float(self.dll.ps3d_cuda_last_advance_ms())
 
     def time_kernel(self, which, reps):

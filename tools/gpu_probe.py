@@ -18,7 +18,7 @@ for n in [int(v) for v in sys.argv[1:]] or [256, 512]:
         N = n * n * (n + 1)
         sweeps = 115 if stepper == "cn2" else 150
         gbs = sweeps * 16 * N / (min(ms) * 1e-3) / 1e9
-        print(json.dumps(dict(n=n, stepper=stepper, ms=ms, pts_per_s=n ** 3 / (min(ms) * 1e-3), alg_GBs=gbs)))
+        print(json.dumps(dict(n=n, stepper=stepper, tma_launches=lib.tma_launches(), launches=lib.kernel_launches(), ms=ms, pts_per_s=n ** 3 / (min(ms) * 1e-3), alg_GBs=gbs)))
         if stepper == "cn2":
             names = ["fwd_y", "fwd_x", "inv_x", "inv_y", "vor2vel_spec", "source_spec"]
             alg = [16, 16, 16, 16, 8 * 16, 5 * 16]
