@@ -85,7 +85,13 @@ def cpu_reference_run(n, steps, warmup, stepper="cn2"):
     extent = math.pi * np.ones(3)
     try:
         from oracle.ps3d_ref import RefSolver
-        r = RefSolver(n, n, n, lower, extent)
+        import __graft_entry__ as G
+        try:
+            path = G.build_ref(native=True)      # -march=native on the machine that runs it (the GPU box's host)
+            native = True
+        except Exception:
+            path, native = G.REF, False
+        r = RefSolver(n, n, n, lower, extent, path=path)
     except (OSError, FileNotFoundError, ValueError):
         r = None
     if r is not None:
@@ -99,7 +105,9 @@ def cpu_reference_run(n, steps, warmup, stepper="cn2"):
         threads = r.threads
         r.close()
         return n ** 3 * steps / dt, dt / steps, ("C++/OpenMP restatement of the reference algorithm (oracle/ps3d_ref.cpp: 4 transposes "
-                                                  f"per 2-D FFT, literal combine/decompose pairs; not the Fortran build), {threads} OpenMP threads")
+                                                  "per 2-D FFT, literal combine/decompose pairs, the reference's own radix-4/2 "
+                                                  "FFT kernels restated in oracle/stafft_lit.c; not the Fortran build), "
+                                                  f"{'-O3 -march=native' if native else '-O3'}, {threads} OpenMP threads")
     from oracle import ps3d_oracle as O
     s = O.beltrami_setup(n)
     t = 0.0
@@ -116,11 +124,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # bounded sample of the 512^3 workload: 256^3 when the whole --steps/--warmup run fits in about six minutes on this
+    # host (calibrated with one 128^3 step; a 256^3 step costs ~11x that), else 128^3.  The same restatement timed once
+    # on the full 512^3 grid is committed in profiles/r02_cpu_512.json.
     n = args.ref_n
+    if n > 128:
+        _, sec128, _ = cpu_reference_run(128, 1, 1, args.stepper)
+        if sec128 * 11.0 * (args.steps + args.warmup) > 360.0:
+            n = 128
     val, sec, how = cpu_reference_run(n, args.steps, args.warmup, args.stepper)
     cores = os.cpu_count()
     sample = f"Beltrami {n}^3 {args.stepper} steps (bounded sample of the {args.n}^3 workload), {how}"
-    print(json.dumps({
+    line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -128,7 +143,11 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }
+    one_off = os.path.join(ROOT, "profiles", "r02_cpu_512.json")
+    if os.path.exists(one_off):
+        line["cpu_baseline"]["same_config_one_off"] = json.load(open(one_off))
+    print(json.dumps(line))
 
 
 def main():
@@ -140,7 +159,7 @@ def main():
     ap.add_argument("--grid", "--n", dest="n", type=int, default=512, help="grid size (nx = ny = nz)")
     ap.add_argument("--nz", type=int, default=0, help="vertical cells if different from --grid (dev runs)")
     ap.add_argument("--stepper", default="cn2")
-    ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=256, help="grid of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -187,26 +206,49 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    dts = []
     for _ in range(args.warmup):
-        solver.advance()
+        dts.append(solver.advance()[0])
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     l0 = lib.kernel_launches()
+    a2a0, sent0 = lib.comm_stats()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
-        solver.advance()
+        dts.append(solver.advance()[0])
         dev_ms += lib.last_advance_ms()          # CUDA events on the library's stream around the whole step
     barrier()
     wall = time.perf_counter() - t0
     launches = lib.kernel_launches() - l0
+    tma_launches = lib.tma_launches()
+    a2a1, sent1 = lib.comm_stats()
     clocks = sampler.stop()
     ms_step = dev_ms / args.steps
     if world > 1:
         tt = torch.tensor([ms_step, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_step, wall = float(tt[0]), float(tt[1])
+    d_after = lib.diagnostics()                  # KE / enstrophy / helicity of the state the last step started from
+
+    # ---- parity of what was just computed: the dt sequence of every step since t = 0 and the diagnostics after the
+    # last one against the committed one-GPU series (tests/golden/, made by tools/make_golden_512.py), so that a run on
+    # any number of GPUs shows it computed the same trajectory ----
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", "beltrami%d_cn2_series.json" % n)
+    nst = args.warmup + args.steps
+    if args.stepper == "cn2" and nzz == n and os.path.exists(gpath):
+        g = json.load(open(gpath))
+        if nst <= len(g["dt"]):
+            rel_dt = max(abs(a - b) / b for a, b in zip(dts, g["dt"][:nst]))
+            rel_d = {k: abs(d_after[k] - g[k][nst - 1]) / abs(g[k][nst - 1]) for k in ("ke", "en", "helicity")}
+            parity = {"ok": bool(rel_dt <= 1e-11 and max(rel_d.values()) <= 1e-10), "steps_checked": nst,
+                      "max_rel_dt": rel_dt, "rel_ke": rel_d["ke"], "rel_en": rel_d["en"], "rel_helicity": rel_d["helicity"],
+                      "tolerances": {"dt": 1e-11, "diagnostics": 1e-10},
+                      "golden": "tests/golden/beltrami%d_cn2_series.json (1 GPU)" % n}
+        else:
+            parity = {"ok": None, "note": "the golden series holds %d steps, this run took %d" % (len(g["dt"]), nst)}
 
     # ---- end-to-end through the C ABI with host buffers (H2D of the step's input, D2H of its result) ----
     h2d = vor_host.nbytes
@@ -226,62 +268,102 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_sec = float(tt[0])
 
-    # ---- per-kernel device times (CUDA events on the library's stream), roofline of the dominant one ----
+    # ---- per-kernel device times (CUDA events on the library's stream, inside this run) ----
     peak, peak_src = peaks()
     N = n * n * (nzz + 1) // world                         # array elements per field on this rank
     kinfo = [("line_fwd_y", 16), ("line_fwd_x", 16), ("line_inv_x", 16), ("line_inv_y", 16),
-             ("vor2vel_columns", 8 * 16), ("source_columns", 5 * 16)]
+             ("vor2vel_columns", 8 * 16), ("source_columns", 5 * 16), ("line_fwd_y_cross", 16)]
     kernels = {}
     for w, (name, bpp) in enumerate(kinfo):
         lib.time_kernel(w, 2)
         ms = lib.time_kernel(w, 10)
-        kernels[name] = {"ms": ms, "alg_bytes": bpp * N * 8 // 8, "GBs": bpp * N / (ms * 1e-3) / 1e9}
-    # share of the step: launches per cn2 step = 3 vor2vel + 3 source column kernels, 3*18 + 10 line sweeps
-    mult = 3 if args.stepper == "cn2" else 4
-    share = {"vor2vel_columns": mult * kernels["vor2vel_columns"]["ms"],
-             "source_columns": mult * kernels["source_columns"]["ms"],
-             "line_sweeps": (mult * 18 + 10) * np.mean([kernels[k]["ms"] for k in list(kernels)[:4]])}
-    dom = max(share, key=share.get)
-    if dom == "line_sweeps":
-        dom = "line_fwd_y"
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command (per launch),
-    # only quoted for the configuration it was captured on
+        kernels[name] = {"ms": ms, "alg_bytes": bpp * N, "GBs": bpp * N / (ms * 1e-3) / 1e9}
+    # launches per step: per vor2vel + source pair 6 inverse 2-D FFTs and 3 forward ones whose y
+    # sweep forms the u x omega product; adapt: 2 inverse 2-D FFTs + 3 y sweeps on one rank (the x-transformed velocity
+    # of vor2vel is kept), 5 inverse 2-D FFTs otherwise
+    pairs = 3 if args.stepper == "cn2" else 4
+    cnt = {"line_inv_x": 6 * pairs + (2 if world == 1 else 5), "line_inv_y": 6 * pairs + 5, "line_fwd_x": 3 * pairs,
+           "line_fwd_y_cross": 3 * pairs, "vor2vel_columns": pairs, "source_columns": pairs}
+    # the source kernel of the time loop also carries the Crank-Nicolson update (cn2): its stand-alone time is a lower bound
+    share = {k: cnt[k] * kernels[k]["ms"] for k in cnt}
+    classes = {"inverse_line_sweeps": ["line_inv_x", "line_inv_y"], "forward_x_sweeps": ["line_fwd_x"],
+               "cross_product_y_sweeps": ["line_fwd_y_cross"], "vor2vel_columns": ["vor2vel_columns"],
+               "source_columns": ["source_columns"]}
+    cshare = {c: sum(share[k] for k in ks) for c, ks in classes.items()}
+    cshare["other (reductions, strain, updates, launch gaps)"] = max(0.0, ms_step - sum(cshare.values()))
+    dom = max(classes, key=lambda c: cshare[c])
+    dks = classes[dom]
+    dom_launches = sum(cnt[k] for k in dks)
+    dom_ms = sum(share[k] for k in dks) / dom_launches             # time-weighted over the variants of the class
+    dom_bytes = kernels[dks[0]]["alg_bytes"]
+    # DRAM traffic per launch of that kernel from the committed ncu --set full capture of this workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01j_ncu_kernels.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")
     if os.path.exists(tpath) and n == 512 and world == 1:
-        t = json.load(open(tpath)).get(dom if dom in ("vor2vel_columns", "source_columns") else "line_fwd_y")
+        t = json.load(open(tpath)).get(dom)
         if t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
-            "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"]}
+    roof = {"kernel": dom, "variants": {k: {"launches_per_step": cnt[k], "ms": kernels[k]["ms"], "GBs": kernels[k]["GBs"]} for k in dks},
+            "bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+            "alg_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms, "launches_per_step": dom_launches,
+            "note": "time-weighted over every launch of the class in one step; 16 B per array element per sweep (SURVEY 8d)"}
     step_bytes = SWEEPS[args.stepper] * 16 * n * n * (nzz + 1)   # whole job, peak = P x one GPU
     value = n * n * nzz / (ms_step * 1e-3)                      # whole job: the grid is split over the ranks
-    n_a2a, sent = lib.comm_stats()
+    n_a2a, sent = a2a1 - a2a0, sent1 - sent0
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"Beltrami {n}^3 {args.stepper} (examples/beltrami_512.config), analytic IC k=l=2 m=1",
-                   "grid": [n, n, n], "stepper": args.stepper, "filtering": "Hou & Li", "nnu": 3, "prediss": 30.0,
+                   "grid": [n, n, nzz], "stepper": args.stepper, "filtering": "Hou & Li", "nnu": 3, "prediss": 30.0,
                    "parallelism": "1 GPU" if world == 1 else
-                   f"slab{world}: x-slabs / ky-slabs, one NCCL all-to-all per 2-D FFT",
-                   "l2": "inputs larger than L2 (each field %.2f GB per GPU vs 126 MB L2)" % (N * 8 / 1e9)},
+                   f"slab{world}: x-slabs / ky-slabs, one all-to-all per 2-D FFT fused into the first sweep (peer-memory stores over NVLink)",
+                   "l2": "inputs larger than L2 (each field %.2f GB per GPU vs 126 MB L2)" % (N * 8 / 1e9),
+                   "line_sweeps": "TMA-staged (cp.async.bulk.tensor)" if tma_launches else "register-staged"},
         "roofline": roof,
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                           "peak": peak * world, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / (peak * world)},
-        "kernels": kernels, "step_share_ms": share,
+        "kernels": kernels, "step_share_ms": cshare,
         "e2e": {"value": n * n * nzz / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
-                "d2h_bytes_per_step": (16 + 8) * 8, "ms_per_step": e2e_sec * 1e3},
-        "comm": {"alltoalls_total": int(n_a2a), "bytes_sent_per_rank_total": sent},
-        "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps * 1e3, "clocks": clocks,
-        "diag": {k: float(v) for k, v in d.items()},
+                "d2h_bytes_per_step": (16 + 8) * 8, "ms_per_step": e2e_sec * 1e3,
+                "note": "per step: 3 vorticity fields host -> device from pinned memory, decompose, one advance, its 16 "
+                        "diagnostics and KE / enstrophy / helicity back to the host; the updated FIELDS are not downloaded "
+                        "(the reference writes fields at output cadence only, utils.f90:77-87)"},
+        "gpu_launches": int(launches), "tma_launches_total": int(tma_launches), "wall_ms_per_step": wall / args.steps * 1e3,
+        "clocks": clocks, "parity": parity,
+        "diag": {k: float(v) for k, v in d_after.items()},
     }
+    if world > 1:
+        # NVLink side of the exchanges: bytes this rank stored into its peers per step, against the step time
+        # (the exchanges are overlapped with the HBM-bound second sweeps, so this is a lower bound of the link rate) and the
+        # scatter sweep timed alone (the fused sweep + all-to-all kernel), both against 900 GB/s per direction per GPU
+        per_step = sent / args.steps
+        nv = {"alltoalls_per_step": n_a2a / args.steps, "bytes_per_rank_per_step": per_step,
+              "achieved_GBs_over_step": per_step / (ms_step * 1e-3) / 1e9, "peak_GBs": 900.0,
+              "frac_of_900_over_step": per_step / (ms_step * 1e-3) / 1e9 / 900.0,
+              "floor_ms_per_step_at_900": per_step / 900e9 * 1e3}
+        try:
+            lib.time_kernel(7, 2)
+            ms7 = lib.time_kernel(7, 10)
+            nb = n * n * (nzz + 1) // world // world * 8 * (world - 1)      # bytes one scatter sweep stores into peers
+            if world > 1:
+                t7 = torch.tensor([ms7], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t7, op=dist.ReduceOp.MAX)
+                ms7 = float(t7[0])
+            nv["scatter_sweep"] = {"ms": ms7, "peer_bytes": nb, "GBs": nb / (ms7 * 1e-3) / 1e9,
+                                   "frac_of_900": nb / (ms7 * 1e-3) / 1e9 / 900.0}
+        except Exception as e:            # NCCL send/recv transport: no fused scatter sweep to time
+            nv["scatter_sweep"] = {"unavailable": str(e)[:120]}
+        out["nvlink"] = nv
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        val, sec, how = cpu_reference_run(args.ref_n, 3, 1, args.stepper)
+        val, sec, how = cpu_reference_run(args.ref_n, 2, 1, args.stepper)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"Beltrami {args.ref_n}^3 {args.stepper}, 3 steps after 1 warm-up, {how}"}
+                               "sample": f"Beltrami {args.ref_n}^3 {args.stepper}, 2 steps after 1 warm-up, {how}"}
+        one_off = os.path.join(ROOT, "profiles", "r02_cpu_512.json")
+        if os.path.exists(one_off):          # the same restatement timed ONCE on the full 512^3 grid (same config as `value`)
+            out["cpu_baseline"]["same_config_one_off"] = json.load(open(one_off))
     solver.close()
     if rank == 0:
         print(json.dumps(out))

@@ -162,7 +162,10 @@ double ps3d_cuda_last_advance_ms(void);
 /* run `reps` back-to-back launches of one hot kernel on resident data and return the
  * average device time per launch in ms (CUDA events on the library's stream).
  * which: 0 = forward y sweep, 1 = forward x sweep, 2 = inverse x sweep,
- *        3 = inverse y sweep, 4 = vor2vel column kernel, 5 = source column kernel */
+ *        3 = inverse y sweep, 4 = vor2vel column kernel, 5 = source column kernel,
+ *        6 = forward y sweep with the u x omega product in the load (four input fields),
+ *        7 = forward y sweep storing straight into the peers' receive buffers over NVLink (nranks > 1 only;
+ *            every rank must make the same call) */
 int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch);
 
 #ifdef __cplusplus

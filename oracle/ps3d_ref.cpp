@@ -24,6 +24,20 @@
 #include <omp.h>
 #endif
 
+// The 1-D transforms are the literal restatement of the reference's own kernels (oracle/stafft_lit.c <- stafft.f90:
+// radix-4/2 decimation in time / frequency, out-of-place sweeps, sequential DST/DCT recurrences, sin/cos evaluated per
+// element in the pre-processing), one line per call as sta3dfft.f90:161-178 does.  -DPS3D_REF_TEXTBOOK_FFT selects the
+// earlier self-contained radix-2 transforms instead.
+#ifndef PS3D_REF_TEXTBOOK_FFT
+extern "C" {
+int lit_initfft(int n, int factors[5], double* trig);
+int lit_forfft_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk);
+int lit_revfft_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk);
+int lit_dct_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk2);
+int lit_dst_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk2);
+}
+#endif
+
 namespace {
 
 typedef std::vector<double> vec;
@@ -35,8 +49,14 @@ struct Fft {
     int n = 0, h = 0;
     std::vector<cplx> w, wr;     // exp(-2 pi i k / h), k < h/2;   exp(-2 pi i k / n), k <= h
     std::vector<int> rev;
+    std::vector<double> trig;    // initfft (stafft.f90:76-125)
+    int factors[5] = {0, 0, 0, 0, 0};
     void init(int n_) {
         n = n_; h = n / 2;
+#ifndef PS3D_REF_TEXTBOOK_FFT
+        trig.assign(2 * (size_t)n, 0.0);
+        lit_initfft(n, factors, trig.data());
+#endif
         w.resize(std::max(1, h / 2)); wr.resize(h + 1); rev.resize(h);
         for (int k = 0; k < h / 2; ++k) w[k] = std::polar(1.0, -2.0 * PI * k / h);
         for (int k = 0; k <= h; ++k) wr[k] = std::polar(1.0, -2.0 * PI * k / n);
@@ -73,12 +93,22 @@ struct Fft {
         }
     }
     void forfft(double* x, cplx* X, cplx* z) const {         // stafft.f90:196-287
+#ifndef PS3D_REF_TEXTBOOK_FFT
+        (void)z;
+        lit_forfft_wk(1, n, x, trig.data(), factors, reinterpret_cast<double*>(X));     // X: n + 2 doubles of work space
+        return;
+#endif
         spectrum(x, X, z);
         const double s = 1.0 / std::sqrt((double)n);
         x[0] = X[0].real() * s; x[h] = X[h].real() * s;
         for (int k = 1; k < h; ++k) { x[k] = X[k].real() * s; x[n - k] = X[k].imag() * s; }
     }
     void revfft(double* x, cplx* X, cplx* z) const {         // stafft.f90:296-403
+#ifndef PS3D_REF_TEXTBOOK_FFT
+        (void)z;
+        lit_revfft_wk(1, n, x, trig.data(), factors, reinterpret_cast<double*>(X));
+        return;
+#endif
         X[0] = cplx(x[0], 0.0); X[h] = cplx(x[h], 0.0);
         for (int k = 1; k < h; ++k) X[k] = cplx(x[k], x[n - k]);
         for (int k = 0; k < h; ++k) {
@@ -163,6 +193,11 @@ static void fftxys2p(const Ref& r, const double* fs, double* fp) {
 // ---- stafft.f90:410-550: dct / dst of one column through a real FFT of length n --------------------------------
 static void dct_col(const Ref& r, double* x, cplx* X, cplx* z, double* y) {
     const int n = r.nz;
+#ifndef PS3D_REF_TEXTBOOK_FFT
+    (void)X; (void)z;
+    lit_dct_wk(1, n, x, r.fz.trig.data(), r.fz.factors, y);          // y: 2 n doubles of work space
+    return;
+#endif
     double x1 = 0.5 * (x[0] - x[n]);
     for (int j = 1; j < n; ++j) x1 += x[j] * r.cosz[j];                                  // :440-448
     y[0] = 0.5 * (x[0] + x[n]);
@@ -181,6 +216,11 @@ static void dct_col(const Ref& r, double* x, cplx* X, cplx* z, double* y) {
 // x points at slot 1 of the reference's x(1:n): transforms slots 1..n-1, sets slot n to 0 (:546-549)
 static void dst_col(const Ref& r, double* x1, cplx* X, cplx* z, double* y) {
     const int n = r.nz;
+#ifndef PS3D_REF_TEXTBOOK_FFT
+    (void)X; (void)z;
+    lit_dst_wk(1, n, x1, r.fz.trig.data(), r.fz.factors, y);         // x1 = x(1:n)
+    return;
+#endif
     double* x = x1 - 1;                                                                   // x[j], j = 1..n
     y[0] = 0.0;
     for (int j = 1; j < n; ++j) y[j] = 0.5 * (x[j] - x[n - j]) + r.sinz[j] * (x[j] + x[n - j]);
@@ -195,7 +235,7 @@ static void dst_col(const Ref& r, double* x1, cplx* X, cplx* z, double* y) {
     }
     x[n] = 0.0;
 }
-struct ZWork { std::vector<cplx> X, z; vec y; explicit ZWork(int n) : X(n / 2 + 1), z(std::max(1, n / 2)), y(n) {} };
+struct ZWork { std::vector<cplx> X, z; vec y; explicit ZWork(int n) : X(n / 2 + 1), z(std::max(1, n / 2)), y(2 * (size_t)n + 2) {} };
 
 // sta3dfft.f90:264-296 fftsine / fftcosine on every column
 static void fftcosine(const Ref& r, double* f) {

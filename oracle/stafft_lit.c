@@ -301,9 +301,15 @@ static void revrdx2(const double* a, double* b, long nv, long lv, const double* 
 typedef void (*rdx_fn)(const double*, double*, long, long, const double*, const double*);
 
 /* stafft.f90:196-287.  x(0:m*n-1), vector index fastest; trig(0:2n-1). */
+int lit_forfft_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk);
 int lit_forfft(int m, int n, double* x, const double* trig, const int factors[5]) {
+    double* wk = (double*)malloc(sizeof(double) * (size_t)m * n);      /* the Fortran's automatic array wk(0:m*n-1) */
+    const int rc = lit_forfft_wk(m, n, x, trig, factors, wk);
+    free(wk);
+    return rc;
+}
+int lit_forfft_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk) {
     if (factors[0] || factors[4]) return 2;
-    double* wk = (double*)malloc(sizeof(double) * (size_t)m * n);
     int orig = 1;
     long rem = n, cum = 1;
     /* order of use: 5, 3, 2, 4, 6 (:210-273) */
@@ -324,14 +330,19 @@ int lit_forfft(int m, int n, double* x, const double* trig, const int factors[5]
     const double normfac = 1.0 / sqrt((double)n);
     if (orig) for (long i = 0; i < (long)m * n; ++i) x[i] = x[i] * normfac;
     else for (long i = 0; i < (long)m * n; ++i) x[i] = wk[i] * normfac;
-    free(wk);
     return 0;
 }
 
 /* stafft.f90:296-403 */
+int lit_revfft_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk);
 int lit_revfft(int m, int n, double* x, const double* trig, const int factors[5]) {
-    if (factors[0] || factors[4]) return 2;
     double* wk = (double*)malloc(sizeof(double) * (size_t)m * n);
+    const int rc = lit_revfft_wk(m, n, x, trig, factors, wk);
+    free(wk);
+    return rc;
+}
+int lit_revfft_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk) {
+    if (factors[0] || factors[4]) return 2;
     for (long i = (long)(n / 2 + 1) * m; i < (long)n * m; ++i) x[i] = -x[i];
     for (long i = 0; i < m; ++i) x[i] = f12 * x[i];
     if (n % 2 == 0) {
@@ -358,7 +369,6 @@ int lit_revfft(int m, int n, double* x, const double* trig, const int factors[5]
     const double normfac = 2.0 / sqrt((double)n);
     if (orig) for (long i = 0; i < (long)m * n; ++i) x[i] = x[i] * normfac;
     else for (long i = 0; i < (long)m * n; ++i) x[i] = wk[i] * normfac;
-    free(wk);
     return 0;
 }
 
@@ -366,9 +376,17 @@ int lit_revfft(int m, int n, double* x, const double* trig, const int factors[5]
 #define WK(i, j) wk[(i) + (long)m * (j)]
 
 /* stafft.f90:410-483.  x(m, 0:n) */
+int lit_dct_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk2);
 int lit_dct(int m, int n, double* x, const double* trig, const int factors[5]) {
+    double* wk2 = (double*)malloc(sizeof(double) * (size_t)2 * m * n);
+    const int rc = lit_dct_wk(m, n, x, trig, factors, wk2);
+    free(wk2);
+    return rc;
+}
+/* wk2: 2*m*n doubles (the automatic arrays of dct and of the forfft it calls) */
+int lit_dct_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk2) {
     const double pi = 3.141592653589793238462643383279502884197169399375105820974944592307816;
-    double* wk = (double*)malloc(sizeof(double) * (size_t)m * n);
+    double* wk = wk2;
     const double fpin = pi / (double)n;
     const double rtn = sqrt((double)n);
     for (int i = 0; i < m; ++i) WK(i, 0) = f12 * (X(i, 0) + X(i, n));
@@ -382,8 +400,8 @@ int lit_dct(int m, int n, double* x, const double* trig, const int factors[5]) {
         rowsum = rowsum - f12 * X(i, n);
         X(i, n) = rt2 * rowsum / rtn;
     }
-    const int rc = lit_forfft(m, n, wk, trig, factors);
-    if (rc) { free(wk); return rc; }
+    const int rc = lit_forfft_wk(m, n, wk, trig, factors, wk2 + (size_t)m * n);
+    if (rc) return rc;
     for (int i = 0; i < m; ++i) X(i, 0) = rt2 * WK(i, 0);
     for (int i = 0; i < m; ++i) X(i, 1) = X(i, n);
     if (n % 2 == 0) {
@@ -401,23 +419,29 @@ int lit_dct(int m, int n, double* x, const double* trig, const int factors[5]) {
                 X(i, 2 * j + 1) = X(i, 2 * j - 1) - rt2 * WK(i, n - j);
             }
     }
-    free(wk);
     return 0;
 }
 #undef X
 
 /* stafft.f90:489-550.  x(m, n) = x(m, 1:n): X(i, j) below takes the Fortran j = 1..n */
 #define X(i, j) x[(i) + (long)m * ((j) - 1)]
+int lit_dst_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk2);
 int lit_dst(int m, int n, double* x, const double* trig, const int factors[5]) {
+    double* wk2 = (double*)malloc(sizeof(double) * (size_t)2 * m * n);
+    const int rc = lit_dst_wk(m, n, x, trig, factors, wk2);
+    free(wk2);
+    return rc;
+}
+int lit_dst_wk(int m, int n, double* x, const double* trig, const int factors[5], double* wk2) {
     const double pi = 3.141592653589793238462643383279502884197169399375105820974944592307816;
-    double* wk = (double*)malloc(sizeof(double) * (size_t)m * n);
+    double* wk = wk2;
     const double fpin = pi / (double)n;
     for (int i = 0; i < m; ++i) WK(i, 0) = 0.0;
     for (int j = 1; j <= n - 1; ++j)
         for (int i = 0; i < m; ++i)
             WK(i, j) = f12 * (X(i, j) - X(i, n - j)) + sin((double)j * fpin) * (X(i, j) + X(i, n - j));
-    const int rc = lit_forfft(m, n, wk, trig, factors);
-    if (rc) { free(wk); return rc; }
+    const int rc = lit_forfft_wk(m, n, wk, trig, factors, wk2 + (size_t)m * n);
+    if (rc) return rc;
     for (int i = 0; i < m; ++i) X(i, 1) = WK(i, 0) / rt2;
     if (n % 2 == 0) {
         for (int j = 1; j <= n / 2 - 1; ++j) {
@@ -433,7 +457,6 @@ int lit_dst(int m, int n, double* x, const double* trig, const int factors[5]) {
         for (int i = 0; i < m; ++i) X(i, n - 1) = -rt2 * WK(i, (n + 1) / 2);
     }
     for (int i = 0; i < m; ++i) X(i, n) = 0.0;
-    free(wk);
     return 0;
 }
 #undef X

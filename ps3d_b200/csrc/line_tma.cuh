@@ -68,33 +68,41 @@ __host__ __device__ constexpr int tma_landing(int n, int zc) {
 }
 template <int N, int ZC>
 constexpr size_t line_tma_smem_bytes() {
-    return (size_t)(tma_groups(N, ZC) + tma_landing(N, ZC)) * N * ZC * sizeof(double) + 128;
+    return (size_t)(tma_groups(N, ZC) + tma_landing(N, ZC)) * N * ZC * sizeof(double) + 8 * tma_groups(N, ZC) * (tma_groups(N, ZC) + tma_landing(N, ZC)) + 64;
 }
 
-template <int N, bool INV, int PRO, int ZC>
+// ROT = false: NL landing buffers + one exchange scratch per group (a tile is copied out of its landing buffer, which
+//   is refilled at once).
+// ROT = true : the NB = G + NL buffers rotate; tile i lands in buffer i % NB, is copied to registers, and the SAME
+//   buffer then serves as the exchange scratch of its group; it is refilled (tile i + NB) when the group has finished
+//   its last exchange.  A load is then issued most of a tile time before it is needed instead of less than half.
+template <int N, bool INV, int PRO, int ZC, bool ROT>
 __global__ void __launch_bounds__(1024, 1) k_line_tma(LineArgs a, TmaArgs ta, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int T = line_threads(N, ZC), NF = ZC / 2, G = tma_groups(N, ZC), NL = tma_landing(N, ZC);
     constexpr int TILE = N * ZC;                       // doubles per tile
+    constexpr int NB = G + NL;                         // ROT: rotating buffers
+    constexpr int NBAR = ROT ? G * NB : G;             // mbarriers: tile i -> full[i % NBAR] (one group, one buffer each)
+    constexpr int AHEAD = ROT ? NB : NL;               // tiles in flight / owned
     static_assert(G * T == 1024 && G <= 15 && G % NL == 0, "one block = 1024 threads = G FFT groups; NL divides G");
     double* land = reinterpret_cast<double*>(smraw);
     double* scr0 = land + (size_t)NL * TILE;
-    uint64_t* full = reinterpret_cast<uint64_t*>(scr0 + (size_t)G * TILE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(land + (size_t)NB * TILE);
     const int grp = threadIdx.x / T, t = threadIdx.x - grp * T, f = t & (NF - 1), u = t / NF;
-    double* sre = scr0 + (size_t)grp * TILE;
+    double* sre = scr0 + (size_t)grp * TILE;           // (ROT: set per tile)
     double* sim = sre + NF * N;
-    const IxIlv<NF> ix{f};
+    IxIlv<NF> ix{f};
     const BarGroup<T> bar{1 + grp};
     const int nseq = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     auto issue = [&](int i) {
         const int tile = blockIdx.x + i * gridDim.x;
         const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
-        const int slot = i % NL;
-        // one mbarrier per FFT group (tile i belongs to group i % G; NL divides G): a barrier's phases are then
+        const int slot = ROT ? i % NB : i % NL;
+        // one mbarrier per (FFT group, buffer) combination (tile i belongs to group i % G): a barrier's phases are then
         // waited for strictly in order by one group, which the parity wait needs (waiting one phase ahead of
         // the current one would succeed at once)
-        uint64_t* fb = &full[i % G];
+        uint64_t* fb = &full[i % NBAR];
         mbar_expect_tx(fb, (uint32_t)(TILE * sizeof(double)));
         for (int j = 0; j < ta.nops; ++j) {
             const int r = j * ta.rows_per_op;
@@ -109,18 +117,19 @@ __global__ void __launch_bounds__(1024, 1) k_line_tma(LineArgs a, TmaArgs ta, co
     };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < NBAR; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0)
-        for (int i = 0; i < NL && i < nseq; ++i) issue(i);
+        for (int i = 0; i < AHEAD && i < nseq; ++i) issue(i);
 
     for (int i = grp; i < nseq; i += G) {
         const int tile = blockIdx.x + i * gridDim.x;
         const int o = tile / a.nzc, zc = a.zc0 + (tile - o * a.nzc);
-        const int slot = i % NL;
-        mbar_wait(&full[grp], (uint32_t)((i / G) & 1));
+        const int slot = ROT ? i % NB : i % NL;
+        mbar_wait(&full[i % NBAR], (uint32_t)((i / NBAR) & 1));
+        if (ROT) { sre = land + (size_t)slot * TILE; sim = sre + NF * N; }
         const double2* L = reinterpret_cast<const double2*>(land + (size_t)slot * TILE) + f;    // row r: L[r * NF]
         const int paired = a.in_map.paired;
         constexpr int H = N / 2;
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(1024, 1) k_line_tma(LineArgs a, TmaArgs ta, co
             }
         }
         bar();                                   // every thread of the group has copied its part of the landing tile
-        if (t == 0 && i + NL < nseq) issue(i + NL);
+        if (!ROT && t == 0 && i + NL < nseq) issue(i + NL);
         const int ul = tile_local(u);
         if (!INV) {
             block_cfft<N, false>(vr, vi, u, true, sre, sim, ix, TwGlobal{a.tw, a.twscale}, bar);
@@ -190,9 +199,17 @@ __global__ void __launch_bounds__(1024, 1) k_line_tma(LineArgs a, TmaArgs ta, co
                     st2f(a.final_store, row_dst(a, k) + obase, (p + r) * hs, (q + s) * hs);
                     st2f(a.final_store, row_dst(a, N - k) + obase, (q - s) * hs, (r - p) * hs);
                 }
+                if (ROT && e == 3) {             // every read of the buffer is done: refill it
+                    bar();
+                    if (t == 0 && i + NB < nseq) issue(i + NB);
+                }
             }
         } else {
             block_cfft<N, true>(vr, vi, u, true, sre, sim, ix, TwGlobal{a.tw, a.twscale}, bar);
+            if (ROT) {                           // the last gather is behind every thread: refill the buffer
+                bar();
+                if (t == 0 && i + NB < nseq) issue(i + NB);
+            }
             const long long obase = (long long)o * a.out_os + (zc - a.out_zc0) * ZC + 2 * f;
             const double sc = a.scale;
 #pragma unroll

@@ -278,28 +278,6 @@ __global__ void k_spec_bin(const double* __restrict__ u, const double* __restric
     }
 }
 
-// get_char_vorticity (field_diagnostics.f90:501-545): sums over cell-averaged |omega|
-__global__ void k_char_vorticity(FieldPtrs f, long long ncol, int nz, int pz, double vortrms,
-                                 double* __restrict__ partial) {
-    PS_SMEM(double, red);
-    double l1 = 0.0, l2 = 0.0;
-    const long long n = ncol * pz;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(i % pz);
-        if (z < 1 || z > nz) continue;
-        const double v1 = 0.5 * fabs(f.vor[0][i - 1] + f.vor[0][i]);
-        const double v2 = 0.5 * fabs(f.vor[1][i - 1] + f.vor[1][i]);
-        const double v3 = 0.5 * fabs(f.vor[2][i - 1] + f.vor[2][i]);
-        if (v1 + v2 + v3 > vortrms) {
-            l1 += v1 + v2 + v3;
-            l2 += v1 * v1 + v2 * v2 + v3 * v3;
-        }
-    }
-    const double r1 = block_reduce(l1, 0, red);
-    const double r2 = block_reduce(l2, 0, red);
-    if (threadIdx.x == 0) { partial[blockIdx.x * 2] = r1; partial[blockIdx.x * 2 + 1] = r2; }
-}
-
 // right-hand side of the pressure Poisson equation (fields_derived.f90:97-113) from the five strain fields and omega
 struct StrainPtrsFwd;
 __global__ void k_pressure_rhs(const double* __restrict__ dudx, const double* __restrict__ dudy, const double* __restrict__ dvdy,
@@ -385,27 +363,58 @@ __device__ __forceinline__ double sym3_max_abs(double a, double d, double e, dou
 struct StrainPtrs { const double* dudx; const double* dudy; const double* dvdy; const double* dwdx; const double* dwdy;
                     const double* vor[3]; };
 
-// partial[b*3 + {0,1,2}] = max over all points / points with iz = nz / iz = 0
-__global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, int strict, double* __restrict__ partial) {
-    PS_SMEM(double, red);
-    double gg = 0.0, us = 0.0, ls = 0.0;
+// One pass over the five strain fields and omega for the two remaining reductions of adapt:
+//  * max |eigenvalue| of the symmetrised strain over all points / points with iz = nz / iz = 0
+//    (advance.f90:222-276) -> partial[b*5 + {0,1,2}];
+//  * get_char_vorticity (field_diagnostics.f90:501-545): sums over the cell-averaged |omega| of the cells with
+//    sum |omega_bar| > vortrms -> partial[b*5 + {3,4}].  vortrms = sqrt(<|omega|^2>) (advance.f90:180-183) is taken
+//    from the first reduction ON THE DEVICE (red[RQ_SUMW2], already reduced over the ranks), with the same two
+//    correctly rounded operations the host would do: no host round trip between the reductions.
+// (red == nullptr: strain only, as before.)
+__global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, int strict, const double* __restrict__ red,
+                         double ncell, double* __restrict__ partial) {
+    PS_SMEM(double, redbuf);
+    double gg = 0.0, us = 0.0, ls = 0.0, l1 = 0.0, l2 = 0.0;
+    const double vortrms = red ? sqrt(red[RQ_SUMW2] / ncell) : 0.0;
     const long long n = ncol * pz;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(i % pz);
         if (z > nz) continue;
         const double ux = f.dudx[i], uy = f.dudy[i], vy = f.dvdy[i], wx = f.dwdx[i], wy = f.dwdy[i];
+        const double o0 = f.vor[0][i], o1 = f.vor[1][i], o2 = f.vor[2][i];
         // advance.f90:252-257
-        const double s12 = uy + 0.5 * f.vor[2][i], s13 = wx + 0.5 * f.vor[1][i], s23 = wy - 0.5 * f.vor[0][i];
+        const double s12 = uy + 0.5 * o2, s13 = wx + 0.5 * o1, s23 = wy - 0.5 * o0;
         const double l = strict ? jacobi_max_abs(ux, s12, s13, vy, s23, -(ux + vy))
                                 : sym3_max_abs(ux, s12, s13, vy, s23, -(ux + vy));
         gg = fmax(gg, l);
         if (z == nz) us = fmax(us, l);
         if (z == 0) ls = fmax(ls, l);
+        if (red && z >= 1) {
+            const double v1 = 0.5 * fabs(f.vor[0][i - 1] + o0);
+            const double v2 = 0.5 * fabs(f.vor[1][i - 1] + o1);
+            const double v3 = 0.5 * fabs(f.vor[2][i - 1] + o2);
+            if (v1 + v2 + v3 > vortrms) {
+                l1 += v1 + v2 + v3;
+                l2 += v1 * v1 + v2 * v2 + v3 * v3;
+            }
+        }
     }
-    const double r0 = block_reduce(gg, 1, red);
-    const double r1 = block_reduce(us, 1, red);
-    const double r2 = block_reduce(ls, 1, red);
-    if (threadIdx.x == 0) { partial[blockIdx.x * 3] = r0; partial[blockIdx.x * 3 + 1] = r1; partial[blockIdx.x * 3 + 2] = r2; }
+    const double r0 = block_reduce(gg, 1, redbuf);
+    const double r1 = block_reduce(us, 1, redbuf);
+    const double r2 = block_reduce(ls, 1, redbuf);
+    const double r3 = block_reduce(l1, 0, redbuf);
+    const double r4 = block_reduce(l2, 0, redbuf);
+    if (threadIdx.x == 0) {
+        double* p = partial + (long long)blockIdx.x * 5;
+        p[0] = r0; p[1] = r1; p[2] = r2; p[3] = r3; p[4] = r4;
+    }
+}
+
+// after a device-side all-reduce of the same values as sums (s) and as maxima (m): out[q] = opmask bit q ? m[q] : s[q]
+__global__ void k_select_reduced(const double* __restrict__ s, const double* __restrict__ m, int n, unsigned opmask,
+                                 double* __restrict__ out) {
+    const int q = threadIdx.x;
+    if (q < n) out[q] = ((opmask >> q) & 1) ? m[q] : s[q];
 }
 
 }  // namespace ps3d

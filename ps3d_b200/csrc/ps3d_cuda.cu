@@ -109,10 +109,14 @@ struct Ctx {
     int scatter_fence = 1;               // PS3D_NO_SCATTER_FENCE=1: rely on kernel completion for the visibility of peer stores
     int fuse_update = 1;                 // PS3D_NO_FUSED_UPDATE=1: cn2 update as a separate kernel after the source kernel
     int l2_chunks = 0;                   // PS3D_L2_CHUNKS: z-chunks per launch of the L2-blocked 2-D FFT (0 = off)
+    int keep_velx = 1;                   // PS3D_NO_KEEP_VELX=1: adapt re-does the x sweeps of u, v, w for its d/dy fields
     int strict_jacobi = 0;               // PS3D_STRICT_JACOBI=1: literal cyclic Jacobi (jacobi.f90) instead of the closed form
 #ifndef PS3D_EMU
-    // TMA-staged line sweeps (line_tma.cuh): PS3D_LINE_TMA=0 falls back to the register-staged sweeps of line_fft.cuh
+    // TMA-staged line sweeps (line_tma.cuh): PS3D_LINE_TMA=0 falls back to the register-staged sweeps of line_fft.cuh,
+    // 1 (default on one rank): lines of 512 and 1024, 2: every length from 128
     int line_tma = 1;
+    int tma_rot = 1;                                   // PS3D_TMA_ROT=0: separate landing buffer instead of rotating buffers
+    int tma_zc8 = 0;                                   // PS3D_TMA_ZC=8: N = 512 sweeps as four groups of 8-z tiles
     void* encode_tiled = nullptr;                      // cuTensorMapEncodeTiled through the runtime's driver entry point
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;    // (input array, sweep kind) -> tensor map
     long long tma_launches = 0;
@@ -125,12 +129,17 @@ struct Ctx {
     bool svorts_stale = false;           // the last source call carried the cn2 update and did not store svorts
 
     DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[9];
+    // one rank: the x-transformed velocity of the last vor2vel ([x][ky'][pz], the intermediate between the two sweeps
+    // of fftxys2p) is kept: adapt's d/dy fields (advance.f90:199-217) then need only their y sweep
+    DevBuf<double> velx[3];
+    bool velx_valid = false;
     Transport tr;
     ps_stream_t comm_stream = 0;          // NCCL all-to-alls run here, overlapped with the sweeps of other fields
 #ifndef PS3D_EMU
     cudaEvent_t ev_first[8] = {}, ev_a2a[8] = {}, ev_second[8] = {};
 #endif
     DevBuf<double> redS, redM;            // all-reduce landing buffers (sum / max)
+    PeerMailPtrs mail;                    // every rank's mailbox (peer-mapped), valid when tr.p2p
     DevBuf<double> stage;                 // natural-layout staging for the host boundary
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
     DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
@@ -256,7 +265,7 @@ static const CUtensorMap* sweep_tmap(Ctx& c, const double* base, int kind, int z
     const int rpo = std::min(256, (kind == 2) ? n : blkrows);
     ta.mode = (kind == 2) ? 1 : 0;
     ta.rows_per_op = rpo; ta.nops = n / rpo; ta.blkrows = blkrows;
-    auto key = std::make_pair((const void*)base, kind);
+    auto key = std::make_pair((const void*)base, kind * 100 + zc);
     auto it = c.tmaps.find(key);
     if (it != c.tmaps.end()) return &it->second;
     cuuint64_t dim[4], str[3];
@@ -285,15 +294,21 @@ static const CUtensorMap* sweep_tmap(Ctx& c, const double* base, int kind, int z
     return &c.tmaps.emplace(key, tm).first->second;
 }
 
-template <int N, int ZC>
-static void launch_line_tma_n(Ctx& c, bool inv, int pro, const LineArgs& a, const TmaArgs& ta, const CUtensorMap& tm, int nctas,
+template <int N, int ZC, bool ROT>
+static void launch_line_tma_r(Ctx& c, bool inv, int pro, const LineArgs& a, const TmaArgs& ta, const CUtensorMap& tm, int nctas,
                               ps_stream_t stream) {
     const size_t sm = line_tma_smem_bytes<N, ZC>();
     const dim3 grid(nctas), block(1024);
-    if (!inv) { allow_smem(k_line_tma<N, false, PRO_PLAIN, ZC>, sm); PS_LAUNCH((k_line_tma<N, false, PRO_PLAIN, ZC>), grid, block, sm, stream, a, ta, tm); }
-    else if (pro == PRO_DIFF) { allow_smem(k_line_tma<N, true, PRO_DIFF, ZC>, sm); PS_LAUNCH((k_line_tma<N, true, PRO_DIFF, ZC>), grid, block, sm, stream, a, ta, tm); }
-    else { allow_smem(k_line_tma<N, true, PRO_PLAIN, ZC>, sm); PS_LAUNCH((k_line_tma<N, true, PRO_PLAIN, ZC>), grid, block, sm, stream, a, ta, tm); }
+    if (!inv) { allow_smem(k_line_tma<N, false, PRO_PLAIN, ZC, ROT>, sm); PS_LAUNCH((k_line_tma<N, false, PRO_PLAIN, ZC, ROT>), grid, block, sm, stream, a, ta, tm); }
+    else if (pro == PRO_DIFF) { allow_smem(k_line_tma<N, true, PRO_DIFF, ZC, ROT>, sm); PS_LAUNCH((k_line_tma<N, true, PRO_DIFF, ZC, ROT>), grid, block, sm, stream, a, ta, tm); }
+    else { allow_smem(k_line_tma<N, true, PRO_PLAIN, ZC, ROT>, sm); PS_LAUNCH((k_line_tma<N, true, PRO_PLAIN, ZC, ROT>), grid, block, sm, stream, a, ta, tm); }
     ++c.launches; ++c.tma_launches;
+}
+template <int N, int ZC>
+static void launch_line_tma_n(Ctx& c, bool inv, int pro, const LineArgs& a, const TmaArgs& ta, const CUtensorMap& tm, int nctas,
+                              ps_stream_t stream) {
+    if (c.tma_rot) launch_line_tma_r<N, ZC, true>(c, inv, pro, a, ta, tm, nctas, stream);
+    else launch_line_tma_r<N, ZC, false>(c, inv, pro, a, ta, tm, nctas, stream);
 }
 #endif
 
@@ -314,7 +329,13 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.add1 = s.add1; a.add3 = s.add3;
     a.out = s.out;
     const int nline = (s.axis == 1) ? c.ny : c.nx;
-    const int zcl = c.gen[s.axis] ? LINE_ZC : sweep_zc(nline, s.scatter >= 0);     // z values per tile of this sweep's kernel
+    int zcl = c.gen[s.axis] ? LINE_ZC : sweep_zc(nline, s.scatter >= 0);     // z values per tile of this sweep's kernel
+#ifndef PS3D_EMU
+    // TMA-staged sweep (line_tma.cuh): whole arrays, plain or derivative prologue, tiles of at most 64 KB
+    const bool tma = c.line_tma && !c.gen[s.axis] && s.pro != PRO_CROSS && s.nzc < 0 && !s.in_pitch && !s.out_pitch &&
+                     nline >= (c.line_tma >= 2 ? 128 : 512) && (long long)nline * zcl * 8 <= 65536;   // (measured: no gain below 512)
+    if (tma && c.tma_zc8 && nline == 512 && s.scatter < 0) zcl = 8;            // PS3D_TMA_ZC=8: four groups of 8-z tiles
+#endif
     a.nzc = (s.nzc < 0) ? c.pz / zcl : s.nzc;
     a.zc0 = s.zc0; a.in_zc0 = s.in_zc0; a.out_zc0 = s.out_zc0; a.final_store = s.final_store;
     a.scatter_fence = c.scatter_fence;
@@ -350,9 +371,7 @@ static void run_sweep(Ctx& c, const Sweep& s) {
     a.twscale = c.ntw / n;
     a.ntiles = nouter * a.nzc;
 #ifndef PS3D_EMU
-    // TMA-staged sweep (line_tma.cuh): whole arrays, plain or derivative prologue, tiles of at most 64 KB
-    if (c.line_tma && !c.gen[s.axis] && s.pro != PRO_CROSS && s.nzc < 0 && !s.in_pitch && !s.out_pitch && n >= 128 &&
-        (long long)n * zcl * 8 <= 65536) {
+    if (tma) {
         TmaArgs ta;
         const int kind = (s.axis == 0) ? 2 : (s.inv ? 1 : 0);
         const CUtensorMap* tm = sweep_tmap(c, s.in[0], kind, zcl, ta);
@@ -362,7 +381,10 @@ static void run_sweep(Ctx& c, const Sweep& s) {
             switch (n) {
                 case 128: launch_line_tma_n<128, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
                 case 256: launch_line_tma_n<256, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
-                case 512: launch_line_tma_n<512, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
+                case 512:
+                    if (zcl == 8) launch_line_tma_n<512, 8>(c, s.inv, s.pro, a, ta, *tm, nctas, st);
+                    else launch_line_tma_n<512, 16>(c, s.inv, s.pro, a, ta, *tm, nctas, st);
+                    return;
                 case 1024: launch_line_tma_n<1024, 8>(c, s.inv, s.pro, a, ta, *tm, nctas, st); return;
                 default: break;
             }
@@ -429,6 +451,11 @@ static void allreduce_host(Ctx& c, double* vals, int n, unsigned opmask) {
 #ifndef PS3D_EMU
 // all ranks' preceding work on the compute stream is complete (and its peer stores visible) before any rank continues
 static void cross_rank_barrier(Ctx& c, ps_stream_t stream) {
+    if (c.tr.p2p && c.tr.peer_sync) {
+        PS_LAUNCH((k_peer_barrier), dim3(1), dim3(32), 0, stream, c.mail, c.rank, c.nranks, ++c.tr.bar_epoch);
+        ++c.launches;
+        return;
+    }
     const int rc = c.tr.nccl.AllReduce(c.redM.p + 32, c.redM.p + 32, 1, NcclApi::kFloat64, NcclApi::kSum, c.tr.comm, (void*)stream);
     if (rc != 0) fail(PS3D_ERR_DEVICE, "NCCL barrier failed: %s", c.tr.nccl.GetErrorString(rc));
 }
@@ -466,6 +493,9 @@ static void setup_p2p(Ctx& c) {
     double flag = ok ? 0.0 : 1.0;
     allreduce_host(c, &flag, 1, 1u);
     t.p2p = (flag == 0.0);
+    if (t.p2p)
+        for (int p = 0; p < P; ++p) c.mail.m[p] = reinterpret_cast<PeerMail*>(t.peer_t2[0][p] + c.nint);
+    t.peer_sync = getenv("PS3D_NO_PEER_SYNC") ? 0 : 1;
     all.release();
 }
 #endif
@@ -482,9 +512,9 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
         const int nzc = c.pz / LINE_ZC, G = (line_zc(c.nx) == LINE_ZC && line_zc(c.ny) == LINE_ZC && !c.gen[0] && !c.gen[1]) ? c.l2_chunks : 0;
         if (G <= 0 || 2 * G > nzc) {       // the two ping-pong intermediates of 16 G levels must fit the work field
             for (int i = 0; i < n; ++i) {
-                first[i].out = c.W[5].p;
+                if (!first[i].out) first[i].out = c.W[5].p;          // (a caller may keep the intermediate: do_vor2vel)
                 run_sweep(c, first[i]);
-                second[i].in[0] = c.W[5].p;
+                second[i].in[0] = first[i].out;
                 run_sweep(c, second[i]);
             }
             return;
@@ -759,6 +789,7 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
     c->fuse_update = getenv("PS3D_NO_FUSED_UPDATE") ? 0 : 1;
+    c->keep_velx = getenv("PS3D_NO_KEEP_VELX") ? 0 : 1;
     c->scatter_fence = getenv("PS3D_NO_SCATTER_FENCE") ? 0 : 1;
     c->p2p_ctas_per_sm = getenv("PS3D_P2P_CTAS") ? atoi(getenv("PS3D_P2P_CTAS")) : -1;
     c->pz = (c->nzp + LINE_ZC - 1) / LINE_ZC * LINE_ZC;
@@ -789,6 +820,8 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
         // fields share the SMs, which one 192 KB block per SM does not allow); PS3D_LINE_TMA=0/1 overrides.
         const char* e = getenv("PS3D_LINE_TMA");
         c->line_tma = e ? atoi(e) : (nranks == 1 ? 1 : 0);
+        c->tma_zc8 = getenv("PS3D_TMA_ZC") && atoi(getenv("PS3D_TMA_ZC")) == 8;
+        c->tma_rot = getenv("PS3D_TMA_ROT") ? atoi(getenv("PS3D_TMA_ROT")) : 1;
         cudaDriverEntryPointQueryResult qr;
         void* fn = nullptr;
         if (c->line_tma && (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
@@ -901,7 +934,8 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
         c->kyd.upload(kyd, s);
     }
     c->stage.alloc(c->nnat);
-    for (int i = 0; i < (nranks > 1 ? 9 : 6); ++i) c->W[i].alloc(c->nint);
+    // (the first receive buffer carries the peer-memory mailbox behind its field: one IPC mapping serves both)
+    for (int i = 0; i < (nranks > 1 ? 9 : 6); ++i) c->W[i].alloc(c->nint + (i == 6 ? sizeof(PeerMail) / sizeof(double) + 1 : 0));
     c->redS.alloc(64); c->redM.alloc(64);
     c->red_blocks = (int)std::min<size_t>((size_t)RED_BLOCKS, (c->nint + RED_THREADS - 1) / RED_THREADS);
     c->partial.alloc((size_t)RED_BLOCKS * 16);
@@ -1018,7 +1052,7 @@ static void do_finalise() {
     if (!g_ctx) return;
     Ctx* c = g_ctx;
     ps_sync(c->stream);
-    DevBuf<double>* groups[] = {c->svor, c->vor, c->vel, c->svel, c->svorts, c->wa, c->wb};
+    DevBuf<double>* groups[] = {c->svor, c->vor, c->vel, c->svel, c->svorts, c->wa, c->wb, c->velx};
     for (auto* g : groups) for (int i = 0; i < 3; ++i) g[i].release();
     for (int i = 0; i < 9; ++i) c->W[i].release();
     c->redS.release(); c->redM.release();
@@ -1060,12 +1094,16 @@ static void do_vor2vel(Ctx& c) {
     a.wsem0 = c.W[0].p; a.wsem1 = c.W[1].p; a.wsem2 = c.W[2].p;
     a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
     launch_v2v(c, a);
+    const bool keep = (c.nranks == 1 && c.l2_chunks <= 0 && c.keep_velx);
     Sweep f[6], g[6];
     for (int i = 0; i < 3; ++i) {
         f[i] = sweep_plain(0, true, false, c.W[i].p, nullptr);        g[i] = sweep_plain(1, true, false, nullptr, c.vor[i].p);
-        f[3 + i] = sweep_plain(0, true, false, c.svel[i].p, nullptr); g[3 + i] = sweep_plain(1, true, false, nullptr, c.vel[i].p);
+        if (keep && !c.velx[i].p) c.velx[i].alloc(c.nint);
+        f[3 + i] = sweep_plain(0, true, false, c.svel[i].p, keep ? c.velx[i].p : nullptr);
+        g[3 + i] = sweep_plain(1, true, false, nullptr, c.vel[i].p);
     }
     fft2d_batch(c, 6, f, g);
+    c.velx_valid = keep;
 }
 
 static StepArgs step_args(Ctx& c);
@@ -1232,6 +1270,25 @@ static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false
 static void strain_fields(Ctx& c) {
     const int comp[5] = {0, 0, 2, 1, 2};
     const bool ddx_[5] = {true, false, true, false, false};
+    if (c.velx_valid) {
+        // d/dy fields: the x sweep of u, v, w was done by vor2vel and kept; only the y sweep with the derivative
+        // prologue remains (3 sweeps instead of 6)
+        for (int i = 0; i < 5; ++i) {
+            if (ddx_[i]) continue;
+            Sweep g = sweep_plain(1, true, true, c.velx[comp[i]].p, c.W[i].p);
+            run_sweep(c, g);
+        }
+        Sweep f[2], g[2];
+        int k = 0;
+        for (int i = 0; i < 5; ++i) {
+            if (!ddx_[i]) continue;
+            f[k] = sweep_plain(0, true, true, c.svel[comp[i]].p, nullptr);
+            g[k] = sweep_plain(1, true, false, nullptr, c.W[i].p);
+            ++k;
+        }
+        fft2d_batch(c, 2, f, g);
+        return;
+    }
     Sweep f[5], g[5];
     for (int i = 0; i < 5; ++i) {
         f[i] = sweep_plain(0, true, ddx_[i], c.svel[comp[i]].p, nullptr);
@@ -1240,44 +1297,69 @@ static void strain_fields(Ctx& c) {
     fft2d_batch(c, 5, f, g);
 }
 
+// device-side all-reduce of red[0..n): sums and maxima according to opmask, result back in red (no host round trip)
+static void allreduce_dev(Ctx& c, double* red, int n, unsigned opmask) {
+    Transport& t = c.tr;
+    if (t.nranks == 1) return;
+#ifndef PS3D_EMU
+    if (t.p2p && t.peer_sync && !t.ar_cb && n <= 32) {
+        PS_LAUNCH((k_peer_allreduce), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, ++t.ar_epoch, n, opmask, red);
+        ++c.launches;
+        return;
+    }
+    if (t.have_nccl() && !t.ar_cb) {
+        ps_d2d(c.redS.p, red, n * sizeof(double), c.stream);
+        ps_d2d(c.redM.p, red, n * sizeof(double), c.stream);
+        int rc = t.nccl.AllReduce(c.redS.p, c.redS.p, n, NcclApi::kFloat64, NcclApi::kSum, t.comm, (void*)c.stream);
+        if (rc == 0) rc = t.nccl.AllReduce(c.redM.p, c.redM.p, n, NcclApi::kFloat64, NcclApi::kMax, t.comm, (void*)c.stream);
+        if (rc != 0) fail(PS3D_ERR_DEVICE, "NCCL all-reduce failed: %s", t.nccl.GetErrorString(rc));
+        PS_LAUNCH((k_select_reduced), dim3(1), dim3(64), 0, c.stream, (const double*)c.redS.p, (const double*)c.redM.p, n, opmask, red);
+        ++c.launches;
+        return;
+    }
+#endif
+    // host-supplied collectives (ps3d_cuda_set_transport): through the host
+    double h[64];
+    ps_d2h(h, red, n * sizeof(double), c.stream);
+    ps_sync(c.stream);
+    allreduce_host(c, h, n, opmask);
+    ps_h2d(red, h, n * sizeof(double), c.stream);
+    ps_sync(c.stream);
+}
+
 static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype, int win, double* dt_out, double* diag) {
     const long long ncol = (long long)c.nxl * c.ny;
+    // first reduction (advance.f90:171-185, 285-313) -> red[0..RQ_N), reduced over the ranks on the device
     field_reduce(c);
-    // char vorticity needs vortrms = sqrt(<|omega|^2>) (advance.f90:180-183); computed on the host from the
-    // first reduction to keep the reference's evaluation order
-    ps_d2h(c.h_red, c.red.p, RQ_N * sizeof(double), c.stream);
-    ps_sync(c.stream);
-    double r1[RQ_N];
-    for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
-    allreduce_host(c, r1, RQ_N, RQ_OPMASK);             // advance.f90:299-305, field_diagnostics.f90:418-424
-    const double vortmax = std::sqrt(r1[RQ_MAXW2]);
-    const double vortrms = std::sqrt(r1[RQ_SUMW2] / (double)c.ncell);
-    PS_LAUNCH((k_char_vorticity), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
-              field_ptrs(c), ncol, c.nz, c.pz, vortrms, c.partial.p);
-    PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
-              (const double*)c.partial.p, c.red_blocks, 2, 0u, c.red.p);
-    c.launches += 2;
+    allreduce_dev(c, c.red.p, RQ_N, RQ_OPMASK);             // advance.f90:299-305, field_diagnostics.f90:418-424
     // velocity strain (advance.f90:199-217): derivative folded into the inverse sweeps
     strain_fields(c);
     StrainPtrs sp;
     sp.dudx = c.W[0].p; sp.dudy = c.W[1].p; sp.dwdx = c.W[2].p; sp.dvdy = c.W[3].p; sp.dwdy = c.W[4].p;
     for (int i = 0; i < 3; ++i) sp.vor[i] = c.vor[i].p;
-    // k_strain writes partial[b*3..], after the char-vorticity final reduce has consumed partial (same stream)
+    // second reduction: strain maxima and the characteristic vorticity (needs vortrms of the first, read on the
+    // device) in one pass -> red[RQ_N .. RQ_N + 5) = ggmax, usggmax, lsggmax, vorl1, vorl2
     PS_LAUNCH((k_strain), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream, sp, ncol, c.nz,
-              c.pz, c.strict_jacobi, c.partial.p);
+              c.pz, c.strict_jacobi, (const double*)c.red.p, (double)c.ncell, c.partial.p);
     PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
-              (const double*)c.partial.p, c.red_blocks, 3, 7u, c.red.p + 2);
+              (const double*)c.partial.p, c.red_blocks, 5, 7u, c.red.p + RQ_N);
     c.launches += 2;
-    ps_d2h(c.h_red, c.red.p, 5 * sizeof(double), c.stream);
+    allreduce_dev(c, c.red.p + RQ_N, 5, 7u);                // sums: vorl1, vorl2 (field_diagnostics.f90:529-535); max: strain
+    // the one device -> host read of the step
+    ps_d2h(c.h_red, c.red.p, (RQ_N + 5) * sizeof(double), c.stream);
     ps_sync(c.stream);
-    allreduce_host(c, c.h_red, 5, 0x1cu);                // sums: vorl1, vorl2 (field_diagnostics.f90:529-535); max: strain
+    double r1[RQ_N];
+    for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
+    const double vortmax = std::sqrt(r1[RQ_MAXW2]);
+    const double vortrms = std::sqrt(r1[RQ_SUMW2] / (double)c.ncell);
+    const double* h2 = c.h_red + RQ_N;
     const double small = 1.0e-12, cflmax = 0.8;                    // constants.f90:63-65
     // vorl1 starts from `small` on every rank before the reduction (field_diagnostics.f90:509,529-535)
-    const double vorl1 = small * (double)c.nranks + c.h_red[0], vorl2 = c.h_red[1];
+    const double vorl1 = small * (double)c.nranks + h2[3], vorl2 = h2[4];
     const double vorch = vorl2 / vorl1;
     const double bfmax = 0.0;
-    const double ggmax = std::max(2.220446049250313e-16, c.h_red[2]);   // ggmax = epsilon(ggmax) (advance.f90:222)
-    const double usggmax = std::max(0.0, c.h_red[3]), lsggmax = std::max(0.0, c.h_red[4]);
+    const double ggmax = std::max(2.220446049250313e-16, h2[0]);   // ggmax = epsilon(ggmax) (advance.f90:222)
+    const double usggmax = std::max(0.0, h2[1]), lsggmax = std::max(0.0, h2[2]);
     const double umax = r1[RQ_MAXU], vmax = r1[RQ_MAXV], wmax = r1[RQ_MAXWV];
     const double dtcfl = cflmax * std::min(std::min(c.dx[0] / (umax + small), c.dx[1] / (vmax + small)),
                                            c.dx[2] / (wmax + small));
@@ -1532,6 +1614,7 @@ int ps3d_cuda_upload(int field_id, int comp, const double* host) {
     DevBuf<double>* f = field_by_id(c, field_id, spectral);
     if (!f || comp < 0 || comp > 2 || !host) fail(PS3D_ERR_BAD_ARGUMENT, "bad field id %d / component %d", field_id, comp);
     to_device(c, host, f[comp].p, spectral);
+    if (field_id == PS3D_F_SVEL) c.velx_valid = false;
     ps_sync(c.stream);
     PS_API_END
 }
@@ -1697,7 +1780,13 @@ double ps3d_cuda_last_advance_ms(void) { return g_ctx ? g_ctx->last_advance_ms :
 int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
     PS_API_BEGIN
     Ctx& c = ready();
-    if (!ms_per_launch || reps < 1 || which < 0 || which > 5) fail(PS3D_ERR_BAD_ARGUMENT, "bad time_kernel arguments");
+    if (!ms_per_launch || reps < 1 || which < 0 || which > 7) fail(PS3D_ERR_BAD_ARGUMENT, "bad time_kernel arguments");
+#ifndef PS3D_EMU
+    if (which == 7) {
+        if (!(c.nranks > 1 && c.tr.p2p)) fail(PS3D_ERR_BAD_ARGUMENT, "time_kernel 7 (peer-memory scatter sweep) needs nranks > 1 with peer access");
+        cross_rank_barrier(c, c.stream);          // every rank is here: the receive buffers are free
+    }
+#endif
 #ifndef PS3D_EMU
     PS_CUDA_TRY(cudaEventRecord(c.ev0, c.stream));
 #endif
@@ -1715,6 +1804,18 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
                 a.svel0 = c.W[5].p; a.svel1 = c.W[5].p; a.svel2 = c.W[5].p;
                 if (r == 0) { ps_d2d(c.W[0].p, c.svor[0].p, c.nint * sizeof(double), c.stream); ps_d2d(c.W[1].p, c.svor[1].p, c.nint * sizeof(double), c.stream); }
                 launch_v2v(c, a);
+                break;
+            }
+            case 6: {    // forward y sweep with the u x omega product in the load (inversion.f90:327)
+                Sweep s{1, false, PRO_CROSS, {c.vel[0].p, c.vor[1].p, c.vel[1].p, c.vor[0].p}, 0, 0, c.W[3].p};
+                run_sweep(c, s);
+                break;
+            }
+            case 7: {    // forward y sweep that stores straight into the peers' receive buffers (the fused sweep + all-to-all)
+                Sweep s{1, false, PRO_PLAIN, {c.vor[0].p, nullptr, nullptr, nullptr}, 0, 0, c.W[6].p};
+                s.scatter = 0;
+                s.max_ctas = (c.p2p_ctas_per_sm >= 0 ? c.p2p_ctas_per_sm : 2) * c.num_sms;
+                run_sweep(c, s);
                 break;
             }
             case 5: {
@@ -1735,6 +1836,7 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
     float ms = 0.f;
     PS_CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
     *ms_per_launch = (double)ms / reps;
+    if (which == 7) { cross_rank_barrier(c, c.stream); ps_sync(c.stream); }
 #else
     ps_sync(c.stream);
     *ms_per_launch = 0.0;

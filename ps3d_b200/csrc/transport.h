@@ -72,8 +72,79 @@ struct Transport {
     void* ipc_opened[2][8] = {};
     long long n_alltoall = 0;
     double bytes_sent = 0.0;
+    // peer-memory mailbox (PeerMail below) behind the first receive buffer of every rank: epoch-flag barrier and
+    // small all-reduce without a collective launch
+    int peer_sync = 1;                          // PS3D_NO_PEER_SYNC=1: one-element NCCL all-reduce / NCCL all-reduces instead
+    unsigned long long bar_epoch = 0, ar_epoch = 0;
 
     bool have_nccl() const { return comm != nullptr; }
 };
+
+// Mailbox in every rank's peer-mapped memory.  Flags only ever grow (epochs), so a late reader never sees a stale "go".
+struct PeerMail {
+    unsigned long long bar_flag[8];             // [src rank]: epoch of src's last barrier arrival
+    unsigned long long ar_flag[2][8];           // [parity][src rank]: epoch of src's last all-reduce contribution
+    double vals[2][8][32];                      // [parity][src rank][value]
+};
+struct PeerMailPtrs { PeerMail* m[8]; };
+
+#ifndef PS3D_EMU
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= e; gives up after ~4 s (a peer died): the caller's results are then garbage, but the GPU is not hung
+__device__ __forceinline__ void spin_until(const unsigned long long* p, unsigned long long e) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < e) {
+        if (clock64() - t0 > 8000000000LL) break;
+        __nanosleep(64);
+    }
+}
+
+// Cross-rank barrier: all ranks' preceding work on this stream is complete (and its peer stores visible) before any
+// rank's following work starts.  One block; thread p talks to rank p.
+__global__ void k_peer_barrier(PeerMailPtrs mp, int rank, int nranks, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p < nranks) {
+        __threadfence_system();
+        st_release_sys(&mp.m[p]->bar_flag[rank], epoch);
+        spin_until(&mp.m[rank]->bar_flag[p], epoch);
+    }
+}
+
+// All-reduce of red[0..n) over the ranks, sums or maxima per bit of opmask: every rank stores its vector into
+// every rank's mailbox, then reduces the P vectors in rank order -- the same order on every rank, so the result
+// is bitwise identical everywhere and independent of timing.
+__global__ void k_peer_allreduce(PeerMailPtrs mp, int rank, int nranks, unsigned long long epoch, int n, unsigned opmask,
+                                 double* red) {
+    const int t = threadIdx.x, par = (int)(epoch & 1);
+    if (t < n) {
+        const double v = red[t];
+        for (int p = 0; p < nranks; ++p) mp.m[p]->vals[par][rank][t] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < nranks) {
+        st_release_sys(&mp.m[t]->ar_flag[par][rank], epoch);
+        spin_until(&mp.m[rank]->ar_flag[par][t], epoch);
+    }
+    __syncthreads();
+    if (t < n) {
+        const PeerMail* me = mp.m[rank];
+        const bool mx = (opmask >> t) & 1;
+        double acc = *((volatile const double*)&me->vals[par][0][t]);
+        for (int p = 1; p < nranks; ++p) {
+            const double v = *((volatile const double*)&me->vals[par][p][t]);
+            acc = mx ? fmax(acc, v) : acc + v;
+        }
+        red[t] = acc;
+    }
+}
+#endif
 
 }  // namespace ps3d
