@@ -45,10 +45,13 @@ enum { PS3D_LSCALE_KOLMOGOROV = 0, PS3D_LSCALE_GEOPHYSICAL = 1 };
 enum { PS3D_STEPPER_CN2 = 0, PS3D_STEPPER_IMPL_RK4 = 1 };
 /* options.f90:55 `pretype` (advance.f90:385-408) */
 enum { PS3D_PRE_CONSTANT = 0, PS3D_PRE_VORCH = 1, PS3D_PRE_BFMAX = 2, PS3D_PRE_ROLL_MEAN_MAX_STRAIN = 3,
-       PS3D_PRE_MAX_STRAIN = 4, PS3D_PRE_US_MAX_STRAIN = 5 };
+       PS3D_PRE_MAX_STRAIN = 4, PS3D_PRE_US_MAX_STRAIN = 5,
+       PS3D_PRE_ROLL_MEAN_BFMAX = 6 /* buoyancy build only (advance.f90:395-398) */ };
 /* resident fields (fields.f90:17-23) for ps3d_cuda_download / ps3d_cuda_upload */
 enum { PS3D_F_SVOR = 0, PS3D_F_VOR = 1, PS3D_F_VEL = 2, PS3D_F_SVEL = 3, PS3D_F_SVORTS = 4,
-       PS3D_F_PRES = 5, PS3D_F_DELTA = 6 };
+       PS3D_F_PRES = 5, PS3D_F_DELTA = 6,
+       /* buoyancy build (fields.f90:28-35): mixed-spectral b', physical b', mixed-spectral tendency; comp ignored */
+       PS3D_F_SBUOY = 7, PS3D_F_BUOY = 8, PS3D_F_SBUOYS = 9 };
 /* slots of the diag_out[16] array filled by ps3d_cuda_adapt / ps3d_cuda_advance
  * (advance.f90:188-193,315-321,366) */
 enum { PS3D_D_VORTMAX = 0, PS3D_D_VORTRMS, PS3D_D_VORCH, PS3D_D_VORMEAN_X, PS3D_D_VORMEAN_Y, PS3D_D_VORMEAN_Z,
@@ -83,6 +86,7 @@ int ps3d_cuda_fftcosine(double* fs);                                  /* sta3dff
 int ps3d_cuda_diffx(const double* fs, double* ds);                    /* sta3dfft.f90:304 */
 int ps3d_cuda_diffy(const double* fs, double* ds);                    /* sta3dfft.f90:345 */
 int ps3d_cuda_central_diffz(const double* fs, double* ds);            /* inversion_utils.f90:653 */
+int ps3d_cuda_diffz(const double* fs, double* ds);                    /* inversion_utils.f90:683 (ENABLE_BUOYANCY) */
 int ps3d_cuda_field_combine_semi_spectral(double* sf);                /* inversion_utils.f90:617 */
 int ps3d_cuda_field_decompose_semi_spectral(double* sfc);             /* inversion_utils.f90:563 */
 int ps3d_cuda_field_combine_physical(const double* sf, double* fc);   /* inversion_utils.f90:599 */
@@ -102,6 +106,33 @@ int ps3d_cuda_step(double* t, double dt);                             /* cn2.f90
 /* advance (advance.f90:77-104) minus write_step */
 int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, int roll_mean_win_size,
                       double* dt_out, double diag_out[16]);
+
+/* ---- physics and the buoyancy build (configure.ac:228-245 --enable-buoyancy; a run-time switch here) ----
+ * ps3d_cuda_set_physics: planetary vorticity f_cor(1:3) and squared buoyancy frequency bfsq of physics.f90:88-92,
+ * 163-169 (the host evaluates 2 Omega cos/sin(lat) and reads / computes N^2 as physics.f90:300-340 does).  f_cor
+ * enters the vorticity tendency (inversion.f90:310-314), the pressure of the buoyancy build (fields_derived.f90:111)
+ * and the Rossby numbers of ps3d_cuda_field_stats.  Default: all zero. */
+int ps3d_cuda_set_physics(const double f_cor[3], double bfsq);
+/* Switches the ENABLE_BUOYANCY code paths on: allocates sbuoy, buoy, sbuoys and the stepper work fields
+ * (fields.f90:28-35, cn2.f90:31 bsm, impl_rk4.f90:67-72).  After ps3d_cuda_init_inversion, before the first step.
+ * From then on source = buoyancy_tendency + vorticity_tendency with r = u eta - v xi + b (inversion.f90:232-292,
+ * 316-331, 378-388), adapt evaluates bfmax (advance.f90:147-168) and the steppers advance sbuoy (cn2.f90:107-117,
+ * 151-160; impl_rk4.f90:91-105, 124-131, 154-164, 187-195).  nz must be a power of two (the spectral diffz of
+ * inversion_utils.f90:683-719 has no mixed-radix coverage kernel): PS3D_ERR_UNSUPPORTED otherwise. */
+int ps3d_cuda_enable_buoyancy(void);
+/* setup_fields (utils.f90:149-158) after the host removed the basic state: b'(0:nz,y,x) -> sbuoy */
+int ps3d_cuda_upload_buoyancy(const double* buoy_phys);
+/* the buoy_visc half of init_diffusion (inversion_utils.f90:144-151) and its options (options.f90:55-61):
+ * bvisc, bhdis; the pretype / rolling-mean window adapt uses for bval (advance.f90:358-374) */
+int ps3d_cuda_init_diffusion_buoyancy(int nnu, double prediss, int length_scale_id, double te, double en,
+                                      int pretype_id, int roll_mean_win_size, double* nu_out);
+/* the `bf` argument of bstep%set_diffusion (cn2.f90:61-75, impl_rk4.f90:44-50) for hosts that call
+ * ps3d_cuda_set_diffusion themselves; ps3d_cuda_adapt / ps3d_cuda_advance do both */
+int ps3d_cuda_set_diffusion_buoyancy(double dt, double bf);
+/* out = bfmax, rmb (rolling mean of bfmax), bval (buoyancy prefactor), bvisc of the last adapt (advance.f90:168,
+ * 358-374) */
+int ps3d_cuda_buoyancy_diag(double out[4]);
+
 /* field_netcdf.f90:216-230 reads these; comp = 0..2 (ignored for pres/delta, which are
  * computed on demand from the current state: fields_derived.f90:67,161) */
 int ps3d_cuda_download(int field_id, int comp, double* host);

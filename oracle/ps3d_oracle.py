@@ -223,6 +223,11 @@ class PS3D:
         self.vvisc = None
         self.rollmean = None
         self.f_cor = np.zeros(3)
+        # ENABLE_BUOYANCY build (configure.ac:228-245): buoyancy perturbation b' (fields.f90:28-35), squared buoyancy
+        # frequency (physics.f90:92); off unless enable_buoyancy() is called
+        self.buoyancy = False
+        self.bfsq = 0.0
+        self.buoy_rollmean = None
         self.diag = {}
         # impl_rk4 work arrays
         self.svori = None
@@ -323,6 +328,8 @@ class PS3D:
         self._set_hyperbolic_functions(zm, zp)
         self.phim[0, 0] = zm / self.extent[2]
         self.phip[0, 0] = zp / self.extent[2]
+        self.dphim[0, 0] = -1.0 / self.extent[2]        # inversion_utils.f90:333-336 (ENABLE_BUOYANCY)
+        self.dphip[0, 0] = 1.0 / self.extent[2]
         self.thetam[0, 0] = 0.0
         self.thetap[0, 0] = 0.0
         self.dthetam[0, 0] = 0.0
@@ -376,6 +383,7 @@ class PS3D:
         self.phip = div * (em - ef * ep)
         dphim = -kl * div * (ep + ef * em)
         dphip = kl * div * (em + ef * ep)
+        self.dphim, self.dphip = dphim, dphip          # module arrays in the ENABLE_BUOYANCY build (:520-521)
         Q = div * (1.0 + ef ** 2)
         R = div * 2.0 * ef
         self.thetam = k2ifac * (R * Lm * self.phip - Q * Lp * self.phim)
@@ -496,7 +504,11 @@ class PS3D:
         vel, vor = self.vel, self.vor
         for nc in range(3):
             vor[nc] = vor[nc] + self.f_cor[nc]
+        if self.buoyancy:
+            self.buoy = self.field_combine_physical(self.sbuoy)          # inversion.f90:316-318
         fp = vel[0] * vor[1] - vel[1] * vor[0]
+        if self.buoyancy:
+            fp = fp + self.buoy                                          # r = u * eta - v * xi + b (:329-331)
         r = self.field_decompose_physical(fp)
         fp = vel[2] * vor[0] - vel[0] * vor[2]
         q = self.field_decompose_physical(fp)
@@ -510,7 +522,61 @@ class PS3D:
         self.svorts[1] = r - s2
         self.svorts[2] = self.diffx(q) - self.diffy(p)
 
-    source = vorticity_tendency      # inversion.f90:378-388 (no buoyancy)
+    # ---- ENABLE_BUOYANCY: inversion_utils.f90:683-719, inversion.f90:232-292 ----
+    def diffz(self, fs):
+        """Spectral d/dz of a mixed-spectral field (inversion_utils.f90:683-719)."""
+        nz = self.nz
+        ds = fs[..., 0:1] * self.dphim + fs[..., nz:nz + 1] * self.dphip
+        as_ = np.zeros_like(fs)
+        as_[..., 1:nz] = self.rkz[None, None, 1:nz] * fs[..., 1:nz]
+        ds = ds + self.fftcosine(as_)
+        return self.field_decompose_semi_spectral(ds)
+
+    def enable_buoyancy(self, buoy_phys, bfsq=0.0):
+        """utils.f90:149-159 after the basic state has been removed: `buoy_phys` is b' in physical space."""
+        self.buoyancy = True
+        self.bfsq = float(bfsq)
+        self.buoy = np.array(buoy_phys, dtype=np.float64)
+        self.sbuoy = self.field_decompose_physical(self.buoy)
+        self.sbuoys = np.zeros_like(self.sbuoy)
+        self.bdiss = np.zeros((self.nx, self.ny))
+
+    def init_diffusion_buoyancy(self, te, en, nnu=3, prediss=30.0, length_scale="Kolmogorov"):
+        """inversion_utils.f90:144-151: bvisc, bhdis."""
+        keep = (self.vvisc, self.nnu, self.vhdis)
+        self.bvisc = self.init_diffusion(te, en, nnu, prediss, length_scale)
+        self.bnnu, self.bhdis = self.nnu, self.vhdis
+        self.vvisc, self.nnu, self.vhdis = keep
+        return self.bvisc
+
+    def buoyancy_tendency(self):
+        """inversion.f90:232-292."""
+        vel = self.vel
+        self.buoy = self.field_combine_physical(self.sbuoy)
+        fs = self.field_decompose_physical(vel[0] * self.buoy)
+        btend = self.field_combine_physical(self.diffx(fs))
+        fs = self.field_decompose_physical(vel[1] * self.buoy)
+        fp = self.field_combine_physical(self.diffy(fs))
+        btend = -btend - fp
+        fs = self.field_decompose_physical(vel[2] * self.buoy)
+        fp = self.field_combine_physical(self.diffz(fs))
+        btend = btend - self.bfsq * vel[2] - fp
+        self.sbuoys = self.field_decompose_physical(btend)
+
+    def source(self):
+        """inversion.f90:378-388."""
+        if self.buoyancy:
+            self.buoyancy_tendency()
+        self.vorticity_tendency()
+
+    def get_bfmax(self):
+        """advance.f90:147-168."""
+        sb = self.field_combine_semi_spectral(self.sbuoy)
+        xp = self.fftxys2p(self.diffx(sb))
+        yp = self.fftxys2p(self.diffy(sb))
+        zp = self.fftxys2p(self.central_diffz(sb))
+        xp = xp ** 2 + yp ** 2 + (zp + self.bfsq) ** 2
+        return math.sqrt(math.sqrt(float(xp.max())))
 
     # ---- field_diagnostics.f90 ----
     def _trap(self, f):
@@ -641,6 +707,9 @@ class PS3D:
         pres = 2.0 * (dudx * dvdy - dudy * (vor[2] + dudy)
                       + dvdy * dwdz - dwdy * (dwdy - vor[0])
                       + dwdz * dudx - dwdx * (dwdx + vor[1]))
+        if self.buoyancy:                                   # fields_derived.f90:108-112
+            self.buoy = self.field_combine_physical(self.sbuoy)
+            pres = pres + self.central_diffz(self.buoy) + self.f_cor[2] * vor[2]
         rs = self.fftxyp2s(pres)
         rs = dct(rs, self.nz)
         rs = self.green * rs
@@ -675,10 +744,10 @@ class PS3D:
         return dudx, dudy, dvdy, dwdx, dwdy
 
     def adapt(self, t, time_limit, alpha=0.1, pretype="vorch", win=1000,
-              with_pressure=False):
+              with_pressure=False, bpretype=None, bwin=None):
         nz = self.nz
         vor, vel = self.vor, self.vel
-        bfmax = 0.0
+        bfmax = self.get_bfmax() if self.buoyancy else 0.0
         xp = vor[0] ** 2 + vor[1] ** 2 + vor[2] ** 2
         vortmax = math.sqrt(np.max(np.abs(xp)))
         vortrms = math.sqrt(self.get_mean(xp))
@@ -706,12 +775,20 @@ class PS3D:
                              self.dx[1] / (vmax + SMALL),
                              self.dx[2] / (wmax + SMALL))
         dt = min(alpha / (ggmax + SMALL), alpha / (bfmax + SMALL), dtcfl, time_limit - t)
+        rmb = 0.0
+        if self.buoyancy:                                   # advance.f90:358-362
+            if self.buoy_rollmean is None:
+                self.buoy_rollmean = RollingMean(bwin if bwin else win)
+            rmb = self.buoy_rollmean.get_next(bfmax)
         if self.rollmean is None:
             self.rollmean = RollingMean(win)
         rmv = self.rollmean.get_next(ggmax)
-        pref = {"constant": 1.0, "vorch": vorch, "bfmax": bfmax,
-                "roll-mean-max-strain": rmv, "max-strain": ggmax,
-                "us-max-strain": usggmax}[pretype]
+        table = {"constant": 1.0, "vorch": vorch, "bfmax": bfmax,
+                 "roll-mean-max-strain": rmv, "roll-mean-bfmax": rmb, "max-strain": ggmax,
+                 "us-max-strain": usggmax}
+        pref = table[pretype]
+        self.bpref = table[bpretype if bpretype else pretype]  # bval = get_diffusion_pre_factor(buoy_visc) (:372-374)
+        self.rmb = rmb
         self.diag = dict(vortmax=vortmax, vortrms=vortrms, vorch=vorch,
                          vormean=vormean, bfmax=bfmax, ggmax=ggmax, umax=umax,
                          vmax=vmax, wmax=wmax, usggmax=usggmax, lsggmax=lsggmax,
@@ -719,9 +796,23 @@ class PS3D:
         return dt, pref
 
     # ---- cn2.f90 ----
-    def cn2_set_diffusion(self, dt, vorch):
+    def cn2_set_diffusion(self, dt, vorch, bf=0.0):
         dfac = dt if self.nnu == 1 else vorch * dt
         self.vdiss = 1.0 / (1.0 + dfac * self.vhdis)
+        if self.buoyancy:                                    # cn2.f90:61-75
+            dbac = dt if self.bnnu == 1 else bf * dt
+            self.bdiss = 1.0 / (1.0 + dbac * self.bhdis)
+
+    def _cn2_update_buoy(self, dt2, literal):
+        """cn2.f90:107-117 / :151-160."""
+        q = self.filt * (self.bsm + dt2 * self.sbuoys)
+        if literal:
+            q = self.field_combine_semi_spectral(q)
+            q = self.bdiss[..., None] * q
+            q = self.field_decompose_semi_spectral(q)
+        else:
+            q = self.bdiss[..., None] * q
+        self.sbuoy = q
 
     def _cn2_update(self, dt2, literal):
         vd = self.vdiss[..., None]
@@ -740,17 +831,24 @@ class PS3D:
         """cn2.f90:92-181.  literal=False uses the identity
         decompose(c(ky,kx)*combine(q)) == c*q."""
         dt2 = 0.5 * dt
+        if self.buoyancy:
+            self.bsm = self.sbuoy + dt2 * self.sbuoys
+            self._cn2_update_buoy(dt2, literal)
         self.vortsm = self.svor + dt2 * self.svorts
         self._cn2_update(dt2, literal)
         for _ in range(niter):
             self.vor2vel()
             self.source()
+            if self.buoyancy:
+                self._cn2_update_buoy(dt2, literal)
             self._cn2_update(dt2, literal)
         return t + dt
 
     # ---- impl_rk4.f90 ----
-    def rk4_set_diffusion(self, dt, vorch):
+    def rk4_set_diffusion(self, dt, vorch, bf=0.0):
         self.vdiss = 0.5 * vorch * dt * self.vhdis
+        if self.buoyancy:                                    # impl_rk4.f90:44-50
+            self.bdiss = 0.5 * bf * dt * self.bhdis
 
     def _cmd(self, q, fac, literal):
         """combine -> multiply by fac(ky,kx) -> decompose."""
@@ -770,6 +868,15 @@ class PS3D:
         svori = np.empty_like(svor)
         svorf = np.empty_like(svor)
         f0 = self.filt[..., 0:1]
+        B = self.buoyancy
+        if B:                                                 # impl_rk4.f90:91-105
+            bpq = np.exp(self.bdiss)
+            bmq = 1.0 / bpq
+            bpq = bpq * self.filt[..., 0]
+            self.sbuoys = f0 * self.sbuoys
+            sbuoyi = self.sbuoy
+            self.sbuoy = self._cmd(sbuoyi + dt2 * self.sbuoys, bmq, literal)
+            sbuoyf = sbuoyi + dt6 * self.sbuoys
         for nc in range(3):                                   # substep one
             svorts[nc] = f0 * svorts[nc]
             svori[nc] = svor[nc]
@@ -777,6 +884,10 @@ class PS3D:
             svorf[nc] = svori[nc] + dt6 * svorts[nc]
         self.vor2vel(); self.source()
         t = t + dt2
+        if B:                                                 # :124-131
+            self.sbuoys = self._cmd(self.sbuoys, bpq, literal)
+            self.sbuoy = self._cmd(sbuoyi + dt2 * self.sbuoys, bmq, literal)
+            sbuoyf = sbuoyf + dt3 * self.sbuoys
         for nc in range(3):                                   # substep two
             svorts[nc] = self._cmd(svorts[nc], epq, literal)
             svor[nc] = self._cmd(svori[nc] + dt2 * svorts[nc], emq, literal)
@@ -784,12 +895,21 @@ class PS3D:
         self.vor2vel(); self.source()
         t = t + dt2
         emq = emq ** 2
+        if B:                                                 # :154-164
+            bmq = bmq ** 2
+            self.sbuoys = self._cmd(self.sbuoys, bpq, literal)
+            self.sbuoy = self._cmd(sbuoyi + dt * self.sbuoys, bmq, literal)
+            sbuoyf = sbuoyf + dt3 * self.sbuoys
         for nc in range(3):                                   # substep three
             svorts[nc] = self._cmd(svorts[nc], epq, literal)
             svor[nc] = self._cmd(svori[nc] + dt * svorts[nc], emq, literal)
             svorf[nc] = svorf[nc] + dt3 * svorts[nc]
         self.vor2vel(); self.source()
         epq = epq ** 2
+        if B:                                                 # :187-195
+            bpq = bpq ** 2
+            self.sbuoys = self._cmd(self.sbuoys, bpq, literal)
+            self.sbuoy = self._cmd(sbuoyf + dt6 * self.sbuoys, bmq, literal)
         for nc in range(3):                                   # substep four
             svorts[nc] = self._cmd(svorts[nc], epq, literal)
             svor[nc] = self._cmd(svorf[nc] + dt6 * svorts[nc], emq, literal)
@@ -798,13 +918,13 @@ class PS3D:
 
     # ---- advance.f90:77-104 ----
     def advance(self, t, time_limit, stepper="cn2", alpha=0.1, pretype="vorch",
-                win=1000, literal=True, with_pressure=False):
+                win=1000, literal=True, with_pressure=False, bpretype=None, bwin=None):
         self.vor2vel()
-        dt, pref = self.adapt(t, time_limit, alpha, pretype, win, with_pressure)
+        dt, pref = self.adapt(t, time_limit, alpha, pretype, win, with_pressure, bpretype, bwin)
         if stepper == "cn2":
-            self.cn2_set_diffusion(dt, pref)
+            self.cn2_set_diffusion(dt, pref, self.bpref)
         else:
-            self.rk4_set_diffusion(dt, pref)
+            self.rk4_set_diffusion(dt, pref, self.bpref)
         self.source()
         if stepper == "cn2":
             return self.cn2_step(t, dt, literal), dt

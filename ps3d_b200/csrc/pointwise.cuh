@@ -58,6 +58,7 @@ struct StepArgs {
     long long ncol;         // nx*nyl
     int nz, pz;
     int has00;
+    int ncomp = 3;          // components updated: 3 (vorticity) or 1 (buoyancy: slot 0 of the pointer arrays)
 };
 
 // cn2.f90:120-135 / :162-173 with combine -> vdiss -> decompose collapsed.
@@ -69,8 +70,7 @@ __global__ void k_cn2_update(StepArgs a) {
         const long long col = i / a.pz;
         double fac = __ldg(&a.f2d[col]) * __ldg(&a.filtz[z]);
         if (a.has00 && col == 0) fac = __ldg(&a.vd[0]);      // filt(:,0,0) = 1 (inversion_utils.f90:275-277)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < a.ncomp; ++c) {
             const double s = a.svorts[c][i];
             double sm;
             if (a.stage == 0) { sm = a.svor[c][i] + a.c1 * s; a.wa[c][i] = sm; }
@@ -88,8 +88,7 @@ __global__ void k_rk4_update(StepArgs a) {
         if (z > a.nz) continue;
         const long long col = i / a.pz;
         const double mq = __ldg(&a.mq[col]), pq = __ldg(&a.pq[col]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < a.ncomp; ++c) {
             const double s = pq * a.svorts[c][i];
             a.svorts[c][i] = s;
             if (a.stage == 1) {
@@ -291,9 +290,42 @@ __global__ void k_pressure_rhs(const double* __restrict__ dudx, const double* __
     }
 }
 
+// ---- buoyancy build (ENABLE_BUOYANCY): flux products, tendency assembly, buoyancy-frequency maximum ----
+__global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] * b[i];
+}
+// sbuoys = -(d1 + d2 + d3) - bfsq * w   (inversion.f90:248-290 in mixed-spectral space, see do_buoyancy_tendency)
+__global__ void k_btend(const double* __restrict__ d1, const double* __restrict__ d2, const double* __restrict__ d3,
+                        const double* __restrict__ w, double bfsq, double* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = -d1[i] - d2[i] - bfsq * w[i] - d3[i];
+}
+// partial[b] = max over the grid of (db/dx)^2 + (db/dy)^2 + (db/dz + bfsq)^2   (advance.f90:160-165)
+__global__ void k_bfmax(const double* __restrict__ xp, const double* __restrict__ yp, const double* __restrict__ zp,
+                        double bfsq, long long ncol, int nz, int pz, double* __restrict__ partial) {
+    PS_SMEM(double, red);
+    double m = -1.0e300;
+    const long long n = ncol * pz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % pz);
+        if (z > nz) continue;
+        const double a = xp[i], b = yp[i], c = zp[i] + bfsq;
+        m = fmax(m, a * a + b * b + c * c);
+    }
+    const double r = block_reduce(m, 1, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
 __global__ void k_add(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = a[i] + b[i];
+}
+// out = a + b + s * c   (pressure source of the buoyancy build, fields_derived.f90:108-112: pres + db/dz + f_cor(3) zeta)
+__global__ void k_add_axpy(const double* __restrict__ a, const double* __restrict__ b, double s, const double* __restrict__ c,
+                           double* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] + b[i] + s * c[i];
 }
 
 // ---- Jacobi eigenvalues of the symmetrised strain (jacobi.f90) -----------------

@@ -133,6 +133,19 @@ struct Ctx {
     // of fftxys2p) is kept: adapt's d/dy fields (advance.f90:199-217) then need only their y sweep
     DevBuf<double> velx[3];
     bool velx_valid = false;
+    // physics.f90:88-92, 163-169: planetary vorticity and squared buoyancy frequency (ps3d_cuda_set_physics)
+    double f_cor[3] = {0.0, 0.0, 0.0};
+    double bfsq = 0.0;
+    // ENABLE_BUOYANCY build (configure.ac:228-245), switched on at run time by ps3d_cuda_enable_buoyancy:
+    // sbuoy (mixed spectral b'), buoy (physical), sbuoys (tendency), bsm / sbuoyi, sbuoyf, bsem (semi-spectral b')
+    bool buoyancy = false;
+    DevBuf<double> sbuoy, buoy, sbuoys, bsm, sbuoyf, bsem;
+    DevBuf<double> bhdis, bfac1, bfac2;
+    int bnnu = 3, bpretype = -1, bwin = 0;
+    double bvisc = 0.0, rk4_dbac = 0.0;
+    bool bdiffusion_ready = false;
+    RollingMean buoy_rollmean;
+    double last_bdiag[4] = {};          // bfmax, rmb, bval
     Transport tr;
     ps_stream_t comm_stream = 0;          // NCCL all-to-alls run here, overlapped with the sweeps of other fields
 #ifndef PS3D_EMU
@@ -1028,9 +1041,8 @@ static Ctx& ready() {
     return c;
 }
 
-static double do_init_diffusion(int nnu, double prediss, int lscale, double te, double en) {
-    Ctx& c = ready();
-    // get_viscosity (inversion_utils.f90:157-184)
+// get_viscosity + init_dissipation (inversion_utils.f90:157-218): returns the (hyper)viscosity, fills hdis[kx][kyl]
+static double viscosity_table(Ctx& c, int nnu, double prediss, int lscale, double te, double en, std::vector<double>& vh) {
     double rkxmax = 0, rkymax = 0;
     for (double v : c.h_rkx) rkxmax = std::max(rkxmax, v);
     for (double v : c.h_rky) rkymax = std::max(rkymax, v);
@@ -1040,9 +1052,16 @@ static double do_init_diffusion(int nnu, double prediss, int lscale, double te, 
     if (lscale == PS3D_LSCALE_KOLMOGOROV) vis = prediss * std::pow(K2max * te / en, 1.0 / 3.0) * std::pow(rkmsi, nnu);
     else if (lscale == PS3D_LSCALE_GEOPHYSICAL) vis = prediss * std::pow(rkmsi, nnu);
     else fail(PS3D_ERR_BAD_ARGUMENT, "We only support 'Kolmogorov' or 'geophysical'");
-    c.vvisc = vis; c.nnu = nnu;
-    std::vector<double> vh(c.h_k2l2.size());
+    vh.resize(c.h_k2l2.size());
     for (size_t i = 0; i < vh.size(); ++i) vh[i] = (nnu == 1) ? vis * c.h_k2l2[i] : vis * std::pow(c.h_k2l2[i], nnu);
+    return vis;
+}
+
+static double do_init_diffusion(int nnu, double prediss, int lscale, double te, double en) {
+    Ctx& c = ready();
+    std::vector<double> vh;
+    const double vis = viscosity_table(c, nnu, prediss, lscale, te, en, vh);
+    c.vvisc = vis; c.nnu = nnu;
     c.vhdis.upload(vh, c.stream);
     c.diffusion_ready = true;
     return vis;
@@ -1064,6 +1083,8 @@ static void do_finalise() {
                                  &c->rkz, &c->gamtop, &c->gambot, &c->filt2d, &c->filtz, &c->vhdis, &c->fac1, &c->fac2,
                                  &c->wz, &c->ini_mean, &c->partial, &c->red};
     for (auto* b : singles) b->release();
+    DevBuf<double>* bb[] = {&c->sbuoy, &c->buoy, &c->sbuoys, &c->bsm, &c->sbuoyf, &c->bsem, &c->bhdis, &c->bfac1, &c->bfac2};
+    for (auto* b : bb) b->release();
     c->tw.release(); c->permy.release();
     for (int i = 0; i < 3; ++i) c->gtw[i].release();
     c->gsinz.release(); c->gcosz.release();
@@ -1108,11 +1129,37 @@ static void do_vor2vel(Ctx& c) {
 
 static StepArgs step_args(Ctx& c);
 static void vor_mean(Ctx& c, int mode);
+static void launch_zop(Ctx& c, int op, const double* in, double* out);
+
+// buoyancy_tendency (inversion.f90:232-292).  The reference takes each flux divergence back to physical space, sums
+// there and decomposes the sum; combine and decompose are linear and mutually inverse, so the sum is formed in
+// mixed-spectral space:  sbuoys = -[diffx(F1) + diffy(F2) + diffz(F3)] - bfsq * decompose(w),  F_i = decompose(u_i b').
+static void do_buoyancy_tendency(Ctx& c) {
+    const long long n = (long long)c.nint;
+    const int nb = stream_blocks(c.nint);
+    launch_zop(c, ZOP_COMBINE, c.sbuoy.p, c.bsem.p);                       // field_combine_physical(sbuoy, buoy) (:247)
+    fft2d_inv(c, c.bsem.p, c.buoy.p, false, false);
+    const int dop[3] = {ZOP_DIFFX, ZOP_DIFFY, ZOP_DIFFZ_SPEC};
+    for (int i = 0; i < 3; ++i) {
+        PS_LAUNCH((k_mul), dim3(nb), dim3(256), 0, c.stream, (const double*)c.vel[i].p, (const double*)c.buoy.p, c.W[3].p, n);
+        ++c.launches;
+        fft2d_fwd(c, c.W[3].p, c.W[4].p);
+        launch_zop(c, ZOP_DECOMPOSE, c.W[4].p, c.W[3].p);
+        launch_zop(c, dop[i], c.W[3].p, c.W[i].p);
+    }
+    launch_zop(c, ZOP_DECOMPOSE, c.svel[2].p, c.W[3].p);                   // mixed-spectral w (vel(:,:,:,3) of :288)
+    PS_LAUNCH((k_btend), dim3(nb), dim3(256), 0, c.stream, (const double*)c.W[0].p, (const double*)c.W[1].p,
+              (const double*)c.W[2].p, (const double*)c.W[3].p, c.bfsq, c.sbuoys.p, n);
+    ++c.launches;
+}
+
+static StepArgs buoy_step_args(Ctx& c);
 
 // upd < 0: svorts only.  upd = 0 / 1 (cn2, power-of-two nz): the Crank-Nicolson update of cn2.f90:120-135 /
 // :162-173 rides on the last stage of the source kernel, svorts is not stored (see SrcArgs)
 static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0) {
-    const double fc[3] = {0.0, 0.0, 0.0};    // physics.f90 f_cor: zero for the configurations in scope
+    const double* fc = c.f_cor;              // vor + f_cor (inversion.f90:310-314; `vor` itself stays relative here)
+    if (c.buoyancy) do_buoyancy_tendency(c); // inversion.f90:381-383; also leaves the semi-spectral b' in bsem
     const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
     const double *xi = c.vor[0].p, *eta = c.vor[1].p, *zeta = c.vor[2].p;
     // r = u*eta - v*xi ; q = w*xi - u*zeta ; p = v*zeta - w*eta   (inversion.f90:327,336,350)
@@ -1122,6 +1169,12 @@ static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0) {
     Sweep g[3];
     for (int i = 0; i < 3; ++i) g[i] = sweep_plain(0, false, false, nullptr, c.W[i].p);
     fft2d_batch(c, 3, f, g);
+    if (c.buoyancy) {
+        // r = u eta - v xi + b (inversion.f90:329-331): the x/y transform is linear, so b joins r in semi-spectral space
+        PS_LAUNCH((k_add), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.W[0].p, (const double*)c.bsem.p,
+                  c.W[0].p, (long long)c.nint);
+        ++c.launches;
+    }
     SrcArgs a;
     a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
     a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
@@ -1173,12 +1226,32 @@ static void do_set_diffusion(Ctx& c, double dt, double pref) {
     }
 }
 
+// bdiss (cn2.f90:61-75 / impl_rk4.f90:48-50)
+static void do_set_diffusion_buoyancy(Ctx& c, double dt, double bf) {
+    if (!c.buoyancy) return;
+    if (!c.bdiffusion_ready) fail(PS3D_ERR_NOT_INITIALISED, "init_diffusion_buoyancy has not been called");
+    const long long ncol = (long long)c.nx * c.nyl;
+    if (c.stepper == PS3D_STEPPER_CN2) {
+        const double dbac = (c.bnnu == 1) ? dt : bf * dt;
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 0, dbac, (const double*)c.bhdis.p,
+                  (const double*)c.filt2d.p, c.bfac1.p, c.bfac2.p, ncol);
+        ++c.launches;
+    } else {
+        c.rk4_dbac = 0.5 * bf * dt;
+    }
+}
+
 static void rk4_factors(Ctx& c) {                               // impl_rk4.f90:87-89
     if (!c.rk4_dfac_set) fail(PS3D_ERR_NOT_INITIALISED, "set_diffusion has not been called");
     const long long ncol = (long long)c.nx * c.nyl;
     PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 1, c.rk4_dfac, (const double*)c.vhdis.p,
               (const double*)c.filt2d.p, c.fac1.p, c.fac2.p, ncol);
     ++c.launches;
+    if (c.buoyancy) {                                           // bpq, bmq (:91-95)
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, 1, c.rk4_dbac, (const double*)c.bhdis.p,
+                  (const double*)c.filt2d.p, c.bfac1.p, c.bfac2.p, ncol);
+        ++c.launches;
+    }
 }
 
 static StepArgs step_args(Ctx& c) {
@@ -1187,6 +1260,14 @@ static StepArgs step_args(Ctx& c) {
     a.f2d = c.fac2.p; a.filtz = c.filtz.p; a.mq = c.fac1.p; a.pq = c.fac2.p; a.vd = c.fac1.p;
     a.c1 = a.c2 = 0.0; a.stage = 0;
     a.ncol = (long long)c.nx * c.nyl; a.nz = c.nz; a.pz = c.pz; a.has00 = (c.rank == 0);
+    return a;
+}
+
+static StepArgs buoy_step_args(Ctx& c) {
+    StepArgs a = step_args(c);
+    a.svor[0] = c.sbuoy.p; a.svorts[0] = c.sbuoys.p; a.wa[0] = c.bsm.p; a.wb[0] = c.sbuoyf.p;
+    a.f2d = c.bfac2.p; a.mq = c.bfac1.p; a.pq = c.bfac2.p; a.vd = c.bfac1.p;
+    a.ncomp = 1;
     return a;
 }
 
@@ -1200,6 +1281,7 @@ static void do_stepper_setup(Ctx& c, int stepper) {
         if (!c.wa[i].p) c.wa[i].alloc(c.nint);
         if (stepper == PS3D_STEPPER_IMPL_RK4 && !c.wb[i].p) c.wb[i].alloc(c.nint);
     }
+    if (c.buoyancy && stepper == PS3D_STEPPER_IMPL_RK4 && !c.sbuoyf.p) c.sbuoyf.alloc(c.nint);    // impl_rk4.f90:67-72
     c.stepper_ready = true;
 }
 
@@ -1211,7 +1293,22 @@ static void cn2_update(Ctx& c, double dt2, int stage) {
     vor_mean(c, 1);
 }
 
+// sbuoy update of cn2_step (cn2.f90:107-117 stage 0, :151-160 stage 1), combine -> bdiss -> decompose collapsed
+static void cn2_update_buoy(Ctx& c, double dt2, int stage) {
+    if (!c.buoyancy) return;
+    StepArgs a = buoy_step_args(c);
+    a.c1 = dt2; a.stage = stage;
+    PS_LAUNCH((k_cn2_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, a);
+    ++c.launches;
+}
+
 static void rk4_update(Ctx& c, int stage, double c1, double c2, const double* pq) {
+    if (c.buoyancy) {                                  // sbuoy first (impl_rk4.f90:99-105, 124-131, 154-164, 187-195)
+        StepArgs b = buoy_step_args(c);
+        b.c1 = c1; b.c2 = c2; b.stage = stage; b.pq = (stage == 1) ? pq : c.bfac2.p;
+        PS_LAUNCH((k_rk4_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, b);
+        ++c.launches;
+    }
     StepArgs a = step_args(c);
     a.c1 = c1; a.c2 = c2; a.stage = stage; a.pq = pq;
     PS_LAUNCH((k_rk4_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, a);
@@ -1223,6 +1320,11 @@ static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 /
     PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, mode, 0.0, (const double*)nullptr,
               (const double*)nullptr, c.fac1.p, c.fac2.p, ncol);
     ++c.launches;
+    if (c.buoyancy) {                                          // bmq = bmq**2 / bpq = bpq**2 (:155, :188)
+        PS_LAUNCH((k_step_factors), dim3(stream_blocks(ncol)), dim3(256), 0, c.stream, mode, 0.0, (const double*)nullptr,
+                  (const double*)nullptr, c.bfac1.p, c.bfac2.p, ncol);
+        ++c.launches;
+    }
 }
 
 // the cn2 update can ride on the source kernel (power-of-two nz; PS3D_NO_FUSED_UPDATE=1 keeps it separate)
@@ -1233,13 +1335,15 @@ static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false
     if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
     if (c.stepper == PS3D_STEPPER_CN2) {
         const double dt2 = 0.5 * dt;                       // cn2.f90:101
-        if (!first_update_done) cn2_update(c, dt2, 0);     // :120-137
+        if (!first_update_done) { cn2_update_buoy(c, dt2, 0); cn2_update(c, dt2, 0); }     // :107-137
         for (int iter = 0; iter < 2; ++iter) {             // niter = 2 (:34, :143-177)
             do_vor2vel(c);
             if (cn2_fused(c)) {
                 do_source(c, 1, dt2);
+                cn2_update_buoy(c, dt2, 1);                // (its operands sbuoys / bsm are untouched by the source kernel)
             } else {
                 do_source(c);
+                cn2_update_buoy(c, dt2, 1);
                 cn2_update(c, dt2, 1);
             }
         }
@@ -1327,8 +1431,26 @@ static void allreduce_dev(Ctx& c, double* red, int n, unsigned opmask) {
     ps_sync(c.stream);
 }
 
+// bfmax (advance.f90:147-168): the three gradient components of b' in physical space, max of |grad b + N^2 z^|^2
+// -> red[RQ_N + 5] (the fourth root is taken on the host)
+static void do_bfmax(Ctx& c) {
+    const long long ncol = (long long)c.nxl * c.ny;
+    launch_zop(c, ZOP_COMBINE, c.sbuoy.p, c.bsem.p);                 // field_combine_semi_spectral(sbuoy) (:150)
+    fft2d_inv(c, c.bsem.p, c.W[0].p, true, false);                   // diffx + fftxys2p (:151-152)
+    fft2d_inv(c, c.bsem.p, c.W[1].p, false, true);                   // diffy + fftxys2p (:154-155)
+    launch_zop(c, ZOP_DIFFZ, c.bsem.p, c.W[3].p);                    // central_diffz (:157)
+    fft2d_inv(c, c.W[3].p, c.W[2].p, false, false);                  // (:158)
+    PS_LAUNCH((k_bfmax), dim3(c.red_blocks), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              (const double*)c.W[0].p, (const double*)c.W[1].p, (const double*)c.W[2].p, c.bfsq, ncol, c.nz, c.pz, c.partial.p);
+    PS_LAUNCH((k_reduce_final), dim3(1), dim3(RED_THREADS), RED_THREADS * sizeof(double), c.stream,
+              (const double*)c.partial.p, c.red_blocks, 1, 1u, c.red.p + RQ_N + 5);
+    c.launches += 2;
+    allreduce_dev(c, c.red.p + RQ_N + 5, 1, 1u);                     // buf(1) of the MPI_MAX reduction (:291-305)
+}
+
 static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype, int win, double* dt_out, double* diag) {
     const long long ncol = (long long)c.nxl * c.ny;
+    if (c.buoyancy) do_bfmax(c);
     // first reduction (advance.f90:171-185, 285-313) -> red[0..RQ_N), reduced over the ranks on the device
     field_reduce(c);
     allreduce_dev(c, c.red.p, RQ_N, RQ_OPMASK);             // advance.f90:299-305, field_diagnostics.f90:418-424
@@ -1346,7 +1468,7 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     c.launches += 2;
     allreduce_dev(c, c.red.p + RQ_N, 5, 7u);                // sums: vorl1, vorl2 (field_diagnostics.f90:529-535); max: strain
     // the one device -> host read of the step
-    ps_d2h(c.h_red, c.red.p, (RQ_N + 5) * sizeof(double), c.stream);
+    ps_d2h(c.h_red, c.red.p, (RQ_N + 6) * sizeof(double), c.stream);
     ps_sync(c.stream);
     double r1[RQ_N];
     for (int i = 0; i < RQ_N; ++i) r1[i] = c.h_red[i];
@@ -1357,7 +1479,7 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     // vorl1 starts from `small` on every rank before the reduction (field_diagnostics.f90:509,529-535)
     const double vorl1 = small * (double)c.nranks + h2[3], vorl2 = h2[4];
     const double vorch = vorl2 / vorl1;
-    const double bfmax = 0.0;
+    const double bfmax = c.buoyancy ? std::sqrt(std::sqrt(h2[5])) : 0.0;    // advance.f90:145, 167
     const double ggmax = std::max(2.220446049250313e-16, h2[0]);   // ggmax = epsilon(ggmax) (advance.f90:222)
     const double usggmax = std::max(0.0, h2[1]), lsggmax = std::max(0.0, h2[2]);
     const double umax = r1[RQ_MAXU], vmax = r1[RQ_MAXV], wmax = r1[RQ_MAXWV];
@@ -1366,18 +1488,31 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
     const double dt = std::min(std::min(alpha / (ggmax + small), alpha / (bfmax + small)), std::min(dtcfl, t_limit - t));
     if (!c.rollmean.alloc(win))
         fail(PS3D_ERR_BAD_ARGUMENT, "roll_mean_win_size changed from %d to %d (rolling_mean.f90: allocated once)", c.rollmean.length, win);
-    const double rmv = c.rollmean.get_next(ggmax);
-    double pref;
-    switch (pretype) {                                             // advance.f90:385-408
-        case PS3D_PRE_CONSTANT: pref = 1.0; break;
-        case PS3D_PRE_VORCH: pref = vorch; break;
-        case PS3D_PRE_BFMAX: pref = bfmax; break;
-        case PS3D_PRE_ROLL_MEAN_MAX_STRAIN: pref = rmv; break;
-        case PS3D_PRE_MAX_STRAIN: pref = ggmax; break;
-        case PS3D_PRE_US_MAX_STRAIN: pref = usggmax; break;
-        default: fail(PS3D_ERR_BAD_ARGUMENT, "We only support 'constant', 'vorch', 'bfmax', 'roll-mean-max-strain', "
-                                             "'max-strain' and us-max-strain");
+    double rmb = 0.0;
+    if (c.buoyancy) {                                              // advance.f90:358-362
+        if (!c.bdiffusion_ready) fail(PS3D_ERR_NOT_INITIALISED, "init_diffusion_buoyancy has not been called");
+        if (!c.buoy_rollmean.alloc(c.bwin))
+            fail(PS3D_ERR_BAD_ARGUMENT, "buoyancy roll_mean_win_size changed (rolling_mean.f90: allocated once)");
+        rmb = c.buoy_rollmean.get_next(bfmax);
     }
+    const double rmv = c.rollmean.get_next(ggmax);
+    auto prefactor = [&](int type) -> double {                     // get_diffusion_pre_factor (advance.f90:381-410)
+        switch (type) {
+            case PS3D_PRE_CONSTANT: return 1.0;
+            case PS3D_PRE_VORCH: return vorch;
+            case PS3D_PRE_BFMAX: return bfmax;
+            case PS3D_PRE_ROLL_MEAN_MAX_STRAIN: return rmv;
+            case PS3D_PRE_MAX_STRAIN: return ggmax;
+            case PS3D_PRE_US_MAX_STRAIN: return usggmax;
+            case PS3D_PRE_ROLL_MEAN_BFMAX: if (c.buoyancy) return rmb; break;      // (#ifdef ENABLE_BUOYANCY, :395-398)
+            default: break;
+        }
+        fail(PS3D_ERR_BAD_ARGUMENT, "We only support 'constant', 'vorch', 'bfmax', 'roll-mean-max-strain', "
+                                    "'roll-mean-bfmax', 'max-strain' and us-max-strain");
+    };
+    const double pref = prefactor(pretype);                        // vval (:370)
+    const double bval = c.buoyancy ? prefactor(c.bpretype) : 0.0;  // bval (:372-374)
+    c.last_bdiag[0] = bfmax; c.last_bdiag[1] = rmb; c.last_bdiag[2] = bval; c.last_bdiag[3] = c.bvisc;
     if (diag) {
         const double ncelli = 1.0 / (double)c.ncell;
         diag[PS3D_D_VORTMAX] = vortmax; diag[PS3D_D_VORTRMS] = vortrms; diag[PS3D_D_VORCH] = vorch;
@@ -1399,7 +1534,10 @@ static void do_adapt(Ctx& c, double t, double t_limit, double alpha, int pretype
         c.have_diag = true;
     }
     *dt_out = dt;
-    if (c.stepper_ready && c.diffusion_ready) do_set_diffusion(c, dt, pref);     // advance.f90:375
+    if (c.stepper_ready && c.diffusion_ready) {                                  // advance.f90:375
+        do_set_diffusion(c, dt, pref);
+        do_set_diffusion_buoyancy(c, dt, bval);
+    }
 }
 
 static void do_upload_vorticity(Ctx& c, const double* vor_phys) {
@@ -1423,6 +1561,16 @@ static void do_pressure(Ctx& c) {
               (const double*)c.W[1].p, (const double*)c.W[3].p, (const double*)c.W[2].p, (const double*)c.W[4].p,
               (const double*)c.vor[0].p, (const double*)c.vor[1].p, (const double*)c.vor[2].p, c.W[0].p, n);
     ++c.launches;
+    if (c.buoyancy) {
+        // pres = pres + dbdz + f_cor(3) * zeta (fields_derived.f90:108-112); central_diffz commutes with the x/y
+        // transform, so db/dz is taken on the semi-spectral b' and brought to physical space
+        launch_zop(c, ZOP_COMBINE, c.sbuoy.p, c.bsem.p);
+        launch_zop(c, ZOP_DIFFZ, c.bsem.p, c.W[2].p);
+        fft2d_inv(c, c.W[2].p, c.W[1].p, false, false);
+        PS_LAUNCH((k_add_axpy), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)c.W[0].p,
+                  (const double*)c.W[1].p, c.f_cor[2], (const double*)c.vor[2].p, c.W[0].p, n);
+        ++c.launches;
+    }
     fft2d_fwd(c, c.W[0].p, c.W[1].p);
     launch_zop(c, ZOP_POISSON, c.W[1].p, c.W[2].p);
     fft2d_inv(c, c.W[2].p, c.W[0].p, false, false);
@@ -1505,6 +1653,12 @@ int ps3d_cuda_fftcosine(double* fs) { PS_API_BEGIN zop_host(ZOP_COSINE, fs, fs);
 int ps3d_cuda_diffx(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFX, fs, ds); PS_API_END }
 int ps3d_cuda_diffy(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFY, fs, ds); PS_API_END }
 int ps3d_cuda_central_diffz(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFZ, fs, ds); PS_API_END }
+int ps3d_cuda_diffz(const double* fs, double* ds) {        // mixed-spectral in, mixed-spectral out (buoyancy build)
+    PS_API_BEGIN
+    if (ready().gen[2]) fail(PS3D_ERR_UNSUPPORTED, "diffz: nz must be a power of two");
+    zop_host(ZOP_DIFFZ_SPEC, fs, ds);
+    PS_API_END
+}
 int ps3d_cuda_field_combine_semi_spectral(double* sf) { PS_API_BEGIN zop_host(ZOP_COMBINE, sf, sf); PS_API_END }
 int ps3d_cuda_field_decompose_semi_spectral(double* sfc) { PS_API_BEGIN zop_host(ZOP_DECOMPOSE, sfc, sfc); PS_API_END }
 
@@ -1540,6 +1694,75 @@ int ps3d_cuda_adapt(double t, double t_limit, double alpha, int pretype_id, int 
     PS_API_END
 }
 
+int ps3d_cuda_set_physics(const double f_cor[3], double bfsq) {
+    PS_API_BEGIN
+    Ctx& c = ctx();
+    if (!f_cor) fail(PS3D_ERR_BAD_ARGUMENT, "f_cor is null");
+    for (int i = 0; i < 3; ++i) c.f_cor[i] = f_cor[i];
+    c.bfsq = bfsq;
+    PS_API_END
+}
+
+int ps3d_cuda_enable_buoyancy(void) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (c.buoyancy) return PS3D_OK;
+    if (c.gen[2]) fail(PS3D_ERR_UNSUPPORTED, "buoyancy build: nz = %d is not a power of two (no coverage kernel for the spectral diffz)", c.nz);
+    DevBuf<double>* f[] = {&c.sbuoy, &c.buoy, &c.sbuoys, &c.bsm, &c.bsem};
+    for (auto* b : f) { b->alloc(c.nint); ps_memset(b->p, 0, c.nint * sizeof(double), c.stream); }
+    const size_t ncol = (size_t)c.nx * c.nyl;
+    c.bhdis.alloc(ncol); c.bfac1.alloc(ncol); c.bfac2.alloc(ncol);
+    if (c.stepper_ready && c.stepper == PS3D_STEPPER_IMPL_RK4) c.sbuoyf.alloc(c.nint);
+    ps_sync(c.stream);
+    c.buoyancy = true;
+    PS_API_END
+}
+
+int ps3d_cuda_upload_buoyancy(const double* buoy_phys) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!c.buoyancy) fail(PS3D_ERR_NOT_INITIALISED, "enable_buoyancy has not been called");
+    if (!buoy_phys) fail(PS3D_ERR_BAD_ARGUMENT, "buoy_phys is null");
+    to_device(c, buoy_phys, c.buoy.p, false);                 // utils.f90:158 field_decompose_physical(buoy, sbuoy)
+    fft2d_fwd(c, c.buoy.p, c.W[0].p);
+    launch_zop(c, ZOP_DECOMPOSE, c.W[0].p, c.sbuoy.p);
+    ps_sync(c.stream);
+    PS_API_END
+}
+
+int ps3d_cuda_init_diffusion_buoyancy(int nnu, double prediss, int length_scale_id, double te, double en, int pretype_id,
+                                      int roll_mean_win_size, double* nu_out) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!c.buoyancy) fail(PS3D_ERR_NOT_INITIALISED, "enable_buoyancy has not been called");
+    if (roll_mean_win_size < 1) fail(PS3D_ERR_BAD_ARGUMENT, "roll_mean_win_size must be >= 1");
+    if (pretype_id < PS3D_PRE_CONSTANT || pretype_id > PS3D_PRE_ROLL_MEAN_BFMAX) fail(PS3D_ERR_BAD_ARGUMENT, "unknown pretype id %d", pretype_id);
+    std::vector<double> vh;
+    c.bvisc = viscosity_table(c, nnu, prediss, length_scale_id, te, en, vh);     // inversion_utils.f90:144-151
+    c.bnnu = nnu; c.bpretype = pretype_id; c.bwin = roll_mean_win_size;
+    c.bhdis.upload(vh, c.stream);
+    c.bdiffusion_ready = true;
+    if (nu_out) *nu_out = c.bvisc;
+    PS_API_END
+}
+
+int ps3d_cuda_set_diffusion_buoyancy(double dt, double bf) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!c.buoyancy) fail(PS3D_ERR_NOT_INITIALISED, "enable_buoyancy has not been called");
+    do_set_diffusion_buoyancy(c, dt, bf);
+    ps_sync(c.stream);
+    PS_API_END
+}
+
+int ps3d_cuda_buoyancy_diag(double out[4]) {
+    PS_API_BEGIN
+    Ctx& c = ready();
+    if (!out) fail(PS3D_ERR_BAD_ARGUMENT, "out is null");
+    for (int i = 0; i < 4; ++i) out[i] = c.last_bdiag[i];
+    PS_API_END
+}
+
 int ps3d_cuda_stepper_setup(int stepper_id) { PS_API_BEGIN do_stepper_setup(ready(), stepper_id); PS_API_END }
 int ps3d_cuda_set_diffusion(double dt, double pref) { PS_API_BEGIN Ctx& c = ready(); do_set_diffusion(c, dt, pref); ps_sync(c.stream); PS_API_END }
 int ps3d_cuda_step(double* t, double dt) { PS_API_BEGIN Ctx& c = ready(); if (!t) fail(PS3D_ERR_BAD_ARGUMENT, "t is null"); do_step(c, t, dt); ps_sync(c.stream); PS_API_END }
@@ -1558,6 +1781,7 @@ int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, i
     do_adapt(c, *t, t_limit, alpha, pretype_id, win, &dt, diag_out);   // :88
     if (cn2_fused(c)) {
         do_source(c, 0, 0.5 * dt);                     // :95 + the first update of cn2_step (cn2.f90:120-137)
+        cn2_update_buoy(c, 0.5 * dt, 0);               // cn2.f90:107-117
         do_step(c, t, dt, true);                       // :102
     } else {
         do_source(c);                                  // :95
@@ -1597,6 +1821,16 @@ int ps3d_cuda_download(int field_id, int comp, double* host) {
         to_host(c, c.W[0].p, host, false);
         return PS3D_OK;
     }
+    if (field_id == PS3D_F_SBUOY || field_id == PS3D_F_BUOY || field_id == PS3D_F_SBUOYS) {
+        if (!c.buoyancy) fail(PS3D_ERR_NOT_INITIALISED, "enable_buoyancy has not been called");
+        if (field_id == PS3D_F_BUOY) {                 // field_combine_physical(sbuoy, buoy) (field_diagnostics_netcdf.f90:275)
+            launch_zop(c, ZOP_COMBINE, c.sbuoy.p, c.bsem.p);
+            fft2d_inv(c, c.bsem.p, c.buoy.p, false, false);
+        }
+        to_host(c, field_id == PS3D_F_SBUOY ? c.sbuoy.p : field_id == PS3D_F_BUOY ? c.buoy.p : c.sbuoys.p, host,
+                field_id != PS3D_F_BUOY);
+        return PS3D_OK;
+    }
     bool spectral = false;
     DevBuf<double>* f = field_by_id(c, field_id, spectral);
     if (!f || comp < 0 || comp > 2) fail(PS3D_ERR_BAD_ARGUMENT, "bad field id %d / component %d", field_id, comp);
@@ -1610,6 +1844,12 @@ int ps3d_cuda_download(int field_id, int comp, double* host) {
 int ps3d_cuda_upload(int field_id, int comp, const double* host) {
     PS_API_BEGIN
     Ctx& c = ready();
+    if ((field_id == PS3D_F_SBUOY || field_id == PS3D_F_SBUOYS) && host) {
+        if (!c.buoyancy) fail(PS3D_ERR_NOT_INITIALISED, "enable_buoyancy has not been called");
+        to_device(c, host, field_id == PS3D_F_SBUOY ? c.sbuoy.p : c.sbuoys.p, true);
+        ps_sync(c.stream);
+        return PS3D_OK;
+    }
     bool spectral = false;
     DevBuf<double>* f = field_by_id(c, field_id, spectral);
     if (!f || comp < 0 || comp > 2 || !host) fail(PS3D_ERR_BAD_ARGUMENT, "bad field id %d / component %d", field_id, comp);
@@ -1682,7 +1922,7 @@ int ps3d_cuda_field_stats(double out[40]) {
     const double nxy = (double)c.nx * (double)c.ny;
     out[PS3D_NC_USZRMS] = std::sqrt(r2[SQ_USZ2] / nxy);
     out[PS3D_NC_USDELRMS] = std::sqrt(r2[SQ_USDEL2] / nxy);
-    const double fcor3 = 0.0;                        // physics.f90 f_cor(3): zero for the configurations in scope
+    const double fcor3 = c.f_cor[2];                 // physics.f90:163-169 (ps3d_cuda_set_physics; 0 by default)
     out[PS3D_NC_ROMIN] = out[PS3D_NC_OZMIN] / fcor3; // field_diagnostics.f90:297-298
     out[PS3D_NC_ROMAX] = out[PS3D_NC_OZMAX] / fcor3; // :313-314
     // handed over by adapt (advance.f90:188-193, 315-321, 366)

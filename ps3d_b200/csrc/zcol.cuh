@@ -464,7 +464,16 @@ __device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int ki
 // field_combine_semi_spectral, field_decompose_semi_spectral).  General
 // instantiation for every group (this is the host-boundary path, not the hot loop).
 // ---------------------------------------------------------------------------
-enum { ZOP_SINE = 0, ZOP_COSINE, ZOP_COMBINE, ZOP_DECOMPOSE, ZOP_DIFFZ, ZOP_DIFFX, ZOP_DIFFY, ZOP_POISSON };
+enum { ZOP_SINE = 0, ZOP_COSINE, ZOP_COMBINE, ZOP_DECOMPOSE, ZOP_DIFFZ, ZOP_DIFFX, ZOP_DIFFY, ZOP_POISSON,
+       ZOP_DIFFZ_SPEC };     // spectral d/dz of a mixed-spectral field (diffz, inversion_utils.f90:683-719; buoyancy build)
+
+// dphim, dphip of one row (inversion_utils.f90:520-521; (0,0): -1/Lz, +1/Lz, :333-336) from phim, phip
+__device__ __forceinline__ void hyp_dphi(const Hyp& h, double Lz, double phim, double phip, double& dpm, double& dpp) {
+    if (h.lin) { dpm = -1.0 / Lz; dpp = 1.0 / Lz; return; }
+    const double ep = phim + h.ef * phip, em = phip + h.ef * phim;
+    dpm = -h.kl * h.div * (ep + h.ef * em);
+    dpp = h.kl * h.div * (em + h.ef * ep);
+}
 
 template <int NZ>
 constexpr size_t zop_smem_bytes() { return (size_t)(ZCfg<NZ>::BUF + ZCfg<NZ>::aux(true)) * sizeof(double); }
@@ -479,7 +488,66 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
     const ZScr<NZ> scr = make_scr<NZ, GEN>(X + BUF);
     scr_init<NZ>(scr, g);
     const Grp r = make_grp<GEN>(g, blockIdx.x);
-    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE) phi_fill<NZ, GEN>(scr, g, r);
+    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE || op == ZOP_DIFFZ_SPEC) phi_fill<NZ, GEN>(scr, g, r);
+    if (op == ZOP_DIFFZ_SPEC) {
+        // diffz (inversion_utils.f90:683-719): ds = fs(0) dphim + fs(nz) dphip + cosine(rkz * fs), then decompose
+        double f0[4], fn[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            f0[s] = (s < 2 || !r.dupx) ? in[r.off[s]] : 0.0;
+            fn[s] = (s < 2 || !r.dupx) ? in[r.off[s] + NZ] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            Row4 x = row_load_g<NZ>(in, r, z);
+            const double rk = (z >= 1 && z < NZ) ? __ldg(&g.rkz[z]) : 0.0;          // as(0) = as(nz) = 0
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x.v[s] *= rk;
+            row_store_s<NZ>(X, z, x);
+        }
+        __syncthreads();
+        xform2<NZ>(X, XF_DCT, nullptr, XF_DST, scr);
+        Hyp h[2];
+        h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            Row4 x = row_load_s<NZ>(X, z);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                double dpm, dpp;
+                hyp_dphi(h[s & 1], g.Lz, phim_of<NZ, GEN>(scr, z, s), phip_of<NZ, GEN>(scr, z, s), dpm, dpp);
+                x.v[s] += f0[s] * dpm + fn[s] * dpp;
+            }
+            row_store_s<NZ>(X, z, x);
+        }
+        __syncthreads();
+        // field_decompose_semi_spectral (:563-592): remove the harmonic part defined by the boundary rows, sine transform
+        double d0[4], dn[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { d0[s] = X[s * LC + cz(0)]; dn[s] = X[s * LC + cz(NZ)]; }
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 1 || z >= NZ) continue;
+            Row4 x = row_load_s<NZ>(X, z);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x.v[s] -= d0[s] * phim_of<NZ, GEN>(scr, z, s) + dn[s] * phip_of<NZ, GEN>(scr, z, s);
+            row_store_s<NZ>(X, z, x);
+        }
+        __syncthreads();
+        xform2<NZ>(X, XF_DST, nullptr, XF_DST, scr);
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int z = my_row<NZ>(it);
+            if (z < 0) continue;
+            row_store_g<NZ>(out, r, z, row_load_s<NZ>(X, z));
+        }
+        return;
+    }
     if (op == ZOP_DIFFX || op == ZOP_DIFFY) {
 #pragma unroll
         for (int it = 0; it < 3; ++it) {

@@ -11,8 +11,10 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libps3d_cud
 FILTER = {"Hou & Li": 0, "2/3-rule": 1}
 LSCALE = {"Kolmogorov": 0, "geophysical": 1}
 STEPPER = {"cn2": 0, "impl-diff-rk4": 1}
-PRETYPE = {"constant": 0, "vorch": 1, "bfmax": 2, "roll-mean-max-strain": 3, "max-strain": 4, "us-max-strain": 5}
-FIELD = {"svor": 0, "vor": 1, "vel": 2, "svel": 3, "svorts": 4, "pres": 5, "delta": 6}
+PRETYPE = {"constant": 0, "vorch": 1, "bfmax": 2, "roll-mean-max-strain": 3, "max-strain": 4, "us-max-strain": 5,
+           "roll-mean-bfmax": 6}
+FIELD = {"svor": 0, "vor": 1, "vel": 2, "svel": 3, "svorts": 4, "pres": 5, "delta": 6, "sbuoy": 7, "buoy": 8,
+         "sbuoys": 9}
 DIAG = ["vortmax", "vortrms", "vorch", "vormean_x", "vormean_y", "vormean_z", "bfmax", "ggmax", "umax", "vmax",
         "wmax", "usggmax", "lsggmax", "rmv", "dt", "prefactor"]
 
@@ -39,6 +41,7 @@ _SIGNATURES = {
     "ps3d_cuda_diffx": [_dp, _dp],
     "ps3d_cuda_diffy": [_dp, _dp],
     "ps3d_cuda_central_diffz": [_dp, _dp],
+    "ps3d_cuda_diffz": [_dp, _dp],
     "ps3d_cuda_field_combine_semi_spectral": [_dp],
     "ps3d_cuda_field_decompose_semi_spectral": [_dp],
     "ps3d_cuda_field_combine_physical": [_dp, _dp],
@@ -57,10 +60,16 @@ _SIGNATURES = {
     "ps3d_cuda_time_kernel": [C.c_int, C.c_int, _dp],
     "ps3d_cuda_set_transport": [C.c_void_p, C.c_void_p, C.c_void_p],
     "ps3d_cuda_comm_stats": [C.POINTER(C.c_longlong), _dp],
+    "ps3d_cuda_set_physics": [_dp, C.c_double],
+    "ps3d_cuda_enable_buoyancy": [],
+    "ps3d_cuda_upload_buoyancy": [_dp],
+    "ps3d_cuda_init_diffusion_buoyancy": [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _dp],
+    "ps3d_cuda_set_diffusion_buoyancy": [C.c_double, C.c_double],
+    "ps3d_cuda_buoyancy_diag": [_dp],
 }
 ALLTOALL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _dp, C.c_int, C.c_int, C.c_void_p)
-SPECTRAL_FIELDS = ("svor", "svel", "svorts")
+SPECTRAL_FIELDS = ("svor", "svel", "svorts", "sbuoy", "sbuoys")
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ps3d_cuda_last_error", "ps3d_cuda_kernel_launches",
                                                "ps3d_cuda_tma_launches", "ps3d_cuda_last_advance_ms"])
 
@@ -126,6 +135,31 @@ class PS3DLib:
         self._call("ps3d_cuda_init_diffusion", nnu, prediss, LSCALE[length_scale], te, en, C.byref(nu))
         return nu.value
 
+    # ---- physics.f90 / the ENABLE_BUOYANCY build ----
+    def set_physics(self, f_cor=(0.0, 0.0, 0.0), bfsq=0.0):
+        fc = _in(f_cor)
+        self._call("ps3d_cuda_set_physics", _ptr(fc), bfsq)
+
+    def enable_buoyancy(self): self._call("ps3d_cuda_enable_buoyancy")
+
+    def upload_buoyancy(self, buoy):
+        buoy = _in(buoy)
+        assert buoy.shape == self.shape, (buoy.shape, self.shape)
+        self._call("ps3d_cuda_upload_buoyancy", _ptr(buoy))
+
+    def init_diffusion_buoyancy(self, te, en, nnu=3, prediss=30.0, length_scale="Kolmogorov", pretype="vorch", win=1000):
+        nu = C.c_double(0.0)
+        self._call("ps3d_cuda_init_diffusion_buoyancy", nnu, prediss, LSCALE[length_scale], te, en, PRETYPE[pretype], win,
+                   C.byref(nu))
+        return nu.value
+
+    def set_diffusion_buoyancy(self, dt, bf): self._call("ps3d_cuda_set_diffusion_buoyancy", dt, bf)
+
+    def buoyancy_diag(self):
+        out = np.zeros(4)
+        self._call("ps3d_cuda_buoyancy_diag", _ptr(out))
+        return dict(bfmax=out[0], rmb=out[1], bval=out[2], bvisc=out[3])
+
     def finalise(self):
         self._call("ps3d_cuda_finalise")
         self.shape = None
@@ -149,6 +183,7 @@ class PS3DLib:
     def diffx(self, fs): return self._op2("ps3d_cuda_diffx", fs)
     def diffy(self, fs): return self._op2("ps3d_cuda_diffy", fs)
     def central_diffz(self, fs): return self._op2("ps3d_cuda_central_diffz", fs)
+    def diffz(self, fs): return self._op2("ps3d_cuda_diffz", fs)
     def field_combine_semi_spectral(self, sf): return self._op1("ps3d_cuda_field_combine_semi_spectral", sf)
     def field_decompose_semi_spectral(self, sf): return self._op1("ps3d_cuda_field_decompose_semi_spectral", sf)
     def field_combine_physical(self, sf): return self._op2("ps3d_cuda_field_combine_physical", sf)
