@@ -124,6 +124,13 @@ module ps3d_cuda_mod
             import :: c_int, c_double
             real(c_double), intent(in) :: vor(*)     ! vor(0:nz, lo2:hi2, lo1:hi1, 3) of fields.f90:62
         end function
+        integer(c_int) function ps3d_cuda_upload_vorticity_begin(vor) bind(C, name='ps3d_cuda_upload_vorticity_begin')
+            import :: c_int, c_double
+            real(c_double), intent(in) :: vor(*)     ! asynchronous: keep `vor` untouched until ..._end
+        end function
+        integer(c_int) function ps3d_cuda_upload_vorticity_end() bind(C, name='ps3d_cuda_upload_vorticity_end')
+            import :: c_int
+        end function
         integer(c_int) function ps3d_cuda_vor2vel() bind(C, name='ps3d_cuda_vor2vel')
             import :: c_int
         end function

@@ -95,6 +95,12 @@ int ps3d_cuda_field_decompose_physical(const double* fc, double* sf); /* inversi
 /* ---- resident mode: state lives in HBM (what the time loop uses) ---- */
 /* setup_fields (utils.f90:160-165): vor(0:nz,y,x,1:3) -> decompose x3, ini_vor_mean */
 int ps3d_cuda_upload_vorticity(const double* vor_phys);
+/* Streamed form of ps3d_cuda_upload_vorticity for hosts that hand over a new state while the device is busy:
+ * _begin queues the host -> device copies of the three components on a copy stream (vor_phys must stay valid and
+ * should be pinned) and returns at once -- they overlap a running ps3d_cuda_advance of the previous state; _end
+ * waits for them and decomposes (utils.f90:160-165).  The state is replaced only by _end. */
+int ps3d_cuda_upload_vorticity_begin(const double* vor_phys);
+int ps3d_cuda_upload_vorticity_end(void);
 int ps3d_cuda_vor2vel(void);                                          /* inversion.f90:23 */
 int ps3d_cuda_source(void);                                           /* inversion.f90:378 */
 /* adapt (advance.f90:109) incl. bstep%set_diffusion; pressure/divergence are lazy (see download) */

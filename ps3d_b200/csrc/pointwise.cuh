@@ -416,11 +416,20 @@ __global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, int stric
         const double o0 = f.vor[0][i], o1 = f.vor[1][i], o2 = f.vor[2][i];
         // advance.f90:252-257
         const double s12 = uy + 0.5 * o2, s13 = wx + 0.5 * o1, s23 = wy - 0.5 * o0;
-        const double l = strict ? jacobi_max_abs(ux, s12, s13, vy, s23, -(ux + vy))
-                                : sym3_max_abs(ux, s12, s13, vy, s23, -(ux + vy));
-        gg = fmax(gg, l);
-        if (z == nz) us = fmax(us, l);
-        if (z == 0) ls = fmax(ls, l);
+        // Only the maximum over the grid is wanted: the matrix is symmetric and traceless, so lambda_max^2 <= 2/3 |S|_F^2,
+        // and a point whose bound does not exceed this thread's running maximum cannot raise it.  The eigenvalues
+        // are evaluated only where it can (and on the two surfaces, which have their own maxima): same result,
+        // the pass becomes a streaming read.
+        const double s33 = -(ux + vy);
+        const double fro = ux * ux + vy * vy + s33 * s33 + 2.0 * (s12 * s12 + s13 * s13 + s23 * s23);
+        const bool surf = (z == nz) || (z == 0);
+        if (surf || fro * (2.0 / 3.0) * (1.0 + 1.0e-9) > gg * gg) {
+            const double l = strict ? jacobi_max_abs(ux, s12, s13, vy, s23, s33)
+                                    : sym3_max_abs(ux, s12, s13, vy, s23, s33);
+            gg = fmax(gg, l);
+            if (z == nz) us = fmax(us, l);
+            if (z == 0) ls = fmax(ls, l);
+        }
         if (red && z >= 1) {
             const double v1 = 0.5 * fabs(f.vor[0][i - 1] + o0);
             const double v2 = 0.5 * fabs(f.vor[1][i - 1] + o1);

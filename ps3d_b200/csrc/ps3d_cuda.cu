@@ -35,6 +35,38 @@ void set_error(const char* fmt, ...) {
     g_last_error = buf;
 }
 
+#ifndef PS3D_EMU
+// ---- PS3D_TRACE: in-situ kernel times (rt.h) ----
+int g_trace = 0;
+struct TraceRec { const char* name; cudaEvent_t a, b; };
+static std::vector<TraceRec> g_trace_recs;
+void ps_trace_begin(const char* name, cudaStream_t s) {
+    TraceRec r{name, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_trace_recs.push_back(r);
+}
+void ps_trace_end(cudaStream_t s) { cudaEventRecord(g_trace_recs.back().b, s); }
+static void trace_dump() {
+    if (!g_trace || g_trace_recs.empty()) return;
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<int, double>> agg;
+    double tot = 0.0;
+    for (auto& r : g_trace_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& a = agg[r.name]; a.first++; a.second += ms; tot += ms; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    std::vector<std::pair<std::string, std::pair<int, double>>> v(agg.begin(), agg.end());
+    std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.second.second > y.second.second; });
+    fprintf(stderr, "PS3D_TRACE: %zu launches, %.3f ms between event pairs\n", g_trace_recs.size(), tot);
+    for (auto& e : v)
+        fprintf(stderr, "PS3D_TRACE %-60s n=%6d total=%10.3f ms avg=%9.4f ms (%5.1f%%)\n", e.first.c_str(), e.second.first,
+                e.second.second, e.second.second / e.second.first, 100.0 * e.second.second / tot);
+    g_trace_recs.clear();
+}
+#endif
+
 struct StatusError { int code; };
 [[noreturn]] static void fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -154,6 +186,14 @@ struct Ctx {
     DevBuf<double> redS, redM;            // all-reduce landing buffers (sum / max)
     PeerMailPtrs mail;                    // every rank's mailbox (peer-mapped), valid when tr.p2p
     DevBuf<double> stage;                 // natural-layout staging for the host boundary
+    // streamed upload (ps3d_cuda_upload_vorticity_begin / _end): three staging fields filled by a copy stream while
+    // the compute stream works on the previous state
+    DevBuf<double> stage3;
+    ps_stream_t copy_stream = 0;
+    bool upload_pending = false;
+#ifndef PS3D_EMU
+    cudaEvent_t ev_copy = nullptr;
+#endif
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
     DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
     DevBuf<double2> tw;
@@ -799,6 +839,9 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     Ctx* c = new Ctx();
     g_ctx = c;
     c->nx = nx; c->ny = ny; c->nz = nz; c->nzp = nz + 1;
+#ifndef PS3D_EMU
+    g_trace = getenv("PS3D_TRACE") ? atoi(getenv("PS3D_TRACE")) : 0;
+#endif
     c->strict_jacobi = getenv("PS3D_STRICT_JACOBI") ? atoi(getenv("PS3D_STRICT_JACOBI")) : 0;
     c->l2_chunks = getenv("PS3D_L2_CHUNKS") ? atoi(getenv("PS3D_L2_CHUNKS")) : 0;
     c->fuse_update = getenv("PS3D_NO_FUSED_UPDATE") ? 0 : 1;
@@ -1071,6 +1114,9 @@ static void do_finalise() {
     if (!g_ctx) return;
     Ctx* c = g_ctx;
     ps_sync(c->stream);
+#ifndef PS3D_EMU
+    trace_dump();
+#endif
     DevBuf<double>* groups[] = {c->svor, c->vor, c->vel, c->svel, c->svorts, c->wa, c->wb, c->velx};
     for (auto* g : groups) for (int i = 0; i < 3; ++i) g[i].release();
     for (int i = 0; i < 9; ++i) c->W[i].release();
@@ -1078,6 +1124,11 @@ static void do_finalise() {
 #ifndef PS3D_EMU
     for (int b = 0; b < 2; ++b) for (int p = 0; p < 8; ++p) if (c->tr.ipc_opened[b][p]) cudaIpcCloseMemHandle(c->tr.ipc_opened[b][p]);
     if (c->tr.comm) c->tr.nccl.CommDestroy(c->tr.comm);
+#endif
+    c->stage3.release();
+#ifndef PS3D_EMU
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
 #endif
     DevBuf<double>* singles[] = {&c->stage, &c->kxl, &c->kyline, &c->kxd, &c->kyd, &c->k2l2, &c->k2l2i, &c->zm, &c->zp,
                                  &c->rkz, &c->gamtop, &c->gambot, &c->filt2d, &c->filtz, &c->vhdis, &c->fac1, &c->fac2,
@@ -1551,6 +1602,41 @@ static void do_upload_vorticity(Ctx& c, const double* vor_phys) {
     ps_sync(c.stream);
 }
 
+// streamed form of do_upload_vorticity: _begin queues the three host -> device copies on the copy stream and
+// returns; _end makes the compute stream wait for them, then repacks and decomposes (utils.f90:160-165)
+static void do_upload_begin(Ctx& c, const double* vor_phys) {
+    if (c.upload_pending) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_begin called twice without upload_vorticity_end");
+    if (!c.stage3.p) c.stage3.alloc(3 * c.nnat);
+#ifndef PS3D_EMU
+    if (!c.copy_stream) {
+        PS_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        PS_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+    }
+#endif
+    ps_h2d(c.stage3.p, vor_phys, 3 * c.nnat * sizeof(double), c.copy_stream);
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaEventRecord(c.ev_copy, c.copy_stream));
+#endif
+    c.upload_pending = true;
+}
+
+static void do_upload_end(Ctx& c) {
+    if (!c.upload_pending) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_end without upload_vorticity_begin");
+#ifndef PS3D_EMU
+    PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+#endif
+    for (int i = 0; i < 3; ++i) {
+        PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)(c.stage3.p + (size_t)i * c.nnat),
+                  c.vor[i].p, c.nxl, c.ny, c.nzp, c.pz, (const int*)nullptr);
+        ++c.launches;
+        fft2d_fwd(c, c.vor[i].p, c.W[0].p);
+        launch_zop(c, ZOP_DECOMPOSE, c.W[0].p, c.svor[i].p);
+    }
+    vor_mean(c, 0);
+    ps_sync(c.stream);
+    c.upload_pending = false;
+}
+
 // pressure (fields_derived.f90:67-157), lazily: needs the five strain fields
 // pressure (fields_derived.f90:67-157), evaluated on demand from the current svel / vor -> W[0]
 static void do_pressure(Ctx& c) {
@@ -1683,6 +1769,13 @@ int ps3d_cuda_field_decompose_physical(const double* fc, double* sf) {
 }
 
 int ps3d_cuda_upload_vorticity(const double* vor_phys) { PS_API_BEGIN do_upload_vorticity(ready(), vor_phys); PS_API_END }
+int ps3d_cuda_upload_vorticity_begin(const double* vor_phys) {
+    PS_API_BEGIN
+    if (!vor_phys) fail(PS3D_ERR_BAD_ARGUMENT, "vor_phys is null");
+    do_upload_begin(ready(), vor_phys);
+    PS_API_END
+}
+int ps3d_cuda_upload_vorticity_end(void) { PS_API_BEGIN do_upload_end(ready()); PS_API_END }
 int ps3d_cuda_vor2vel(void) { PS_API_BEGIN Ctx& c = ready(); do_vor2vel(c); ps_sync(c.stream); PS_API_END }
 int ps3d_cuda_source(void) { PS_API_BEGIN Ctx& c = ready(); do_source(c); ps_sync(c.stream); PS_API_END }
 

@@ -70,9 +70,16 @@ inline void ps_check_launch() {}
 #else
 typedef cudaStream_t ps_stream_t;
 #define PS_UNPAREN(...) __VA_ARGS__
+// PS3D_TRACE=1: CUDA events around every launch, aggregated by kernel name at ps3d_cuda_finalise (in-situ times
+// of a whole run, launch gaps included; development aid, off by default)
+void ps_trace_begin(const char* name, cudaStream_t s);
+void ps_trace_end(cudaStream_t s);
+extern int g_trace;
 #define PS_LAUNCH(kernel, grid, block, smem, stream, ...)                    \
     do {                                                                     \
+        if (::ps3d::g_trace) ::ps3d::ps_trace_begin(#kernel, (stream));      \
         PS_UNPAREN kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        if (::ps3d::g_trace) ::ps3d::ps_trace_end((stream));                 \
         ::ps3d::ps_check_launch();                                           \
     } while (0)
 #define PS_SMEM(type, name) extern __shared__ __align__(16) unsigned char _ps_smem_raw[]; \

@@ -47,6 +47,8 @@ _SIGNATURES = {
     "ps3d_cuda_field_combine_physical": [_dp, _dp],
     "ps3d_cuda_field_decompose_physical": [_dp, _dp],
     "ps3d_cuda_upload_vorticity": [_dp],
+    "ps3d_cuda_upload_vorticity_begin": [_dp],
+    "ps3d_cuda_upload_vorticity_end": [],
     "ps3d_cuda_vor2vel": [],
     "ps3d_cuda_source": [],
     "ps3d_cuda_adapt": [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp],
@@ -194,6 +196,17 @@ class PS3DLib:
         vor = _in(vor)
         assert vor.shape == (3,) + self.shape, (vor.shape, self.shape)
         self._call("ps3d_cuda_upload_vorticity", _ptr(vor))
+
+    def upload_vorticity_begin(self, vor):
+        """Queue the host -> device copies and return; `vor` (C-contiguous float64, ideally pinned) must stay alive
+        until upload_vorticity_end()."""
+        assert vor.dtype == np.float64 and vor.flags["C_CONTIGUOUS"] and vor.shape == (3,) + self.shape
+        self._pending_upload = vor
+        self._call("ps3d_cuda_upload_vorticity_begin", _ptr(vor))
+
+    def upload_vorticity_end(self):
+        self._call("ps3d_cuda_upload_vorticity_end")
+        self._pending_upload = None
 
     def vor2vel(self): self._call("ps3d_cuda_vor2vel")
     def source(self): self._call("ps3d_cuda_source")

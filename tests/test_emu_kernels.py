@@ -335,3 +335,29 @@ def test_rank_limit_and_window_change(emu):
         assert e.value.status == 2
     finally:
         emu.finalise()
+
+
+def test_streamed_upload_matches_blocking_upload(emu):
+    """ps3d_cuda_upload_vorticity_begin/_end leave the same state as ps3d_cuda_upload_vorticity, and the pending
+    copy does not disturb the state it will replace."""
+    n = 8
+    emu.init(n, n, n, np.zeros(3), np.ones(3))
+    emu.init_inversion()
+    try:
+        rng = np.random.default_rng(11)
+        v1, v2 = rng.uniform(-1, 1, (3, n, n, n + 1)), rng.uniform(-1, 1, (3, n, n, n + 1))
+        emu.upload_vorticity(v1)
+        s1 = emu.download3("svor")
+        emu.upload_vorticity(v2)
+        s2 = emu.download3("svor")
+        emu.upload_vorticity(v1)
+        emu.upload_vorticity_begin(v2)
+        assert np.array_equal(emu.download3("svor"), s1)
+        with pytest.raises(Exception):
+            emu.upload_vorticity_begin(v2)
+        emu.upload_vorticity_end()
+        assert np.array_equal(emu.download3("svor"), s2)
+        with pytest.raises(Exception):
+            emu.upload_vorticity_end()
+    finally:
+        emu.finalise()

@@ -453,3 +453,29 @@ def test_cpp_driver_matches_oracle(lib):
     ref.vor2vel()
     ke = float(re.search(r"ke (\S+)", out.stdout).group(1))
     assert ke == pytest.approx(ref.get_kinetic_energy(), rel=1e-12)
+
+
+def test_streamed_upload_matches_blocking_upload(lib):
+    """ps3d_cuda_upload_vorticity_begin/_end (copy stream + staging fields) against the blocking upload, with an
+    advance running between _begin and _end as in bench.py's end-to-end loop."""
+    from ps3d_b200 import host
+    import torch
+    n = 64
+    s = host.beltrami_solver(lib, n, stepper="cn2")
+    try:
+        lower = -0.5 * PI * np.ones(3)
+        extent = PI * np.ones(3)
+        v = torch.from_numpy(host.beltrami_vorticity(n, n, n, lower, extent)).pin_memory().numpy()
+        lib.upload_vorticity(v)
+        s0 = lib.download3("svor")
+        lib.upload_vorticity_begin(v)          # copies in flight while the step runs
+        s.t = 0.0
+        dt1, _ = s.advance()
+        assert rel(lib.download3("svor"), s0) > 1e-6          # the step changed the state
+        lib.upload_vorticity_end()                             # ... and the streamed upload restores the initial one
+        assert np.array_equal(lib.download3("svor"), s0)
+        s.t = 0.0
+        dt2, _ = s.advance()
+        assert dt1 == dt2
+    finally:
+        s.close()
