@@ -67,15 +67,18 @@ template <int NZ>
 struct ZCfg {
     static constexpr int TPF = NZ / 8;            // threads per complex FFT of length NZ (two columns)
     static constexpr int NT = 4 * TPF;            // 4 FFTs = two 4-slot fields at a time  (= NZ/2)
-    // column buffer stride: rows 0..NZ, XOR-swizzled in 16-row blocks (row NZ lands at NZ + (NZ/16 & 15))
-    static constexpr int LC = (((NZ >> 4) & 15) != 0) ? NZ + 16 : NZ + 1;
+        // column buffer: rows 0..NZ/2 in a lower plane, rows NZ/2+1..NZ mirrored in an upper plane that starts at OFFU
+    // (see cz); both XOR-swizzled in 16-row blocks (the swizzle moves row NZ/2 past NZ/2 unless NZ/32 is a multiple of 16)
+    static constexpr int OFFU = (((NZ >> 5) & 15) != 0) ? NZ / 2 + 16 : NZ / 2 + 1;
+    static constexpr int LC = OFFU + NZ / 2;
     static constexpr int BUF = 4 * LC;            // doubles per 4-slot field buffer
     static constexpr int NSIN = NZ / 2 + 2;       // sin(m pi/nz), m = 0..nz/2
     static constexpr int PST = NZ + 1;            // stride of one phim / phip plane
     static constexpr int ZI = 3;                  // rows per thread: t, t+NT, and NZ (thread 0 only)
-    // tables behind the column buffers: sines, phim/phip planes (one per distinct k^2+l^2), warp totals (40),
-    // parked scalars (24)
-    static constexpr int aux(bool gen) { return NSIN + (gen ? 4 : 2) * PST + 40 + 24; }
+    // tables behind the column buffers: sines, phim/phip planes (one per distinct k^2+l^2), warp totals (WT),
+    // parked scalars (24), rows 0 / NZ of the columns whose transform input is handed over pre-processed (32)
+    static constexpr int WT = (NT / 8 > 40) ? NT / 8 : 40;      // >= 4 per warp (put_pre's cosine sums), >= 32 (xform scans)
+    static constexpr int aux(bool gen) { return NSIN + (gen ? 4 : 2) * PST + WT + 24 + 32; }
     // blocks per SM the launch bounds ask for: what shared memory allows, at no fewer than 80 registers
     static constexpr int ctas(int nbuf, bool gen) {
         const int bytes = (nbuf * BUF + aux(gen)) * 8 + 1024;
@@ -86,9 +89,15 @@ struct ZCfg {
     }
 };
 
-// row z of a column buffer: XOR swizzle inside 16-row blocks, so that both the unit-stride (z-owner)
-// and the stride-8 (transform output: thread u owns rows 8u..8u+7) accesses are bank-conflict free
-__device__ __forceinline__ int cz(int z) { return z ^ ((z >> 4) & 15); }
+// Row z of a column buffer.  Two planes: rows 0..NZ/2 at swz(z), rows NZ/2+1..NZ MIRRORED at OFFU + swz(NZ - z),
+// swz = XOR swizzle inside 16-row blocks.  A thread owns the row pair (t, NZ - t) (my_row), i.e. the same position
+// of the two planes: its accesses are unit-stride and 16-aligned in both planes, and the stride-8 accesses of the
+// transform output (thread u owns rows 8u..8u+7) stay bank-conflict free in either plane through the swizzle.
+__device__ __forceinline__ int swz16(int m) { return m ^ ((m >> 4) & 15); }
+template <int NZ>
+__device__ __forceinline__ int cz(int z) {
+    return (2 * z <= NZ) ? swz16(z) : ZCfg<NZ>::OFFU + swz16(NZ - z);
+}
 
 // ---- group bookkeeping -----------------------------------------------------
 template <bool GEN> __device__ __forceinline__ constexpr int sy_of(int s) { return GEN ? (s & 1) : 0; }
@@ -129,7 +138,8 @@ template <int NZ>
 __device__ __forceinline__ int my_row(int it) {
     constexpr int NT = ZCfg<NZ>::NT;
     const int t = threadIdx.x;
-    if (it < 2) return t + it * NT;
+    if (it == 0) return t;                               // rows 0 .. NZ/2-1
+    if (it == 1) return (t == 0) ? NZ / 2 : NZ - t;      // the mirror row (thread 0: the self-mirrored row NZ/2)
     return (t == 0) ? NZ : -1;
 }
 
@@ -153,7 +163,7 @@ template <int NZ>
 __device__ __forceinline__ Row4 row_load_s(const double* buf, int z) {
     constexpr int LC = ZCfg<NZ>::LC;
     Row4 x;
-    const int zz = cz(z);
+    const int zz = cz<NZ>(z);
 #pragma unroll
     for (int s = 0; s < 4; ++s) x.v[s] = buf[s * LC + zz];
     return x;
@@ -161,7 +171,7 @@ __device__ __forceinline__ Row4 row_load_s(const double* buf, int z) {
 template <int NZ>
 __device__ __forceinline__ void row_store_s(double* buf, int z, const Row4& x) {
     constexpr int LC = ZCfg<NZ>::LC;
-    const int zz = cz(z);
+    const int zz = cz<NZ>(z);
 #pragma unroll
     for (int s = 0; s < 4; ++s) buf[s * LC + zz] = x.v[s];
 }
@@ -185,8 +195,9 @@ struct ZScr {
     double* sintab;   // [NZ/2 + 1]  sin(m pi / NZ)
     double* phim;     // [planes][PST]  harmonic functions of this block's (kx, ky): plane sy (fast path: one plane)
     double* phip;
-    double* wt;       // [40] warp totals of the group scan / sum
+    double* wt;       // [WT] warp totals of the group scan / sum
     double* keep;     // [24] block-wide scalars parked between stages (keeps them out of registers)
+    double* park;     // [4 buffers][4 slots][2] rows 0 and NZ of a DST whose input was handed over pre-processed
 };
 template <int NZ, bool GEN>
 __device__ __forceinline__ ZScr<NZ> make_scr(double* base) {
@@ -196,7 +207,8 @@ __device__ __forceinline__ ZScr<NZ> make_scr(double* base) {
     s.phim = s.sintab + Z::NSIN;
     s.phip = s.phim + (GEN ? 2 : 1) * Z::PST;
     s.wt = s.phip + (GEN ? 2 : 1) * Z::PST;
-    s.keep = s.wt + 40;
+    s.keep = s.wt + Z::WT;
+    s.park = s.keep + 24;
     return s;
 }
 // sine table (once per block; followed by a barrier in the caller)
@@ -343,64 +355,17 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, int u, double* 
 //        X_1 = x_0/2 - x_n/2 + sum_j x_j cos(j pi/n), X_0 = Y_0, X_{2k} = Re Y_k, X_n = Y_{n/2},
 //        X_{2k+1} = X_{2k-1} - Im Y_k
 // In place: once the pre-processed sequence is in registers, the two column buffers of an FFT serve as the
-// re/im planes of its Stockham exchanges (indices 0..n-1; row n of a column lives at index >= n and is
-// untouched, row 0 of a DST is carried across in a register).
+// re/im planes of its Stockham exchanges (indices 0..n-1); rows 0 and n of a DST are carried across in registers.
 // The caller must have a barrier between its last write of X0/X1 and this call; ends with a barrier.
+// Second half of a transform: complex FFT of the pre-processed sequence held in (vr, vi), Hermitian split into the
+// two columns, post-processing recurrence, rows written back in the column layout (cz).  (sa, sb): DCT: X_1 of the
+// two columns; DST, u == 0: row 0.  (na, nb): DST, u == 0: row n.  Entered with every read of the buffers done
+// (they become the exchange scratch); ends with a barrier.
 template <int NZ>
-__device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int kind1, const ZScr<NZ>& sc) {
-    constexpr int n = NZ, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
-    const int t = threadIdx.x;
-    const int fg = t / (2 * TPF), f = (t / TPF) & 1, u = t - (t / TPF) * TPF, fft = 2 * fg + f;
-    double* X = fg ? X1 : X0;
-    const int kind = fg ? kind1 : kind0;
-    const bool act = (X != nullptr);
-    double* xa = (act ? X : X0) + (2 * f) * LC;     // (inactive threads never dereference these)
-    double* xb = xa + LC;
-    double* wt = sc.wt + fft * 8;
+__device__ __forceinline__ void xform_tail(double (&vr)[8], double (&vi)[8], double sa, double sb, double na, double nb,
+                                           double* xa, double* xb, int kind, bool act, int u, double* wt, const ZScr<NZ>& sc) {
+    constexpr int n = NZ, TPF = ZCfg<NZ>::TPF;
     const IxSwz ix;
-
-    // ---- pre-process: two real sequences -> one complex sequence
-    double vr[8], vi[8];
-    double sa = 0.0, sb = 0.0;                 // DCT: X_1 partial sums;  DST, u == 0: row 0 carried across
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int j = u + e * TPF;
-        double yr = 0.0, yi = 0.0;
-        if (act) {
-            if (j == 0) {
-                const double a0 = xa[cz(0)], b0 = xb[cz(0)];
-                if (kind == XF_DCT) {
-                    const double an = xa[cz(n)], bn = xb[cz(n)];
-                    yr = 0.5 * (a0 + an); yi = 0.5 * (b0 + bn);
-                    sa += 0.5 * (a0 - an); sb += 0.5 * (b0 - bn);
-                } else {
-                    sa = a0; sb = b0;
-                }
-            } else {
-                const double aj = xa[cz(j)], an = xa[cz(n - j)], bj = xb[cz(j)], bn = xb[cz(n - j)];
-                const double sn = sin_j<NZ>(sc, j);
-                if (kind == XF_DST) {
-                    yr = 0.5 * (aj - an) + sn * (aj + an);
-                    yi = 0.5 * (bj - bn) + sn * (bj + bn);
-                } else {
-                    yr = 0.5 * (aj + an) - sn * (aj - an);
-                    yi = 0.5 * (bj + bn) - sn * (bj - bn);
-                    const double cs = cos_j<NZ>(sc, j);
-                    sa += aj * cs; sb += bj * cs;
-                }
-            }
-        }
-        vr[e] = yr; vi[e] = yi;
-    }
-    {
-        // DCT: block-wide sums for X_1.  DST: (sa, sb) of thread u == 0 hold row 0 and must survive as they
-        // are, so the sum runs on a copy and is discarded.
-        double ta = (kind == XF_DCT) ? sa : 0.0, tb = (kind == XF_DCT) ? sb : 0.0;
-        group_sum2<TPF>(ta, tb, u, wt);        // executed uniformly (barrier inside when TPF > 32)
-        if (kind == XF_DCT) { sa = ta; sb = tb; }
-    }
-    if (TPF <= 32) __syncthreads();            // every pre-process read is done before the buffers become scratch
-
     block_cfft<n, false>(vr, vi, u, act, xa, xb, ix, TwSin<NZ>{sc.sintab});
     __syncthreads();
     if (act) {
@@ -447,15 +412,165 @@ __device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int ki
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int k = 4 * u + c;
-            xa[cz(2 * k + 1)] = scl * (oa[c] + pa);
-            xb[cz(2 * k + 1)] = scl * (ob[c] + pb);
+            xa[cz<NZ>(2 * k + 1)] = scl * (oa[c] + pa);
+            xb[cz<NZ>(2 * k + 1)] = scl * (ob[c] + pb);
             // row 0 of a DST: the value it had on entry (unscaled)
             const double se = (k == 0 && kind == XF_DST) ? 1.0 : scl;
-            xa[cz(2 * k)] = se * ea[c]; xb[cz(2 * k)] = se * eb[c];
+            xa[cz<NZ>(2 * k)] = se * ea[c]; xb[cz<NZ>(2 * k)] = se * eb[c];
         }
-        if (u == 0 && kind == XF_DCT) { xa[cz(n)] = scl * nyq_a; xb[cz(n)] = scl * nyq_b; }
+        if (u == 0) {
+            if (kind == XF_DCT) { xa[cz<NZ>(n)] = scl * nyq_a; xb[cz<NZ>(n)] = scl * nyq_b; }
+            else { xa[cz<NZ>(n)] = na; xb[cz<NZ>(n)] = nb; }
+        }
     }
     __syncthreads();
+}
+
+template <int NZ>
+__device__ __forceinline__ void xform2(double* X0, int kind0, double* X1, int kind1, const ZScr<NZ>& sc) {
+    constexpr int n = NZ, TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC;
+    const int t = threadIdx.x;
+    const int fg = t / (2 * TPF), f = (t / TPF) & 1, u = t - (t / TPF) * TPF, fft = 2 * fg + f;
+    double* X = fg ? X1 : X0;
+    const int kind = fg ? kind1 : kind0;
+    const bool act = (X != nullptr);
+    double* xa = (act ? X : X0) + (2 * f) * LC;     // (inactive threads never dereference these)
+    double* xb = xa + LC;
+    double* wt = sc.wt + fft * 8;
+
+    // ---- pre-process: two real sequences -> one complex sequence
+    double vr[8], vi[8];
+    double sa = 0.0, sb = 0.0;                 // DCT: X_1 partial sums;  DST, u == 0: row 0 carried across
+    double na = 0.0, nb = 0.0;                 // DST, u == 0: row n carried across (it lies inside the scratch range)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int j = u + e * TPF;
+        double yr = 0.0, yi = 0.0;
+        if (act) {
+            if (j == 0) {
+                const double a0 = xa[cz<NZ>(0)], b0 = xb[cz<NZ>(0)];
+                if (kind == XF_DCT) {
+                    const double an = xa[cz<NZ>(n)], bn = xb[cz<NZ>(n)];
+                    yr = 0.5 * (a0 + an); yi = 0.5 * (b0 + bn);
+                    sa += 0.5 * (a0 - an); sb += 0.5 * (b0 - bn);
+                } else {
+                    sa = a0; sb = b0;
+                    na = xa[cz<NZ>(n)]; nb = xb[cz<NZ>(n)];
+                }
+            } else {
+                const double aj = xa[cz<NZ>(j)], an = xa[cz<NZ>(n - j)], bj = xb[cz<NZ>(j)], bn = xb[cz<NZ>(n - j)];
+                const double sn = sin_j<NZ>(sc, j);
+                if (kind == XF_DST) {
+                    yr = 0.5 * (aj - an) + sn * (aj + an);
+                    yi = 0.5 * (bj - bn) + sn * (bj + bn);
+                } else {
+                    yr = 0.5 * (aj + an) - sn * (aj - an);
+                    yi = 0.5 * (bj + bn) - sn * (bj - bn);
+                    const double cs = cos_j<NZ>(sc, j);
+                    sa += aj * cs; sb += bj * cs;
+                }
+            }
+        }
+        vr[e] = yr; vi[e] = yi;
+    }
+    {
+        // DCT: block-wide sums for X_1.  DST: (sa, sb) of thread u == 0 hold row 0 and must survive as they
+        // are, so the sum runs on a copy and is discarded.
+        double ta = (kind == XF_DCT) ? sa : 0.0, tb = (kind == XF_DCT) ? sb : 0.0;
+        group_sum2<TPF>(ta, tb, u, wt);        // executed uniformly (barrier inside when TPF > 32)
+        if (kind == XF_DCT) { sa = ta; sb = tb; }
+    }
+    if (TPF <= 32) __syncthreads();            // every pre-process read is done before the buffers become scratch
+    xform_tail<NZ>(vr, vi, sa, sb, na, nb, xa, xb, kind, act, u, wt, sc);
+}
+
+// ---- transforms whose input is handed over pre-processed (the hot kernels) ------------------------------------
+// The stage that PRODUCES the input of a transform owns the row pair (t, n - t) of all four slots (my_row), which is
+// exactly what the pre-processing step needs: it writes y_t, y_{n-t} instead of x_t, x_{n-t} (put_pre), at the plain
+// positions t, n - t of the column buffers (unit stride for the producer and for the first FFT pass alike: no bank
+// conflicts at any alignment).  Against pre-processing inside the transform this saves, per element, two mirrored
+// shared-memory reads (the conflict-laden ones) and the sine look-up.  Rows 0 and n of a DST (kept by the transform)
+// are parked in `park`, the cosine sums of a DCT (X_1) are reduced over the block in put_pre_sums.
+//
+// lo = row t, hi = row n - t.  Thread 0 (rows 0, n/2, n) passes hi = row n/2 and hands rows 0 and n over separately,
+// where it computes them (park_rows: the values a DST carries through; a DCT of this file has zero boundary rows),
+// so that no thread holds them in registers.  sn, cs = sin, cos(t pi / n) of the calling thread.  ps: running
+// cosine sums of a DCT.
+template <int NZ>
+__device__ __forceinline__ void put_pre(double* X, int kind, double sn, double cs, const Row4& lo, const Row4& hi,
+                                        double (&ps)[4]) {
+    constexpr int LC = ZCfg<NZ>::LC;
+    const int t = threadIdx.x;
+    if (t != 0) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const double a = lo.v[s], b = hi.v[s];
+            if (kind == XF_DST) {
+                const double d = 0.5 * (a - b), e = sn * (a + b);
+                X[s * LC + t] = d + e; X[s * LC + NZ - t] = e - d;
+            } else {
+                const double d = 0.5 * (a + b), e = sn * (a - b);
+                X[s * LC + t] = d - e; X[s * LC + NZ - t] = d + e;
+                ps[s] += cs * (a - b);                       // cos((n - t) pi / n) = -cos(t pi / n)
+            }
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            // y_0 = 0 (DST) / (x_0 + x_n)/2 = 0 (DCT with zero boundary rows);  y_{n/2} = 2 x_{n/2} (DST) / x_{n/2} (DCT)
+            X[s * LC] = 0.0;
+            X[s * LC + NZ / 2] = (kind == XF_DST) ? 2.0 * hi.v[s] : hi.v[s];
+        }
+    }
+}
+// row 0 (top = 0) or row n (top = 1) of the four columns of a DST input: parked, restored by the transform
+__device__ __forceinline__ void park_row(double* park, int top, const Row4& x) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) park[2 * s + top] = x.v[s];
+}
+// warp totals of the cosine sums -> wt[warp][slot]; xform2p adds them up after the caller's barrier
+template <int NZ>
+__device__ __forceinline__ void put_pre_sums(const double (&ps)[4], const ZScr<NZ>& sc) {
+    constexpr int NT = ZCfg<NZ>::NT, W = (NT < 32) ? NT : 32;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        double v = ps[s];
+#pragma unroll
+        for (int d = W >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d, W);
+        if ((threadIdx.x & (W - 1)) == 0) sc.wt[(threadIdx.x / W) * 4 + s] = v;
+    }
+}
+
+// xform2 for pre-processed input (see put_pre).  pk0 / pk1: the parked rows of X0 / X1 (DST); a DCT takes its X_1
+// from the warp totals in sc.wt.  The caller has a barrier between put_pre / put_pre_sums and this call.
+template <int NZ>
+__device__ __forceinline__ void xform2p(double* X0, int kind0, const double* pk0, double* X1, int kind1, const double* pk1,
+                                        const ZScr<NZ>& sc) {
+    constexpr int TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC, NT = ZCfg<NZ>::NT, NW = (NT < 32) ? 1 : NT / 32;
+    const int t = threadIdx.x;
+    const int fg = t / (2 * TPF), f = (t / TPF) & 1, u = t - (t / TPF) * TPF, fft = 2 * fg + f;
+    double* X = fg ? X1 : X0;
+    const double* pk = fg ? pk1 : pk0;
+    const int kind = fg ? kind1 : kind0;
+    const bool act = (X != nullptr);
+    double* xa = (act ? X : X0) + (2 * f) * LC;
+    double* xb = xa + LC;
+    double vr[8], vi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        vr[e] = act ? xa[u + e * TPF] : 0.0;
+        vi[e] = act ? xb[u + e * TPF] : 0.0;
+    }
+    double sa = 0.0, sb = 0.0, na = 0.0, nb = 0.0;
+    if (act && u == 0) {
+        if (kind == XF_DST) {
+            sa = pk[4 * f]; na = pk[4 * f + 1]; sb = pk[4 * f + 2]; nb = pk[4 * f + 3];
+        } else {
+            for (int w = 0; w < NW; ++w) { sa += sc.wt[4 * w + 2 * f]; sb += sc.wt[4 * w + 2 * f + 1]; }
+        }
+    }
+    __syncthreads();                           // every read of the input (and of the warp totals) is done
+    xform_tail<NZ>(vr, vi, sa, sb, na, nb, xa, xb, kind, act, u, sc.wt + fft * 8, sc);
 }
 
 // ---------------------------------------------------------------------------
@@ -528,7 +643,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         // field_decompose_semi_spectral (:563-592): remove the harmonic part defined by the boundary rows, sine transform
         double d0[4], dn[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) { d0[s] = X[s * LC + cz(0)]; dn[s] = X[s * LC + cz(NZ)]; }
+        for (int s = 0; s < 4; ++s) { d0[s] = X[s * LC + cz<NZ>(0)]; dn[s] = X[s * LC + cz<NZ>(NZ)]; }
 #pragma unroll
         for (int it = 0; it < 3; ++it) {
             const int z = my_row<NZ>(it);
@@ -583,7 +698,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const double* c = X + s * LC;
-                d.v[s] = (z == 0) ? g.dzi * (c[cz(1)] - c[cz(0)]) : (z == NZ) ? g.dzi * (c[cz(NZ)] - c[cz(NZ - 1)]) : (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi;
+                d.v[s] = (z == 0) ? g.dzi * (c[cz<NZ>(1)] - c[cz<NZ>(0)]) : (z == NZ) ? g.dzi * (c[cz<NZ>(NZ)] - c[cz<NZ>(NZ - 1)]) : (c[cz<NZ>(z + 1)] - c[cz<NZ>(z - 1)]) * g.hdzi;
             }
             row_store_g<NZ>(out, r, z, d);
         }
@@ -615,7 +730,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT) k_zop(SpecGeom g, int op, const 
         if (op == ZOP_COMBINE && z >= 1 && z < NZ) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                x.v[s] += X[s * LC + cz(0)] * phim_of<NZ, GEN>(scr, z, s) + X[s * LC + cz(NZ)] * phip_of<NZ, GEN>(scr, z, s);
+                x.v[s] += X[s * LC + cz<NZ>(0)] * phim_of<NZ, GEN>(scr, z, s) + X[s * LC + cz<NZ>(NZ)] * phip_of<NZ, GEN>(scr, z, s);
         }
         row_store_g<NZ>(out, r, z, x);
     }
@@ -656,6 +771,14 @@ __device__ __forceinline__ void project_row(Row4& fa, Row4& fb, const Row4& fe, 
     }
 }
 
+// sin, cos(t pi / NZ) of the calling thread (t < NZ/2) from the twiddle table: the two constants of put_pre
+template <int NZ>
+__device__ __forceinline__ void my_sincos(const SpecGeom& g, double& sn, double& cs) {
+    const int step = g.ntw / (2 * NZ), t = threadIdx.x;
+    sn = __ldg(&g.tw[t * step]).y;
+    cs = __ldg(&g.tw[(NZ / 2 - t) * step]).y;
+}
+
 template <int NZ, bool GEN>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2vel_spec(SpecGeom g, V2VArgs a) {
     PS_SMEM(double, sm);
@@ -665,25 +788,43 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
     double* C = B + BUF;
     double* E = C + BUF;
     const ZScr<NZ> scr = make_scr<NZ, GEN>(E + BUF);
+    double* pkA = scr.park;
+    double* pkB = pkA + 8;
+    double* pkC = pkB + 8;
+    double* pkE = pkC + 8;
     scr_init<NZ>(scr, g);
     const Grp r = make_grp<GEN>(g, blockIdx.x);
     phi_fill<NZ, GEN>(scr, g, r);
+    double sn, cs;
+    my_sincos<NZ>(g, sn, cs);
+    const int t = threadIdx.x;
+    const int z0 = my_row<NZ>(0), z1 = my_row<NZ>(1);          // the row pair of this thread (thread 0: rows 0, NZ/2, NZ)
+    double nops[4] = {0.0, 0.0, 0.0, 0.0};
+    Row4 zero4;
+    zero4.v[0] = zero4.v[1] = zero4.v[2] = zero4.v[3] = 0.0;
 
-    // stage svor
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        row_store_s<NZ>(A, z, row_load_g<NZ>(a.svor0, r, z));
-        row_store_s<NZ>(B, z, row_load_g<NZ>(a.svor1, r, z));
-        row_store_s<NZ>(C, z, row_load_g<NZ>(a.svor2, r, z));
+    // svor from memory straight into the pre-processed input of the three sine transforms (thread 0: rows 0 and NZ,
+    // which the transforms carry through, go to the park)
+    {
+        const Row4 cl = row_load_g<NZ>(a.svor2, r, z0), ch = row_load_g<NZ>(a.svor2, r, z1);
+        const Row4 al = row_load_g<NZ>(a.svor0, r, z0), ah = row_load_g<NZ>(a.svor0, r, z1);
+        put_pre<NZ>(C, XF_DST, sn, cs, cl, ch, nops);
+        put_pre<NZ>(A, XF_DST, sn, cs, al, ah, nops);
+        const Row4 bl = row_load_g<NZ>(a.svor1, r, z0), bh = row_load_g<NZ>(a.svor1, r, z1);
+        put_pre<NZ>(B, XF_DST, sn, cs, bl, bh, nops);
+        if (t == 0) {
+            park_row(pkC, 0, cl); park_row(pkA, 0, al); park_row(pkB, 0, bl);
+            park_row(pkC, 1, row_load_g<NZ>(a.svor2, r, NZ));
+            park_row(pkA, 1, row_load_g<NZ>(a.svor0, r, NZ));
+            park_row(pkB, 1, row_load_g<NZ>(a.svor1, r, NZ));
+        }
     }
     __syncthreads();
 
     // C -> semi-spectral zeta (inversion.f90:45, :142-144): DST + harmonic part; this is also the
     // semi-spectral zeta that feeds the inverse x/y passes (:81).  A (xi) rides along: its sine sum is the
     // interior of combine(xi_old), used by the semi-spectral projection below.
-    xform2<NZ>(C, XF_DST, A, XF_DST, scr);
+    xform2p<NZ>(C, XF_DST, pkC, A, XF_DST, pkA, scr);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -692,45 +833,52 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
         if (z >= 1 && z < NZ) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                c.v[s] += C[s * LC + cz(0)] * phim_of<NZ, GEN>(scr, z, s) + C[s * LC + cz(NZ)] * phip_of<NZ, GEN>(scr, z, s);
+                c.v[s] += C[s * LC + cz<NZ>(0)] * phim_of<NZ, GEN>(scr, z, s) + C[s * LC + cz<NZ>(NZ)] * phip_of<NZ, GEN>(scr, z, s);
             row_store_s<NZ>(C, z, c);
         }
         row_store_g<NZ>(a.wsem2, r, z, c);
     }
     __syncthreads();
-    // E = decompose(central_diffz(C)) (:46-47): FD, harmonic part removed, then DST (with eta in B)
+    // E = decompose(central_diffz(C)) (:46-47): FD, harmonic part removed -> pre-processed input of its DST (with
+    // eta in B); rows 0 and NZ (the one-sided differences) ride through the transform
     {
         double e0[4], en[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const double* c = C + s * LC;
-            e0[s] = g.dzi * (c[cz(1)] - c[cz(0)]);
-            en[s] = g.dzi * (c[cz(NZ)] - c[cz(NZ - 1)]);
+            e0[s] = g.dzi * (c[cz<NZ>(1)] - c[cz<NZ>(0)]);
+            en[s] = g.dzi * (c[cz<NZ>(NZ)] - c[cz<NZ>(NZ - 1)]);
         }
+        Row4 er[2];
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {
-            const int z = my_row<NZ>(it);
-            if (z < 0) continue;
-            Row4 e;
+        for (int it = 0; it < 2; ++it) {
+            const int z = it ? z1 : z0;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const double* c = C + s * LC;
-                if (z == 0) e.v[s] = e0[s];
-                else if (z == NZ) e.v[s] = en[s];
-                else e.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi
-                              - (e0[s] * phim_of<NZ, GEN>(scr, z, s) + en[s] * phip_of<NZ, GEN>(scr, z, s));
+                if (z == 0) er[it].v[s] = e0[s];
+                else er[it].v[s] = (c[cz<NZ>(z + 1)] - c[cz<NZ>(z - 1)]) * g.hdzi
+                                   - (e0[s] * phim_of<NZ, GEN>(scr, z, s) + en[s] * phip_of<NZ, GEN>(scr, z, s));
             }
-            row_store_s<NZ>(E, z, e);
+        }
+        put_pre<NZ>(E, XF_DST, sn, cs, er[0], er[1], nops);
+        if (t == 0) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { pkE[2 * s] = e0[s]; pkE[2 * s + 1] = en[s]; }
         }
     }
     __syncthreads();
-    xform2<NZ>(E, XF_DST, B, XF_DST, scr);
+    xform2p<NZ>(E, XF_DST, pkE, B, XF_DST, pkB, scr);
 
     // Solenoidal projection (:39-76), twice (see project_row):
     //  * semi-spectral rows (combine(xi_old), combine(eta_old), dzeta/dz) -> wsem0, wsem1, the vorticity that the
     //    inverse x/y passes take to physical space (:80-82);
     //  * mixed-spectral rows (xi_old, eta_old re-read from memory, E) -> new svor, and the source of the w
-    //    inversion D2 = A_y - B_x (:86-90) -> E buffer.
+    //    inversion D2 = A_y - B_x (:86-90).
+    // The Laplacian inversion (:108-122) follows in registers: ds = green * D2 (rows 1..nz-1; sine series of w),
+    // as = rkz * ds (cosine series of dw/dz); both go to the buffers as pre-processed transform input once every
+    // thread has read its rows.
+    Row4 dsr[2], asr[2];
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
@@ -743,9 +891,9 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
             for (int s = 0; s < 4; ++s) {
                 const double* c = C + s * LC;
                 const double pm = phim_of<NZ, GEN>(scr, z, s), pp = phip_of<NZ, GEN>(scr, z, s);
-                sa.v[s] += A[s * LC + cz(0)] * pm + A[s * LC + cz(NZ)] * pp;
-                sb.v[s] += B[s * LC + cz(0)] * pm + B[s * LC + cz(NZ)] * pp;
-                se.v[s] = (c[cz(z + 1)] - c[cz(z - 1)]) * g.hdzi;
+                sa.v[s] += A[s * LC + cz<NZ>(0)] * pm + A[s * LC + cz<NZ>(NZ)] * pp;
+                sb.v[s] += B[s * LC + cz<NZ>(0)] * pm + B[s * LC + cz<NZ>(NZ)] * pp;
+                se.v[s] = (c[cz<NZ>(z + 1)] - c[cz<NZ>(z - 1)]) * g.hdzi;
             }
         } else {
             se = fe;            // rows 0, NZ of E still hold the one-sided differences
@@ -757,39 +905,33 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
         row_store_g<NZ>(a.svor0, r, z, fa);
         row_store_g<NZ>(a.svor1, r, z, fb);
         const Row4 ay2 = ddy(fa, r), bx2 = ddx(fb, r);
-        Row4 d;
+        Row4 d, as;
 #pragma unroll
         for (int s = 0; s < 4; ++s) d.v[s] = ay2.v[s] - bx2.v[s];
-        row_store_s<NZ>(E, z, d);
-    }
-    __syncthreads();
-    // boundary values of D2 (:96-104), before anything is overwritten (parked in shared memory: they are
-    // needed again only in the last stage)
-    if (threadIdx.x < 4) {
-        const int s = threadIdx.x;
-        scr.keep[s] = E[s * LC + cz(0)];
-        scr.keep[4 + s] = E[s * LC + cz(NZ)];
-    }
-
-    // invert Laplacian (:108-122): E <- green * D2 (rows 1..nz-1), A <- rkz * E (cosine series of dw/dz)
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        Row4 as, ds = row_load_s<NZ>(E, z);
         if (z >= 1 && z < NZ) {
             const double rk = __ldg(&g.rkz[z]);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const double green = -1.0 / (r.k2[sy_of<GEN>(s)] + rk * rk);
-                ds.v[s] = green * ds.v[s];
-                as.v[s] = rk * ds.v[s];
+                d.v[s] = green * d.v[s];
+                as.v[s] = rk * d.v[s];
             }
-            row_store_s<NZ>(E, z, ds);
         } else {
-            as.v[0] = as.v[1] = as.v[2] = as.v[3] = 0.0;
+            // boundary values of D2 (:96-104): needed again in the last stage (keep); as rows 0 / NZ of the sine
+            // series they ride through its transform (park: nobody else touches pkE between the two transforms)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) scr.keep[(z == 0 ? 0 : 4) + s] = d.v[s];
+            park_row(pkE, z == 0 ? 0 : 1, d);
+            as = zero4;
         }
-        row_store_s<NZ>(A, z, as);
+        if (it < 2) { dsr[it] = d; asr[it] = as; }
+    }
+    __syncthreads();          // every read of A, B, E is done: they take the input of the last two transforms
+    {
+        double ps[4] = {0.0, 0.0, 0.0, 0.0};
+        put_pre<NZ>(E, XF_DST, sn, cs, dsr[0], dsr[1], nops);
+        put_pre<NZ>(A, XF_DCT, sn, cs, asr[0], asr[1], ps);
+        put_pre_sums<NZ>(ps, scr);
     }
     // horizontally averaged flow from the (0,0) column (:150-165): cosine transform in B slots 0, 1
     if (GEN && r.g00) {
@@ -809,7 +951,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
         }
     }
     __syncthreads();
-    xform2<NZ>(A, XF_DCT, E, XF_DST, scr);     // (:128-129)
+    xform2p<NZ>(A, XF_DCT, pkA, E, XF_DST, pkE, scr);     // (:128-129)
     if (GEN && r.g00) xform2<NZ>(B, XF_DCT, nullptr, XF_DST, scr);
 
     // w = E + boundary part, dw/dz = es + as (:96-104, :136-139);
@@ -826,7 +968,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        const Row4 as = row_load_s<NZ>(A, z), ds = row_load_s<NZ>(E, z), cs = row_load_s<NZ>(C, z);
+        const Row4 as = row_load_s<NZ>(A, z), ds = row_load_s<NZ>(E, z), cs_ = row_load_s<NZ>(C, z);
         const double zm = __ldg(&g.zm[z]), zp = __ldg(&g.zp[z]);
         Theta th[GEN ? 2 : 1];
 #pragma unroll
@@ -840,7 +982,7 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
             es.v[s] = d0 * q.dthm + dn * q.dthp + as.v[s];
             w.v[s] = (z == 0 || z == NZ) ? 0.0 : ds.v[s] + d0 * q.thm + dn * q.thp;
         }
-        const Row4 ex = ddx(es, r), ey = ddy(es, r), cx = ddx(cs, r), cy = ddy(cs, r);
+        const Row4 ex = ddx(es, r), ey = ddy(es, r), cx = ddx(cs_, r), cy = ddy(cs_, r);
         Row4 u, v;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -849,8 +991,8 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_vor2ve
         }
         if (GEN && r.g00) {
             const double gt = __ldg(&g.gamtop[z]), gb = __ldg(&g.gambot[z]);
-            u.v[0] = B[cz(z)] + b0n * gt - b00 * gb;               // ubar (:163)
-            v.v[0] = B[LC + cz(z)] - a0n * gt + a00 * gb;          // vbar (:164)
+            u.v[0] = B[cz<NZ>(z)] + b0n * gt - b00 * gb;               // ubar (:163)
+            v.v[0] = B[LC + cz<NZ>(z)] - a0n * gt + a00 * gb;          // vbar (:164)
         }
         row_store_g<NZ>(a.svel0, r, z, u);
         row_store_g<NZ>(a.svel1, r, z, v);
@@ -917,7 +1059,7 @@ __device__ __forceinline__ void rows_prefetch(double* buf, const double* __restr
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        const int zz = cz(z);
+        const int zz = cz<NZ>(z);
 #pragma unroll
         for (int s = 0; s < 4; ++s)
             if (s < 2 || !r.dupx) ps_cp_async8(buf + s * LC + zz, src + r.off[s] + z);
@@ -953,81 +1095,87 @@ template <int NZ, bool GEN>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_source_spec(SpecGeom g, SrcArgs a) {
     PS_SMEM(double, sm);
     constexpr int BUF = ZCfg<NZ>::BUF;
-    double* R = sm;           // r, then curl component 0
+    double* R = sm;           // curl component 0 (r itself stays in the registers of its row owner)
     double* Q = R + BUF;      // q, then curl component 2
-    double* P = Q + BUF;      // p
+    double* P = Q + BUF;      // p, then the operand of the update
     double* T = P + BUF;      // curl component 1
     const ZScr<NZ> scr = make_scr<NZ, GEN>(T + BUF);
+    double* pkR = scr.park;
+    double* pkQ = pkR + 8;
+    double* pkT = pkQ + 8;
     scr_init<NZ>(scr, g);
     const Grp r = make_grp<GEN>(g, blockIdx.x);
     phi_fill<NZ, GEN>(scr, g, r);
+    double sn, cs;
+    my_sincos<NZ>(g, sn, cs);
+    const int t = threadIdx.x;
+    const int z0 = my_row<NZ>(0), z1 = my_row<NZ>(1);
+    double nops[4] = {0.0, 0.0, 0.0, 0.0};
+    Row4 zero4;
+    zero4.v[0] = zero4.v[1] = zero4.v[2] = zero4.v[3] = 0.0;
 
-    // stage the fluxes (each element is read from memory exactly once)
+    // stage q and p (their neighbour rows are needed for d/dz); every flux element is read from memory exactly once,
+    // the rows of r are used by their owner only
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
         const int z = my_row<NZ>(it);
         if (z < 0) continue;
-        row_store_s<NZ>(R, z, row_load_g<NZ>(a.r, r, z));
         row_store_s<NZ>(Q, z, row_load_g<NZ>(a.q, r, z));
         row_store_s<NZ>(P, z, row_load_g<NZ>(a.p, r, z));
     }
+    const Row4 rl = row_load_g<NZ>(a.r, r, z0), rh = row_load_g<NZ>(a.r, r, z1);
     __syncthreads();
-    // boundary rows of the curl (they define the harmonic part removed from every interior row): one thread
-    // each, parked in shared memory as keep[(c*2 + top)*4 + slot]
-    if (threadIdx.x == 0 || threadIdx.x == ZCfg<NZ>::NT - 1) {
-        const bool top = (threadIdx.x != 0);
-        const int z = top ? NZ : 0, zl = top ? NZ - 1 : 0, zh = top ? NZ : 1;
-        Row4 c0, c1;
-        curl01_row(row_load_s<NZ>(R, z), row_load_s<NZ>(Q, zl), row_load_s<NZ>(Q, zh), row_load_s<NZ>(P, zl),
-                   row_load_s<NZ>(P, zh), g.dzi, r, c0, c1);
-        const Row4 c2 = curl2_row(row_load_s<NZ>(Q, z), row_load_s<NZ>(P, z), r);
+    // boundary rows of the curl (they define the harmonic part removed from every interior row): thread 0 owns
+    // both; parked in shared memory as keep[(c*2 + top)*4 + slot]
+    if (t == 0) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            scr.keep[(0 + top) * 4 + s] = c0.v[s];
-            scr.keep[(2 + top) * 4 + s] = c1.v[s];
-            scr.keep[(4 + top) * 4 + s] = c2.v[s];
-        }
-    }
-    __syncthreads();
-    // components 0, 1 (need the neighbour rows of q, p): R <- s0 in place (row z of r is only read by its
-    // owner), T <- s1
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        Row4 s0, s1;
-        if (z == 0 || z == NZ) {
-            const int top = (z == NZ);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { s0.v[s] = scr.keep[(0 + top) * 4 + s]; s1.v[s] = scr.keep[(2 + top) * 4 + s]; }
-        } else {
-            curl01_row(row_load_s<NZ>(R, z), row_load_s<NZ>(Q, z - 1), row_load_s<NZ>(Q, z + 1),
-                       row_load_s<NZ>(P, z - 1), row_load_s<NZ>(P, z + 1), g.hdzi, r, s0, s1);
+        for (int top = 0; top < 2; ++top) {
+            const int z = top ? NZ : 0, zl = top ? NZ - 1 : 0, zh = top ? NZ : 1;
+            Row4 c0, c1;
+            curl01_row(top ? row_load_g<NZ>(a.r, r, NZ) : rl, row_load_s<NZ>(Q, zl), row_load_s<NZ>(Q, zh), row_load_s<NZ>(P, zl),
+                       row_load_s<NZ>(P, zh), g.dzi, r, c0, c1);
+            const Row4 c2 = curl2_row(row_load_s<NZ>(Q, z), row_load_s<NZ>(P, z), r);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const double pm = phim_of<NZ, GEN>(scr, z, s), pp = phip_of<NZ, GEN>(scr, z, s);
-                s0.v[s] -= scr.keep[0 + s] * pm + scr.keep[4 + s] * pp;
-                s1.v[s] -= scr.keep[8 + s] * pm + scr.keep[12 + s] * pp;
+                scr.keep[(0 + top) * 4 + s] = c0.v[s];
+                scr.keep[(2 + top) * 4 + s] = c1.v[s];
+                scr.keep[(4 + top) * 4 + s] = c2.v[s];
             }
+            // rows 0 and NZ of the three sine transforms
+            park_row(pkR, top, c0); park_row(pkT, top, c1); park_row(pkQ, top, c2);
         }
-        row_store_s<NZ>(R, z, s0);
-        row_store_s<NZ>(T, z, s1);
-    }
-    __syncthreads();          // every neighbour row of q, p has been read
-    // component 2 (own rows only): Q <- s2 in place
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        const int z = my_row<NZ>(it);
-        if (z < 0) continue;
-        Row4 s2 = curl2_row(row_load_s<NZ>(Q, z), row_load_s<NZ>(P, z), r);
-        if (z >= 1 && z < NZ) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                s2.v[s] -= scr.keep[16 + s] * phim_of<NZ, GEN>(scr, z, s) + scr.keep[20 + s] * phip_of<NZ, GEN>(scr, z, s);
-        }
-        row_store_s<NZ>(Q, z, s2);
     }
     __syncthreads();
+    // the three curl components of this thread's row pair, harmonic part removed; components 0 and 1 go to R and T
+    // as pre-processed transform input at once (both buffers are free), component 2 takes the place of q once every
+    // thread has read its neighbour rows
+    Row4 c2r[2];
+    {
+        Row4 c0r[2], c1r[2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int z = it ? z1 : z0;
+            if (z == 0) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) { c0r[it].v[s] = scr.keep[s]; c1r[it].v[s] = scr.keep[8 + s]; c2r[it].v[s] = scr.keep[16 + s]; }
+            } else {
+                curl01_row(it ? rh : rl, row_load_s<NZ>(Q, z - 1), row_load_s<NZ>(Q, z + 1),
+                           row_load_s<NZ>(P, z - 1), row_load_s<NZ>(P, z + 1), g.hdzi, r, c0r[it], c1r[it]);
+                c2r[it] = curl2_row(row_load_s<NZ>(Q, z), row_load_s<NZ>(P, z), r);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const double pm = phim_of<NZ, GEN>(scr, z, s), pp = phip_of<NZ, GEN>(scr, z, s);
+                    c0r[it].v[s] -= scr.keep[0 + s] * pm + scr.keep[4 + s] * pp;
+                    c1r[it].v[s] -= scr.keep[8 + s] * pm + scr.keep[12 + s] * pp;
+                    c2r[it].v[s] -= scr.keep[16 + s] * pm + scr.keep[20 + s] * pp;
+                }
+            }
+        }
+        put_pre<NZ>(R, XF_DST, sn, cs, c0r[0], c0r[1], nops);
+        put_pre<NZ>(T, XF_DST, sn, cs, c1r[0], c1r[1], nops);
+    }
+    __syncthreads();          // every neighbour row of q, p has been read
+    put_pre<NZ>(Q, XF_DST, sn, cs, c2r[0], c2r[1], nops);
     // per-slot factor of the update: vdiss * filt2d of the column ((0,0): vdiss, filt = 1)
     double f2[4] = {0.0, 0.0, 0.0, 0.0};
     if (a.upd >= 0) {
@@ -1042,12 +1190,13 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_source
     const double* x2 = (a.upd == 0) ? a.svor[2] : a.vortsm[2];
     // component 2 first (the half-filled transform round); its update operand lands in P, free since the curl
     if (a.upd >= 0) rows_prefetch<NZ>(P, x2, r);
-    xform2<NZ>(Q, XF_DST, nullptr, XF_DST, scr);
+    __syncthreads();
+    xform2p<NZ>(Q, XF_DST, pkQ, nullptr, XF_DST, pkQ, scr);
     if (a.upd >= 0) ps_cp_async_wait();
     src_finish<NZ, GEN>(a, 2, Q, P, a.s2, g, r, f2);
     // components 0, 1: operands into P and Q (this thread only ever touches its own rows of them from here on)
     if (a.upd >= 0) { rows_prefetch<NZ>(P, x0, r); rows_prefetch<NZ>(Q, x1, r); }
-    xform2<NZ>(R, XF_DST, T, XF_DST, scr);
+    xform2p<NZ>(R, XF_DST, pkR, T, XF_DST, pkT, scr);
     if (a.upd >= 0) ps_cp_async_wait();
     src_finish<NZ, GEN>(a, 0, R, P, a.s0, g, r, f2);
     src_finish<NZ, GEN>(a, 1, T, Q, a.s1, g, r, f2);
