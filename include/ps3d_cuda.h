@@ -153,7 +153,9 @@ int ps3d_cuda_diagnostics(double out[8]);
  * set_netcdf_field_diagnostic (advance.f90:188-193, 315-321, 366): out[NC_x - 1] with the reference's indices
  * (field_diagnostics_netcdf.f90:36-75), see the PS3D_NC_* enumerators.  Assumes, like the reference, that the
  * fields are up to date (vor2vel done) and that adapt has run for the current state; evaluates the horizontal
- * divergence (fields_derived.f90:161-182) for NC_USDELRMS.  Buoyancy-only entries (BFMAX, RBFMAX, RIMIN) are 0;
+ * divergence (fields_derived.f90:161-182) for NC_USDELRMS.  BFMAX is that of the last adapt (0 without buoyancy); RBFMAX and RIMIN
+ * are 0 here (ps3d_cuda_buoyancy_diag returns the rolling mean; the Richardson number, APE and the other NC_APE..NC_MSS
+ * statistics of the buoyancy build are host-side reductions over ps3d_cuda_download(PS3D_F_BUOY));
  * ROMIN / ROMAX are min / max zeta divided by f_cor(3) exactly as field_diagnostics.f90:293-320 (f_cor = 0 in the
  * configurations in scope: +-inf or nan, as in the reference). */
 enum { PS3D_NC_KE = 0, PS3D_NC_EN, PS3D_NC_OMAX, PS3D_NC_ORMS, PS3D_NC_OCHAR, PS3D_NC_OXMEAN, PS3D_NC_OYMEAN,

@@ -7,11 +7,18 @@ checked against something that follows the reference line by line.  Only
 legs of `bench.py` may import it.  The product (`ps3d_b200`) never does.
 
 Parity pinning: the reference cannot be compiled here (no gfortran / MPI /
-netCDF) and ships no golden vectors, so the oracle is pinned by the
+netCDF) and ships no golden vectors, so the oracle is pinned by (a) the
 reference's own analytic known-answer unit tests (tests/test_oracle_*.py):
 test_vor2vel_1..5, test_diffx/diffy, test_diffz_1..4, test_implicit_rk,
-DST/DCT self-inverse and revfft(forfft(x)) = x.  Multi-step trajectories are
-pinned by nothing but this oracle (the reference has no such test).
+DST/DCT self-inverse and revfft(forfft(x)) = x, and (b) a literal C
+restatement of the reference's own transform code, oracle/stafft_lit.c <-
+src/fft/stafft.f90 (tests/test_stafft_lit.py: every power-of-two length
+8..1024, <= 2e-14): pinned at operator level.  Multi-step trajectories are
+pinned by nothing but this oracle and its independent C++ twin
+(oracle/ps3d_ref.cpp; the reference has no such test): trajectory parity is
+"oracle-pinned, reference-unpinned".  The ENABLE_BUOYANCY paths have no test
+in the reference at all; they are pinned by an analytic known answer for
+diffz (tests/test_buoyancy.py) and by inspection against the cited lines.
 
 Array convention: Fortran `f(0:nz, y, x)` == NumPy `f[x, y, z]` (C order, z
 contiguous), `f(0:nz, y, x, c)` == `f[c, x, y, z]`.

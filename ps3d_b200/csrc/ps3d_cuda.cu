@@ -518,9 +518,12 @@ static void setup_p2p(Ctx& c) {
     Transport& t = c.tr;
     if (!t.have_nccl() || getenv("PS3D_NO_P2P")) return;
     const int P = t.nranks;
-    cudaIpcMemHandle_t mine[2];
+    constexpr int NB = Transport::NPEERBUF;
+    double* local[NB] = {c.W[6].p, c.W[8].p, c.velx[0].p, c.velx[1].p, c.velx[2].p};
+    cudaIpcMemHandle_t mine[NB];
     int ok = 1;
-    if (cudaIpcGetMemHandle(&mine[0], c.W[6].p) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], c.W[8].p) != cudaSuccess) ok = 0;
+    for (int b = 0; b < NB; ++b)
+        if (cudaIpcGetMemHandle(&mine[b], local[b]) != cudaSuccess) ok = 0;
     (void)cudaGetLastError();
     const size_t hb = sizeof(mine);
     DevBuf<unsigned char> all;
@@ -532,8 +535,8 @@ static void setup_p2p(Ctx& c) {
     ps_d2h(host.data(), all.p, hb * P, c.stream);
     ps_sync(c.stream);
     for (int p = 0; p < P && ok; ++p) {
-        for (int b = 0; b < 2; ++b) {
-            if (p == t.rank) { t.peer_t2[b][p] = (b ? c.W[8].p : c.W[6].p); continue; }
+        for (int b = 0; b < NB; ++b) {
+            if (p == t.rank) { t.peer_t2[b][p] = local[b]; continue; }
             cudaIpcMemHandle_t h;
             memcpy(&h, host.data() + hb * p + sizeof(h) * b, sizeof(h));
             void* ptr = nullptr;
@@ -605,8 +608,9 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
         PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_first[0], 0));
         cross_rank_barrier(c, c.comm_stream);
         for (int i = 0; i < n; ++i) {
-            first[i].out = t2[i & 1];
-            first[i].scatter = i & 1;
+            // (a caller may name a dedicated receive buffer >= 2 that it keeps: do_vor2vel)
+            if (first[i].scatter < 2) first[i].scatter = i & 1;
+            first[i].out = c.tr.peer_t2[first[i].scatter][c.rank];
             first[i].on_comm_stream = true;
             // persistent launch, two blocks per SM: the system-scope fence that ends a scatter sweep is then paid once
             // per block instead of once per tile (measured, 512^3 cn2 on 4 GPUs: full grid 27.4 ms/step, persistent
@@ -619,7 +623,7 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
             cross_rank_barrier(c, c.comm_stream);
             PS_CUDA_TRY(cudaEventRecord(c.ev_a2a[i], c.comm_stream));
             PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_a2a[i], 0));
-            second[i].in[0] = t2[i & 1];
+            second[i].in[0] = first[i].out;
             run_sweep(c, second[i]);
             PS_CUDA_TRY(cudaEventRecord(c.ev_second[i], c.stream));
         }
@@ -997,7 +1001,12 @@ static void do_init(int nx, int ny, int nz, const double* lower, const double* e
     c->partial.alloc((size_t)RED_BLOCKS * 16);
     c->red.alloc(64);
 #ifndef PS3D_EMU
-    if (nranks > 1) setup_p2p(*c);
+    if (nranks > 1) {
+        // the kept x-transformed velocity (do_vor2vel) is a peer-written receive buffer on several ranks: it must exist
+        // before the IPC handles are exchanged
+        if (c->keep_velx && nccl_id && !getenv("PS3D_NO_P2P")) for (int i = 0; i < 3; ++i) c->velx[i].alloc(c->nint);
+        setup_p2p(*c);
+    }
 #endif
 }
 
@@ -1122,7 +1131,7 @@ static void do_finalise() {
     for (int i = 0; i < 9; ++i) c->W[i].release();
     c->redS.release(); c->redM.release();
 #ifndef PS3D_EMU
-    for (int b = 0; b < 2; ++b) for (int p = 0; p < 8; ++p) if (c->tr.ipc_opened[b][p]) cudaIpcCloseMemHandle(c->tr.ipc_opened[b][p]);
+    for (int b = 0; b < Transport::NPEERBUF; ++b) for (int p = 0; p < 8; ++p) if (c->tr.ipc_opened[b][p]) cudaIpcCloseMemHandle(c->tr.ipc_opened[b][p]);
     if (c->tr.comm) c->tr.nccl.CommDestroy(c->tr.comm);
 #endif
     c->stage3.release();
@@ -1166,12 +1175,17 @@ static void do_vor2vel(Ctx& c) {
     a.wsem0 = c.W[0].p; a.wsem1 = c.W[1].p; a.wsem2 = c.W[2].p;
     a.svel0 = c.svel[0].p; a.svel1 = c.svel[1].p; a.svel2 = c.svel[2].p;
     launch_v2v(c, a);
-    const bool keep = (c.nranks == 1 && c.l2_chunks <= 0 && c.keep_velx);
+    // one rank: the intermediate of the two sweeps is kept; several ranks with peer memory: the velocity fields are
+    // scattered into dedicated receive buffers (peer buffers 2..4 = velx) that nobody overwrites until the next vor2vel
+    const bool keep1 = (c.nranks == 1 && c.l2_chunks <= 0 && c.keep_velx);
+    const bool keepP = (c.nranks > 1 && c.tr.p2p && c.keep_velx && c.velx[0].p);
+    const bool keep = keep1 || keepP;
     Sweep f[6], g[6];
     for (int i = 0; i < 3; ++i) {
         f[i] = sweep_plain(0, true, false, c.W[i].p, nullptr);        g[i] = sweep_plain(1, true, false, nullptr, c.vor[i].p);
-        if (keep && !c.velx[i].p) c.velx[i].alloc(c.nint);
-        f[3 + i] = sweep_plain(0, true, false, c.svel[i].p, keep ? c.velx[i].p : nullptr);
+        if (keep1 && !c.velx[i].p) c.velx[i].alloc(c.nint);
+        f[3 + i] = sweep_plain(0, true, false, c.svel[i].p, keep1 ? c.velx[i].p : nullptr);
+        if (keepP) f[3 + i].scatter = 2 + i;
         g[3 + i] = sweep_plain(1, true, false, nullptr, c.vel[i].p);
     }
     fft2d_batch(c, 6, f, g);

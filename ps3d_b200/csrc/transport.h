@@ -68,8 +68,11 @@ struct Transport {
     allreduce_fn ar_cb = nullptr;
     void* user = nullptr;
     bool p2p = false;                 // sweeps store straight into the peers' receive buffers (CUDA IPC)
-    double* peer_t2[2][8] = {};       // [buffer][rank]: base of that rank's receive buffer
-    void* ipc_opened[2][8] = {};
+    // [buffer][rank]: base of that rank's receive buffer.  Buffers 0, 1: the two rotating receive fields of the 2-D
+    // FFT pipeline; 2..4: the kept x-transformed velocity of the last vor2vel (Ctx::velx), see do_vor2vel
+    static constexpr int NPEERBUF = 5;
+    double* peer_t2[NPEERBUF][8] = {};
+    void* ipc_opened[NPEERBUF][8] = {};
     long long n_alltoall = 0;
     double bytes_sent = 0.0;
     // peer-memory mailbox (PeerMail below) behind the first receive buffer of every rank: epoch-flag barrier and
