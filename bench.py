@@ -323,7 +323,10 @@ def main():
         return sec
 
     e2e_serial_sec = e2e_loop(False)
-    e2e_sec = e2e_loop(True)
+    e2e_streamed_sec = e2e_loop(True)
+    # both are the public API; the streamed upload wins when the copy hides behind the step (1, 4, 8 GPUs here) and
+    # loses when the DMA, slowed by the running kernels, outlasts it (2 GPUs): the line reports the better one and both times
+    e2e_sec = min(e2e_serial_sec, e2e_streamed_sec)
 
     # ---- per-kernel device times (CUDA events on the library's stream, inside this run) ----
     peak, peak_src = peaks()
@@ -384,13 +387,14 @@ def main():
         "kernels": kernels, "step_share_ms": cshare,
         "e2e": {"value": n * n * nzz / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                 "d2h_bytes_per_step": (16 + 8) * 8, "ms_per_step": e2e_sec * 1e3,
-                "serial_ms_per_step": e2e_serial_sec * 1e3,
+                "serial_ms_per_step": e2e_serial_sec * 1e3, "streamed_ms_per_step": e2e_streamed_sec * 1e3,
+                "upload": "streamed" if e2e_streamed_sec <= e2e_serial_sec else "blocking",
                 "note": "per step: 3 vorticity fields host -> device from pinned memory, decompose, one advance, its 16 "
-                        "diagnostics and KE / enstrophy / helicity back to the host; the copy of the next step's input is "
-                        "queued on a copy stream before the advance (ps3d_cuda_upload_vorticity_begin/_end) and overlaps "
-                        "it, every copy inside the timed region; serial_ms_per_step = the same loop with the blocking "
-                        "ps3d_cuda_upload_vorticity; the updated FIELDS are not downloaded (the reference writes fields at "
-                        "output cadence only, utils.f90:77-87)"},
+                        "diagnostics and KE / enstrophy / helicity back to the host.  streamed: the copy of the next step's "
+                        "input is queued on a copy stream before the advance (ps3d_cuda_upload_vorticity_begin/_end) and "
+                        "overlaps it, every copy inside the timed region; serial: the blocking ps3d_cuda_upload_vorticity; "
+                        "value = the faster of the two loops (`upload`).  The updated FIELDS are not downloaded (the "
+                        "reference writes fields at output cadence only, utils.f90:77-87)"},
         "gpu_launches": int(launches), "tma_launches_total": int(tma_launches), "wall_ms_per_step": wall / args.steps * 1e3,
         "clocks": clocks, "parity": parity,
         "diag": {k: float(v) for k, v in d_after.items()},

@@ -192,23 +192,35 @@ __global__ void k_field_reduce(FieldPtrs f, long long ncol, int nz, int pz, doub
     double acc[RQ_N];
 #pragma unroll
     for (int q = 0; q < RQ_N; ++q) acc[q] = ((RQ_OPMASK >> q) & 1) ? -1.0e300 : 0.0;
-    const long long n = ncol * pz;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(i % pz);
-        if (z > nz) continue;
-        const double w = (z == 0 || z == nz) ? 0.5 : 1.0;
-        const double a = f.vor[0][i], b = f.vor[1][i], c = f.vor[2][i];
-        const double u = f.vel[0][i], v = f.vel[1][i], ww = f.vel[2][i];
-        const double w2 = a * a + b * b + c * c;
-        acc[RQ_MAXW2] = fmax(acc[RQ_MAXW2], fabs(w2));
-        acc[RQ_SUMW2] += w * w2;
-        acc[RQ_SUMW0] += w * a; acc[RQ_SUMW1] += w * b; acc[RQ_SUMW2C] += w * c;
-        acc[RQ_MAXU] = fmax(acc[RQ_MAXU], u); acc[RQ_MAXV] = fmax(acc[RQ_MAXV], v); acc[RQ_MAXWV] = fmax(acc[RQ_MAXWV], ww);
-        acc[RQ_SUMU2] += w * (u * u + v * v + ww * ww);
-        acc[RQ_SUMUW] += w * (u * a + v * b + ww * c);
-        acc[RQ_SUMUH] += w * (u * u + v * v);                          // field_diagnostics.f90:135-142
-        acc[RQ_SUMWH] += w * (a * a + b * b);                          // :215-222
-        acc[RQ_MAXWH] = fmax(acc[RQ_MAXWH], a * a + b * b);           // :237 (sqrt taken on the host)
+    // two consecutive z per thread (16-byte loads; pz is even and every column starts 16-byte aligned), 32-bit
+    // index arithmetic
+    const unsigned hp = (unsigned)pz >> 1;
+    const unsigned long long n2 = (unsigned long long)ncol * hp;
+    for (unsigned long long i2 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < n2;
+         i2 += (unsigned long long)gridDim.x * blockDim.x) {
+        const int z0 = 2 * (int)((n2 >> 32) ? (i2 % hp) : ((unsigned)i2 % hp));
+        if (z0 > nz) continue;
+        const double2 a2 = reinterpret_cast<const double2*>(f.vor[0])[i2], b2 = reinterpret_cast<const double2*>(f.vor[1])[i2];
+        const double2 c2 = reinterpret_cast<const double2*>(f.vor[2])[i2], u2 = reinterpret_cast<const double2*>(f.vel[0])[i2];
+        const double2 v2 = reinterpret_cast<const double2*>(f.vel[1])[i2], w2_ = reinterpret_cast<const double2*>(f.vel[2])[i2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int z = z0 + h;
+            if (z > nz) continue;
+            const double w = (z == 0 || z == nz) ? 0.5 : 1.0;
+            const double a = h ? a2.y : a2.x, b = h ? b2.y : b2.x, c = h ? c2.y : c2.x;
+            const double u = h ? u2.y : u2.x, v = h ? v2.y : v2.x, ww = h ? w2_.y : w2_.x;
+            const double w2 = a * a + b * b + c * c;
+            acc[RQ_MAXW2] = fmax(acc[RQ_MAXW2], fabs(w2));
+            acc[RQ_SUMW2] += w * w2;
+            acc[RQ_SUMW0] += w * a; acc[RQ_SUMW1] += w * b; acc[RQ_SUMW2C] += w * c;
+            acc[RQ_MAXU] = fmax(acc[RQ_MAXU], u); acc[RQ_MAXV] = fmax(acc[RQ_MAXV], v); acc[RQ_MAXWV] = fmax(acc[RQ_MAXWV], ww);
+            acc[RQ_SUMU2] += w * (u * u + v * v + ww * ww);
+            acc[RQ_SUMUW] += w * (u * a + v * b + ww * c);
+            acc[RQ_SUMUH] += w * (u * u + v * v);                          // field_diagnostics.f90:135-142
+            acc[RQ_SUMWH] += w * (a * a + b * b);                          // :215-222
+            acc[RQ_MAXWH] = fmax(acc[RQ_MAXWH], a * a + b * b);           // :237 (sqrt taken on the host)
+        }
     }
     for (int q = 0; q < RQ_N; ++q) {
         const double r = block_reduce(acc[q], (RQ_OPMASK >> q) & 1, red);
@@ -408,35 +420,53 @@ __global__ void k_strain(StrainPtrs f, long long ncol, int nz, int pz, int stric
     PS_SMEM(double, redbuf);
     double gg = 0.0, us = 0.0, ls = 0.0, l1 = 0.0, l2 = 0.0;
     const double vortrms = red ? sqrt(red[RQ_SUMW2] / ncell) : 0.0;
-    const long long n = ncol * pz;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(i % pz);
-        if (z > nz) continue;
-        const double ux = f.dudx[i], uy = f.dudy[i], vy = f.dvdy[i], wx = f.dwdx[i], wy = f.dwdy[i];
-        const double o0 = f.vor[0][i], o1 = f.vor[1][i], o2 = f.vor[2][i];
-        // advance.f90:252-257
-        const double s12 = uy + 0.5 * o2, s13 = wx + 0.5 * o1, s23 = wy - 0.5 * o0;
-        // Only the maximum over the grid is wanted: the matrix is symmetric and traceless, so lambda_max^2 <= 2/3 |S|_F^2,
-        // and a point whose bound does not exceed this thread's running maximum cannot raise it.  The eigenvalues
-        // are evaluated only where it can (and on the two surfaces, which have their own maxima): same result,
-        // the pass becomes a streaming read.
-        const double s33 = -(ux + vy);
-        const double fro = ux * ux + vy * vy + s33 * s33 + 2.0 * (s12 * s12 + s13 * s13 + s23 * s23);
-        const bool surf = (z == nz) || (z == 0);
-        if (surf || fro * (2.0 / 3.0) * (1.0 + 1.0e-9) > gg * gg) {
-            const double l = strict ? jacobi_max_abs(ux, s12, s13, vy, s23, s33)
-                                    : sym3_max_abs(ux, s12, s13, vy, s23, s33);
-            gg = fmax(gg, l);
-            if (z == nz) us = fmax(us, l);
-            if (z == 0) ls = fmax(ls, l);
-        }
-        if (red && z >= 1) {
-            const double v1 = 0.5 * fabs(f.vor[0][i - 1] + o0);
-            const double v2 = 0.5 * fabs(f.vor[1][i - 1] + o1);
-            const double v3 = 0.5 * fabs(f.vor[2][i - 1] + o2);
-            if (v1 + v2 + v3 > vortrms) {
-                l1 += v1 + v2 + v3;
-                l2 += v1 * v1 + v2 * v2 + v3 * v3;
+    // two consecutive z per thread (16-byte loads), 32-bit index arithmetic
+    const unsigned hp = (unsigned)pz >> 1;
+    const unsigned long long n2 = (unsigned long long)ncol * hp;
+    for (unsigned long long i2 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < n2;
+         i2 += (unsigned long long)gridDim.x * blockDim.x) {
+        const int z0 = 2 * (int)((n2 >> 32) ? (i2 % hp) : ((unsigned)i2 % hp));
+        if (z0 > nz) continue;
+        const double2 ux2 = reinterpret_cast<const double2*>(f.dudx)[i2], uy2 = reinterpret_cast<const double2*>(f.dudy)[i2];
+        const double2 vy2 = reinterpret_cast<const double2*>(f.dvdy)[i2], wx2 = reinterpret_cast<const double2*>(f.dwdx)[i2];
+        const double2 wy2 = reinterpret_cast<const double2*>(f.dwdy)[i2];
+        const double2 p0 = reinterpret_cast<const double2*>(f.vor[0])[i2], p1 = reinterpret_cast<const double2*>(f.vor[1])[i2];
+        const double2 p2 = reinterpret_cast<const double2*>(f.vor[2])[i2];
+        // omega one level below the pair (cell averages of get_char_vorticity)
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+        if (red && z0 >= 1) { q0 = f.vor[0][2 * i2 - 1]; q1 = f.vor[1][2 * i2 - 1]; q2 = f.vor[2][2 * i2 - 1]; }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int z = z0 + h;
+            if (z > nz) continue;
+            const double ux = h ? ux2.y : ux2.x, uy = h ? uy2.y : uy2.x, vy = h ? vy2.y : vy2.x;
+            const double wx = h ? wx2.y : wx2.x, wy = h ? wy2.y : wy2.x;
+            const double o0 = h ? p0.y : p0.x, o1 = h ? p1.y : p1.x, o2 = h ? p2.y : p2.x;
+            // advance.f90:252-257
+            const double s12 = uy + 0.5 * o2, s13 = wx + 0.5 * o1, s23 = wy - 0.5 * o0;
+            // Only the maximum over the grid is wanted: the matrix is symmetric and traceless, so lambda_max^2 <= 2/3 |S|_F^2,
+            // and a point whose bound does not exceed this thread's running maximum cannot raise it.  The eigenvalues
+            // are evaluated only where it can (and on the two surfaces, which have their own maxima): same result,
+            // the pass becomes a streaming read.
+            const double s33 = -(ux + vy);
+            const double fro = ux * ux + vy * vy + s33 * s33 + 2.0 * (s12 * s12 + s13 * s13 + s23 * s23);
+            const bool surf = (z == nz) || (z == 0);
+            if (surf || fro * (2.0 / 3.0) * (1.0 + 1.0e-9) > gg * gg) {
+                const double l = strict ? jacobi_max_abs(ux, s12, s13, vy, s23, s33)
+                                        : sym3_max_abs(ux, s12, s13, vy, s23, s33);
+                gg = fmax(gg, l);
+                if (z == nz) us = fmax(us, l);
+                if (z == 0) ls = fmax(ls, l);
+            }
+            if (red && z >= 1) {
+                const double m0 = h ? p0.x : q0, m1 = h ? p1.x : q1, m2 = h ? p2.x : q2;
+                const double v1 = 0.5 * fabs(m0 + o0);
+                const double v2 = 0.5 * fabs(m1 + o1);
+                const double v3 = 0.5 * fabs(m2 + o2);
+                if (v1 + v2 + v3 > vortrms) {
+                    l1 += v1 + v2 + v3;
+                    l2 += v1 * v1 + v2 * v2 + v3 * v3;
+                }
             }
         }
     }

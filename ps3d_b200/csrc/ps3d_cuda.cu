@@ -552,6 +552,9 @@ static void setup_p2p(Ctx& c) {
     if (t.p2p)
         for (int p = 0; p < P; ++p) c.mail.m[p] = reinterpret_cast<PeerMail*>(t.peer_t2[0][p] + c.nint);
     t.peer_sync = getenv("PS3D_NO_PEER_SYNC") ? 0 : 1;
+    // (measured at 4 GPUs, 512^3: 21.5 ms/step split-phase vs 20.8 with one barrier kernel per 2-D FFT -- the three extra
+    //  one-warp kernels per exchange cost more stream time than the decoupling saves; off by default)
+    t.split_phase = (getenv("PS3D_SPLIT_PHASE") && atoi(getenv("PS3D_SPLIT_PHASE"))) ? 1 : 0;
     all.release();
 }
 #endif
@@ -606,6 +609,40 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
         // s1(i+1) writes the peers' buffer (i+1)&1, last read by their s2(i-1): they enter barrier(i) only after it.
         PS_CUDA_TRY(cudaEventRecord(c.ev_first[0], c.stream));
         PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_first[0], 0));
+        if (c.tr.peer_sync && c.tr.split_phase) {
+            // Split-phase protocol (no stream ever blocks on a full barrier): per receive buffer b every rank counts
+            // its exchanges k = 1, 2, ...;
+            //   B: wait[done(b) >= k-1 from every rank] ; s1(i) -> peers' buffer b ; signal arr(b) = k to every rank
+            //   A: wait[arr(b) >= k from every rank] ; s2(i) ; signal done(b) = k to every rank
+            // The NVLink-bound first sweeps run back to back on B, skew between the ranks is absorbed by A, which has
+            // slack (its sweeps are 2-4x shorter).  The flags a rank sends itself order its own two streams.
+            // The kept velocity buffers (>= 2) are read until the next vor2vel: their done flag is sent there.
+            for (int i = 0; i < n; ++i) {
+                if (first[i].scatter < 2) first[i].scatter = i & 1;
+                const int b = first[i].scatter;
+                const unsigned long long k = ++c.tr.use_count[b];
+                first[i].out = c.tr.peer_t2[b][c.rank];
+                first[i].on_comm_stream = true;
+                first[i].max_ctas = (c.p2p_ctas_per_sm >= 0 ? c.p2p_ctas_per_sm : 2) * c.num_sms;
+                if (k > 1) {
+                    PS_LAUNCH((k_peer_wait), dim3(1), dim3(32), 0, c.comm_stream, c.mail, c.rank, c.nranks, 1, b, k - 1);
+                    ++c.launches;
+                }
+                run_sweep(c, first[i]);
+                ++c.tr.n_alltoall;
+                c.tr.bytes_sent += (double)c.nxl * c.nyl * c.pz * 8.0 * (c.nranks - 1);
+                PS_LAUNCH((k_peer_signal), dim3(1), dim3(32), 0, c.comm_stream, c.mail, c.rank, c.nranks, 0, b, k);
+                PS_LAUNCH((k_peer_wait), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, 0, b, k);
+                second[i].in[0] = first[i].out;
+                run_sweep(c, second[i]);
+                if (b < 2) {
+                    PS_LAUNCH((k_peer_signal), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, 1, b, k);
+                    ++c.launches;
+                }
+                c.launches += 2;
+            }
+            return;
+        }
         cross_rank_barrier(c, c.comm_stream);
         for (int i = 0; i < n; ++i) {
             // (a caller may name a dedicated receive buffer >= 2 that it keeps: do_vor2vel)
@@ -1180,6 +1217,17 @@ static void do_vor2vel(Ctx& c) {
     const bool keep1 = (c.nranks == 1 && c.l2_chunks <= 0 && c.keep_velx);
     const bool keepP = (c.nranks > 1 && c.tr.p2p && c.keep_velx && c.velx[0].p);
     const bool keep = keep1 || keepP;
+#ifndef PS3D_EMU
+    if (keepP && c.tr.peer_sync && c.tr.split_phase) {
+        // every earlier reader of the kept velocity buffers (the second sweeps of the last vor2vel, adapt's d/dy sweeps)
+        // is behind this point of the compute stream: the peers may overwrite them
+        for (int b = 2; b < 5; ++b)
+            if (c.tr.use_count[b] > 0) {
+                PS_LAUNCH((k_peer_signal), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, 1, b, c.tr.use_count[b]);
+                ++c.launches;
+            }
+    }
+#endif
     Sweep f[6], g[6];
     for (int i = 0; i < 3; ++i) {
         f[i] = sweep_plain(0, true, false, c.W[i].p, nullptr);        g[i] = sweep_plain(1, true, false, nullptr, c.vor[i].p);

@@ -79,6 +79,9 @@ struct Transport {
     // small all-reduce without a collective launch
     int peer_sync = 1;                          // PS3D_NO_PEER_SYNC=1: one-element NCCL all-reduce / NCCL all-reduces instead
     unsigned long long bar_epoch = 0, ar_epoch = 0;
+    // split-phase exchange protocol (fft2d_batch): exchanges done so far on each peer receive buffer
+    unsigned long long use_count[NPEERBUF] = {};
+    int split_phase = 0;                        // PS3D_SPLIT_PHASE=1: signal / wait pairs instead of one full barrier per 2-D FFT
 
     bool have_nccl() const { return comm != nullptr; }
 };
@@ -88,6 +91,11 @@ struct PeerMail {
     unsigned long long bar_flag[8];             // [src rank]: epoch of src's last barrier arrival
     unsigned long long ar_flag[2][8];           // [parity][src rank]: epoch of src's last all-reduce contribution
     double vals[2][8][32];                      // [parity][src rank][value]
+    // split-phase exchange: [buffer][src rank] = how many exchanges on receive buffer b rank src has
+    //   arr : finished scattering into MY buffer b (its first sweep is complete and visible here)
+    //   done: finished reading out of ITS OWN buffer b (its second sweep is complete: b may be overwritten there)
+    unsigned long long arr_flag[5][8];
+    unsigned long long done_flag[5][8];
 };
 struct PeerMailPtrs { PeerMail* m[8]; };
 
@@ -118,6 +126,27 @@ __global__ void k_peer_barrier(PeerMailPtrs mp, int rank, int nranks, unsigned l
         st_release_sys(&mp.m[p]->bar_flag[rank], epoch);
         spin_until(&mp.m[rank]->bar_flag[p], epoch);
     }
+}
+
+// Split-phase form of the barrier between the two sweeps of a 2-D FFT.  `which` 0 = arr, 1 = done (PeerMail).
+// k_peer_signal: this rank's preceding work on the stream is complete and visible -> every rank's flag [b][rank] = epoch
+// (one thread per destination).  k_peer_wait: spin until every rank's flag [b][p] in MY mailbox has reached epoch.
+// The NVLink-bound first sweeps (comm stream) signal and move on; only the second sweep (compute stream) waits.
+__global__ void k_peer_signal(PeerMailPtrs mp, int rank, int nranks, int which, int b, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p < nranks) {
+        __threadfence_system();
+        PeerMail* m = mp.m[p];
+        st_release_sys(which ? &m->done_flag[b][rank] : &m->arr_flag[b][rank], epoch);
+    }
+}
+__global__ void k_peer_wait(PeerMailPtrs mp, int rank, int nranks, int which, int b, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p < nranks) {
+        const PeerMail* m = mp.m[rank];
+        spin_until(which ? &m->done_flag[b][p] : &m->arr_flag[b][p], epoch);
+    }
+    __threadfence_system();
 }
 
 // All-reduce of red[0..n) over the ranks, sums or maxima per bit of opmask: every rank stores its vector into
