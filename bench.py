@@ -418,6 +418,16 @@ def main():
                 ms7 = float(t7[0])
             nv["scatter_sweep"] = {"ms": ms7, "peer_bytes": nb, "GBs": nb / (ms7 * 1e-3) / 1e9,
                                    "frac_of_900": nb / (ms7 * 1e-3) / 1e9 / 900.0}
+            # the ceiling of SM-issued stores over NVLink on this box: a plain copy kernel (16-byte stores, contiguous) into
+            # the next rank's buffer (whole field) and in the exchange pattern (same peer bytes as the scatter sweep)
+            for w, nm, pb in ((8, "peer_copy_ring", n * n * (nzz + 1) // world * 8), (9, "peer_copy_alltoall", nb)):
+                lib.time_kernel(w, 2)
+                msw = lib.time_kernel(w, 10)
+                tw = torch.tensor([msw], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+                msw = float(tw[0])
+                nv[nm] = {"ms": msw, "peer_bytes": pb, "GBs": pb / (msw * 1e-3) / 1e9}
+            nv["scatter_sweep"]["frac_of_peer_copy"] = nv["scatter_sweep"]["GBs"] / nv["peer_copy_alltoall"]["GBs"]
         except Exception as e:            # NCCL send/recv transport: no fused scatter sweep to time
             nv["scatter_sweep"] = {"unavailable": str(e)[:120]}
         out["nvlink"] = nv

@@ -204,7 +204,9 @@ double ps3d_cuda_last_advance_ms(void);
  *        3 = inverse y sweep, 4 = vor2vel column kernel, 5 = source column kernel,
  *        6 = forward y sweep with the u x omega product in the load (four input fields),
  *        7 = forward y sweep storing straight into the peers' receive buffers over NVLink (nranks > 1 only;
- *            every rank must make the same call) */
+ *            every rank must make the same call),
+ *        8 = plain 16-byte-store copy of one field into the next rank's receive buffer, 9 = the same bytes in the
+ *            exchange pattern (block d to rank d): the NVLink ceiling of SM-issued stores beside kernel 7 */
 int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch);
 
 #ifdef __cplusplus

@@ -2175,9 +2175,9 @@ double ps3d_cuda_last_advance_ms(void) { return g_ctx ? g_ctx->last_advance_ms :
 int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
     PS_API_BEGIN
     Ctx& c = ready();
-    if (!ms_per_launch || reps < 1 || which < 0 || which > 7) fail(PS3D_ERR_BAD_ARGUMENT, "bad time_kernel arguments");
+    if (!ms_per_launch || reps < 1 || which < 0 || which > 9) fail(PS3D_ERR_BAD_ARGUMENT, "bad time_kernel arguments");
 #ifndef PS3D_EMU
-    if (which == 7) {
+    if (which >= 7) {
         if (!(c.nranks > 1 && c.tr.p2p)) fail(PS3D_ERR_BAD_ARGUMENT, "time_kernel 7 (peer-memory scatter sweep) needs nranks > 1 with peer access");
         cross_rank_barrier(c, c.stream);          // every rank is here: the receive buffers are free
     }
@@ -2213,6 +2213,22 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
                 run_sweep(c, s);
                 break;
             }
+#ifndef PS3D_EMU
+            case 8: case 9: {    // NVLink ceiling of SM-issued stores: 8 = the whole field to the next rank, contiguous;
+                                 // 9 = the exchange pattern (block d to rank d, this rank's block stays local), contiguous blocks
+                PeerCopyDst dst;
+                const long long nb = (long long)c.nxl * c.nyl * c.pz;
+                if (which == 8) {
+                    for (int d = 0; d < 8; ++d) dst.p[d] = c.tr.peer_t2[1][(c.rank + 1) % c.nranks];
+                    PS_LAUNCH((k_peer_copy), dim3(c.num_sms * 8), dim3(256), 0, c.stream, (const double*)c.vor[0].p, dst, (long long)c.nint, 0LL, 1);
+                } else {
+                    for (int d = 0; d < 8; ++d) dst.p[d] = c.tr.peer_t2[1][d % c.nranks];
+                    PS_LAUNCH((k_peer_copy), dim3(c.num_sms * 8), dim3(256), 0, c.stream, (const double*)c.vor[0].p, dst, nb, (long long)c.rank * nb, c.nranks);
+                }
+                ++c.launches;
+                break;
+            }
+#endif
             case 5: {
                 SrcArgs a;
                 a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
@@ -2231,7 +2247,7 @@ int ps3d_cuda_time_kernel(int which, int reps, double* ms_per_launch) {
     float ms = 0.f;
     PS_CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
     *ms_per_launch = (double)ms / reps;
-    if (which == 7) { cross_rank_barrier(c, c.stream); ps_sync(c.stream); }
+    if (which >= 7) { cross_rank_barrier(c, c.stream); ps_sync(c.stream); }
 #else
     ps_sync(c.stream);
     *ms_per_launch = 0.0;

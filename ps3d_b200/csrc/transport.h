@@ -149,6 +149,19 @@ __global__ void k_peer_wait(PeerMailPtrs mp, int rank, int nranks, int which, in
     __threadfence_system();
 }
 
+// Plain streaming copy into peer memory (16-byte stores): the ceiling of SM-issued stores over NVLink, measured by
+// ps3d_cuda_time_kernel(8 / 9) beside the scatter sweeps.  Block d of `src` (nb doubles) goes to dst[d] + off.
+struct PeerCopyDst { double* p[8]; };
+__global__ void k_peer_copy(const double* __restrict__ src, PeerCopyDst dst, long long nb, long long off, int nblk) {
+    const long long n2 = nb / 2;
+    for (int d = 0; d < nblk; ++d) {
+        const double2* s2 = reinterpret_cast<const double2*>(src + (long long)d * nb);
+        double2* d2 = reinterpret_cast<double2*>(dst.p[d] + off);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+            d2[i] = s2[i];
+    }
+}
+
 // All-reduce of red[0..n) over the ranks, sums or maxima per bit of opmask: every rank stores its vector into
 // every rank's mailbox, then reduces the P vectors in rank order -- the same order on every rank, so the result
 // is bitwise identical everywhere and independent of timing.

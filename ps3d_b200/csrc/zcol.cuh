@@ -543,9 +543,20 @@ __device__ __forceinline__ void put_pre_sums(const double (&ps)[4], const ZScr<N
 
 // xform2 for pre-processed input (see put_pre).  pk0 / pk1: the parked rows of X0 / X1 (DST); a DCT takes its X_1
 // from the warp totals in sc.wt.  The caller has a barrier between put_pre / put_pre_sums and this call.
+// NOT inlined in the device build: the hot kernels call it three (vor2vel) / two (source) times, and an inlined copy
+// of the transform per call site makes their bodies (105 KB of SASS for vor2vel at nz = 512) overflow the instruction
+// cache when the three resident blocks of an SM run different phases (13 % "no instruction" stalls, ncu r02i).  All
+// its heavy state is internal (the FFT values are loaded here), so a call costs a few pointer arguments.
+#ifdef PS3D_EMU
+#define PS_XFORM_CALL __device__ __forceinline__
+#else
+#define PS_XFORM_CALL __device__ __noinline__
+#endif
 template <int NZ>
-__device__ __forceinline__ void xform2p(double* X0, int kind0, const double* pk0, double* X1, int kind1, const double* pk1,
-                                        const ZScr<NZ>& sc) {
+PS_XFORM_CALL void xform2p_(double* X0, int kind0, const double* pk0, double* X1, int kind1, const double* pk1,
+                            double* sintab, double* wtab) {
+    ZScr<NZ> sc;
+    sc.sintab = sintab; sc.wt = wtab; sc.phim = sc.phip = sc.keep = sc.park = nullptr;
     constexpr int TPF = ZCfg<NZ>::TPF, LC = ZCfg<NZ>::LC, NT = ZCfg<NZ>::NT, NW = (NT < 32) ? 1 : NT / 32;
     const int t = threadIdx.x;
     const int fg = t / (2 * TPF), f = (t / TPF) & 1, u = t - (t / TPF) * TPF, fft = 2 * fg + f;
@@ -571,6 +582,12 @@ __device__ __forceinline__ void xform2p(double* X0, int kind0, const double* pk0
     }
     __syncthreads();                           // every read of the input (and of the warp totals) is done
     xform_tail<NZ>(vr, vi, sa, sb, na, nb, xa, xb, kind, act, u, sc.wt + fft * 8, sc);
+}
+
+template <int NZ>
+__device__ __forceinline__ void xform2p(double* X0, int kind0, const double* pk0, double* X1, int kind1, const double* pk1,
+                                        const ZScr<NZ>& sc) {
+    xform2p_<NZ>(X0, kind0, pk0, X1, kind1, pk1, sc.sintab, sc.wt);
 }
 
 // ---------------------------------------------------------------------------
