@@ -543,15 +543,11 @@ __device__ __forceinline__ void put_pre_sums(const double (&ps)[4], const ZScr<N
 
 // xform2 for pre-processed input (see put_pre).  pk0 / pk1: the parked rows of X0 / X1 (DST); a DCT takes its X_1
 // from the warp totals in sc.wt.  The caller has a barrier between put_pre / put_pre_sums and this call.
-// NOT inlined in the device build: the hot kernels call it three (vor2vel) / two (source) times, and an inlined copy
-// of the transform per call site makes their bodies (105 KB of SASS for vor2vel at nz = 512) overflow the instruction
-// cache when the three resident blocks of an SM run different phases (13 % "no instruction" stalls, ncu r02i).  All
-// its heavy state is internal (the FFT values are loaded here), so a call costs a few pointer arguments.
-#ifdef PS3D_EMU
+// Inlined at every call site.  (Measured: as a real function call -- to shrink the 105 KB body of vor2vel, whose
+// three resident blocks per SM run different phases: 13 % "no instruction" stalls in ncu r02i -- the kernels get
+// SLOWER, vor2vel 4.89 -> 5.70 ms, source 2.77 -> 3.14 ms, same-box A/B profiles/r02o_ab_noinline.log: the values
+// that live across the call are spilled around it.)
 #define PS_XFORM_CALL __device__ __forceinline__
-#else
-#define PS_XFORM_CALL __device__ __noinline__
-#endif
 template <int NZ>
 PS_XFORM_CALL void xform2p_(double* X0, int kind0, const double* pk0, double* X1, int kind1, const double* pk1,
                             double* sintab, double* wtab) {
