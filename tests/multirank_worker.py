@@ -25,6 +25,7 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    buoyancy = len(sys.argv) > 4 and sys.argv[4] == "buoyancy"      # ENABLE_BUOYANCY paths on the slab decomposition
     nx, ny, nz = n, n, n
     lower = np.array([-0.5 * math.pi] * 3)
     extent = np.array([math.pi] * 3)
@@ -75,7 +76,16 @@ def main():
     nxl, nyl = nx // world, ny // world
     xs = slice(rank * nxl, (rank + 1) * nxl)
     kys = PS3DLib.paired_ky(ny)[rank * nyl:(rank + 1) * nyl]
+    if buoyancy:
+        f_cor, bfsq = (0.0, 0.1, 0.2), 0.7
+        buoy = np.random.default_rng(6).uniform(-0.5, 0.5, (nx, ny, nz + 1))
+        ref.f_cor = np.asarray(f_cor)
+        ref.enable_buoyancy(buoy, bfsq)
+        lib.set_physics(f_cor, bfsq)
+        lib.enable_buoyancy()
     lib.upload_vorticity(np.ascontiguousarray(vor[:, xs]))
+    if buoyancy:
+        lib.upload_buoyancy(np.ascontiguousarray(buoy[xs]))
     lib.vor2vel()
     errs = {}
     for name in ("vor", "vel"):
@@ -86,12 +96,18 @@ def main():
     errs["ke"] = abs(d["ke"] - ref.get_kinetic_energy()) / ref.get_kinetic_energy()
     errs["en"] = abs(d["en"] - ref.get_enstrophy()) / ref.get_enstrophy()
     lib.init_diffusion(d["ke"], d["en"])
+    if buoyancy:
+        lib.init_diffusion_buoyancy(d["ke"], d["en"], 3, 20.0, "Kolmogorov", "roll-mean-bfmax", 2)
+        ref.init_diffusion_buoyancy(ref.get_kinetic_energy(), ref.get_enstrophy(), 3, 20.0)
     lib.stepper_setup(stepper)
     t = tr = 0.0
     for _ in range(2):
         t, dt, diag = lib.advance(t, 100.0)
-        tr, dtr = ref.advance(tr, 100.0, stepper, literal=True)
+        tr, dtr = ref.advance(tr, 100.0, stepper, literal=True, bpretype="roll-mean-bfmax", bwin=2)
         errs["dt"] = max(errs.get("dt", 0.0), abs(dt - dtr) / dtr)
+        if buoyancy:
+            errs["bfmax"] = max(errs.get("bfmax", 0.0), abs(diag["bfmax"] - ref.diag["bfmax"]) / ref.diag["bfmax"])
+            errs["sbuoy"] = max(errs.get("sbuoy", 0.0), rel(lib.download("sbuoy"), ref.sbuoy[:, kys]))
         for k in ("vortmax", "vortrms", "vorch", "ggmax", "umax", "usggmax", "lsggmax"):
             errs[k] = max(errs.get(k, 0.0), abs(diag[k] - ref.diag[k]) / abs(ref.diag[k]))
     errs["svor_after"] = rel(lib.download3("svor"), ref.svor[:, :, kys])

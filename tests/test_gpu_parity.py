@@ -433,6 +433,23 @@ def test_multi_gpu_slab_matches_oracle(nranks):
     assert res.stdout.count("worst") == nranks
 
 
+def test_multi_gpu_buoyancy_matches_oracle():
+    """The ENABLE_BUOYANCY paths on a 2-GPU slab decomposition (peer-memory transport) against the one-rank oracle."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29623", os.path.join(root, "tests", "multirank_worker.py"), "cuda", "cn2", "32",
+           "buoyancy"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("worst") == 2
+
+
 def test_cpp_driver_matches_oracle(lib):
     """examples/ps3d_driver.cpp (C++ stand-in for ps3d.f90) through the same C ABI: 5 cn2 steps of Beltrami 32^3."""
     import os
