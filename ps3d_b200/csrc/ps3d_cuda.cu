@@ -189,10 +189,10 @@ struct Ctx {
     // streamed upload (ps3d_cuda_upload_vorticity_begin / _end): three staging fields filled by a copy stream while
     // the compute stream works on the previous state
     DevBuf<double> stage3;
-    ps_stream_t copy_stream = 0;
+    ps_stream_t copy_stream = 0, copy_stream2 = 0;   // two copy streams: the three components go over two DMA engines
     bool upload_pending = false;
 #ifndef PS3D_EMU
-    cudaEvent_t ev_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_copy2 = nullptr;
 #endif
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
     DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
@@ -519,7 +519,7 @@ static void setup_p2p(Ctx& c) {
     if (!t.have_nccl() || getenv("PS3D_NO_P2P")) return;
     const int P = t.nranks;
     constexpr int NB = Transport::NPEERBUF;
-    double* local[NB] = {c.W[6].p, c.W[8].p, c.velx[0].p, c.velx[1].p, c.velx[2].p};
+    double* local[NB] = {c.W[6].p, c.W[8].p, c.velx[0].p, c.velx[1].p, c.velx[2].p, c.W[5].p, c.W[7].p};
     cudaIpcMemHandle_t mine[NB];
     int ok = 1;
     for (int b = 0; b < NB; ++b)
@@ -552,6 +552,7 @@ static void setup_p2p(Ctx& c) {
     if (t.p2p)
         for (int p = 0; p < P; ++p) c.mail.m[p] = reinterpret_cast<PeerMail*>(t.peer_t2[0][p] + c.nint);
     t.peer_sync = getenv("PS3D_NO_PEER_SYNC") ? 0 : 1;
+    t.rot_bufs = (getenv("PS3D_ROT_BUFS") && atoi(getenv("PS3D_ROT_BUFS")) == 2) ? 2 : 4;
     // (measured at 4 GPUs, 512^3: 21.5 ms/step split-phase vs 20.8 with one barrier kernel per 2-D FFT -- the three extra
     //  one-warp kernels per exchange cost more stream time than the decoupling saves; off by default)
     t.split_phase = (getenv("PS3D_SPLIT_PHASE") && atoi(getenv("PS3D_SPLIT_PHASE"))) ? 1 : 0;
@@ -617,8 +618,8 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
             // The NVLink-bound first sweeps run back to back on B, skew between the ranks is absorbed by A, which has
             // slack (its sweeps are 2-4x shorter).  The flags a rank sends itself order its own two streams.
             // The kept velocity buffers (>= 2) are read until the next vor2vel: their done flag is sent there.
-            for (int i = 0; i < n; ++i) {
-                if (first[i].scatter < 2) first[i].scatter = i & 1;
+            for (int i = 0, j = 0; i < n; ++i) {
+                if (!Transport::is_kept(first[i].scatter)) first[i].scatter = Transport::rot_index(j++ % c.tr.rot_bufs);
                 const int b = first[i].scatter;
                 const unsigned long long k = ++c.tr.use_count[b];
                 first[i].out = c.tr.peer_t2[b][c.rank];
@@ -635,7 +636,7 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
                 PS_LAUNCH((k_peer_wait), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, 0, b, k);
                 second[i].in[0] = first[i].out;
                 run_sweep(c, second[i]);
-                if (b < 2) {
+                if (!Transport::is_kept(b)) {
                     PS_LAUNCH((k_peer_signal), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, 1, b, k);
                     ++c.launches;
                 }
@@ -644,9 +645,12 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
             return;
         }
         cross_rank_barrier(c, c.comm_stream);
-        for (int i = 0; i < n; ++i) {
-            // (a caller may name a dedicated receive buffer >= 2 that it keeps: do_vor2vel)
-            if (first[i].scatter < 2) first[i].scatter = i & 1;
+        const int NR = c.tr.rot_bufs;
+        for (int i = 0, j = 0; i < n; ++i) {
+            // (a caller may name a dedicated receive buffer that it keeps: do_vor2vel); the others rotate through NR
+            // buffers: s1(i+1) overwrites the buffer last read by a second sweep no later than s2(i+1-NR), and every
+            // rank enters barrier(i) only after its s2(i+1-NR)
+            if (!Transport::is_kept(first[i].scatter)) first[i].scatter = Transport::rot_index(j++ % NR);
             first[i].out = c.tr.peer_t2[first[i].scatter][c.rank];
             first[i].on_comm_stream = true;
             // persistent launch, two blocks per SM: the system-scope fence that ends a scatter sweep is then paid once
@@ -656,7 +660,7 @@ static void fft2d_batch(Ctx& c, int n, Sweep* first, Sweep* second) {
             run_sweep(c, first[i]);
             ++c.tr.n_alltoall;
             c.tr.bytes_sent += (double)c.nxl * c.nyl * c.pz * 8.0 * (c.nranks - 1);
-            if (i >= 1) PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_second[i - 1], 0));
+            if (i + 1 - NR >= 0) PS_CUDA_TRY(cudaStreamWaitEvent(c.comm_stream, c.ev_second[i + 1 - NR], 0));
             cross_rank_barrier(c, c.comm_stream);
             PS_CUDA_TRY(cudaEventRecord(c.ev_a2a[i], c.comm_stream));
             PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_a2a[i], 0));
@@ -1174,7 +1178,9 @@ static void do_finalise() {
     c->stage3.release();
 #ifndef PS3D_EMU
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->copy_stream2) { cudaStreamSynchronize(c->copy_stream2); cudaStreamDestroy(c->copy_stream2); }
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_copy2) cudaEventDestroy(c->ev_copy2);
 #endif
     DevBuf<double>* singles[] = {&c->stage, &c->kxl, &c->kyline, &c->kxd, &c->kyd, &c->k2l2, &c->k2l2i, &c->zm, &c->zp,
                                  &c->rkz, &c->gamtop, &c->gambot, &c->filt2d, &c->filtz, &c->vhdis, &c->fac1, &c->fac2,
@@ -1221,7 +1227,7 @@ static void do_vor2vel(Ctx& c) {
     if (keepP && c.tr.peer_sync && c.tr.split_phase) {
         // every earlier reader of the kept velocity buffers (the second sweeps of the last vor2vel, adapt's d/dy sweeps)
         // is behind this point of the compute stream: the peers may overwrite them
-        for (int b = 2; b < 5; ++b)
+        for (int b = 2; b <= 4; ++b)
             if (c.tr.use_count[b] > 0) {
                 PS_LAUNCH((k_peer_signal), dim3(1), dim3(32), 0, c.stream, c.mail, c.rank, c.nranks, 1, b, c.tr.use_count[b]);
                 ++c.launches;
@@ -1672,12 +1678,22 @@ static void do_upload_begin(Ctx& c, const double* vor_phys) {
 #ifndef PS3D_EMU
     if (!c.copy_stream) {
         PS_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        PS_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream2, cudaStreamNonBlocking));
         PS_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+        PS_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy2, cudaEventDisableTiming));
     }
+    const bool two = getenv("PS3D_ONE_COPY_STREAM") == nullptr;
+    ps_stream_t s2 = two ? c.copy_stream2 : c.copy_stream;
+#else
+    ps_stream_t s2 = c.copy_stream;
 #endif
-    ps_h2d(c.stage3.p, vor_phys, 3 * c.nnat * sizeof(double), c.copy_stream);
+    // halves of the buffer on the two streams (any split works: _end waits for both)
+    const size_t half = (3 * c.nnat / 2) & ~(size_t)1;
+    ps_h2d(c.stage3.p, vor_phys, half * sizeof(double), c.copy_stream);
+    ps_h2d(c.stage3.p + half, vor_phys + half, (3 * c.nnat - half) * sizeof(double), s2);
 #ifndef PS3D_EMU
     PS_CUDA_TRY(cudaEventRecord(c.ev_copy, c.copy_stream));
+    PS_CUDA_TRY(cudaEventRecord(c.ev_copy2, s2));
 #endif
     c.upload_pending = true;
 }
@@ -1686,6 +1702,7 @@ static void do_upload_end(Ctx& c) {
     if (!c.upload_pending) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_end without upload_vorticity_begin");
 #ifndef PS3D_EMU
     PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+    PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy2, 0));
 #endif
     for (int i = 0; i < 3; ++i) {
         PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)(c.stage3.p + (size_t)i * c.nnat),

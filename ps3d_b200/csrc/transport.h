@@ -68,9 +68,12 @@ struct Transport {
     allreduce_fn ar_cb = nullptr;
     void* user = nullptr;
     bool p2p = false;                 // sweeps store straight into the peers' receive buffers (CUDA IPC)
-    // [buffer][rank]: base of that rank's receive buffer.  Buffers 0, 1: the two rotating receive fields of the 2-D
-    // FFT pipeline; 2..4: the kept x-transformed velocity of the last vor2vel (Ctx::velx), see do_vor2vel
-    static constexpr int NPEERBUF = 5;
+    // [buffer][rank]: base of that rank's receive buffer.  Buffers 0, 1, 5, 6: the rotating receive fields of the 2-D
+    // FFT pipeline (rot_bufs of them in use); 2..4: the kept x-transformed velocity of the last vor2vel (Ctx::velx)
+    static constexpr int NPEERBUF = 7;
+    int rot_bufs = 4;                           // PS3D_ROT_BUFS=2: two rotating receive buffers (r01 / r02k behaviour)
+    static int rot_index(int j) { const int t[4] = {0, 1, 5, 6}; return t[j & 3]; }
+    static bool is_kept(int b) { return b >= 2 && b <= 4; }
     double* peer_t2[NPEERBUF][8] = {};
     void* ipc_opened[NPEERBUF][8] = {};
     long long n_alltoall = 0;
@@ -94,8 +97,8 @@ struct PeerMail {
     // split-phase exchange: [buffer][src rank] = how many exchanges on receive buffer b rank src has
     //   arr : finished scattering into MY buffer b (its first sweep is complete and visible here)
     //   done: finished reading out of ITS OWN buffer b (its second sweep is complete: b may be overwritten there)
-    unsigned long long arr_flag[5][8];
-    unsigned long long done_flag[5][8];
+    unsigned long long arr_flag[7][8];
+    unsigned long long done_flag[7][8];
 };
 struct PeerMailPtrs { PeerMail* m[8]; };
 
