@@ -98,7 +98,9 @@ int ps3d_cuda_upload_vorticity(const double* vor_phys);
 /* Streamed form of ps3d_cuda_upload_vorticity for hosts that hand over a new state while the device is busy:
  * _begin queues the host -> device copies of the three components on a copy stream (vor_phys must stay valid and
  * should be pinned) and returns at once -- they overlap a running ps3d_cuda_advance of the previous state; _end
- * waits for them and decomposes (utils.f90:160-165).  The state is replaced only by _end. */
+ * waits for them and decomposes (utils.f90:160-165).  The state is replaced only by _end.  Up to two uploads may be
+ * queued (first in, first out; two staging sets), so that the copy of state k+1 can be started before _end of
+ * state k and also overlaps its decomposition. */
 int ps3d_cuda_upload_vorticity_begin(const double* vor_phys);
 int ps3d_cuda_upload_vorticity_end(void);
 int ps3d_cuda_vor2vel(void);                                          /* inversion.f90:23 */

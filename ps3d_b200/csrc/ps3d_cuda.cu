@@ -188,11 +188,11 @@ struct Ctx {
     DevBuf<double> stage;                 // natural-layout staging for the host boundary
     // streamed upload (ps3d_cuda_upload_vorticity_begin / _end): three staging fields filled by a copy stream while
     // the compute stream works on the previous state
-    DevBuf<double> stage3;
-    ps_stream_t copy_stream = 0, copy_stream2 = 0;   // two copy streams: the three components go over two DMA engines
-    bool upload_pending = false;
+    DevBuf<double> stage3[2];                        // two staging sets: a second upload may be queued while the first waits for _end
+    ps_stream_t copy_stream = 0;
+    int upload_head = 0, upload_pending = 0;         // FIFO of queued uploads (depth <= 2)
 #ifndef PS3D_EMU
-    cudaEvent_t ev_copy = nullptr, ev_copy2 = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
 #endif
     DevBuf<double> kxl, kyline, kxd, kyd, k2l2, k2l2i, zm, zp, rkz, gamtop, gambot;
     DevBuf<double> filt2d, filtz, vhdis, fac1, fac2, wz, ini_mean, partial, red;
@@ -1175,13 +1175,11 @@ static void do_finalise() {
     for (int b = 0; b < Transport::NPEERBUF; ++b) for (int p = 0; p < 8; ++p) if (c->tr.ipc_opened[b][p]) cudaIpcCloseMemHandle(c->tr.ipc_opened[b][p]);
     if (c->tr.comm) c->tr.nccl.CommDestroy(c->tr.comm);
 #endif
-    c->stage3.release();
 #ifndef PS3D_EMU
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-    if (c->copy_stream2) { cudaStreamSynchronize(c->copy_stream2); cudaStreamDestroy(c->copy_stream2); }
-    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
-    if (c->ev_copy2) cudaEventDestroy(c->ev_copy2);
+    for (int i = 0; i < 2; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
 #endif
+    c->stage3[0].release(); c->stage3[1].release();
     DevBuf<double>* singles[] = {&c->stage, &c->kxl, &c->kyline, &c->kxd, &c->kyd, &c->k2l2, &c->k2l2i, &c->zm, &c->zp,
                                  &c->rkz, &c->gamtop, &c->gambot, &c->filt2d, &c->filtz, &c->vhdis, &c->fac1, &c->fac2,
                                  &c->wz, &c->ini_mean, &c->partial, &c->red};
@@ -1673,39 +1671,30 @@ static void do_upload_vorticity(Ctx& c, const double* vor_phys) {
 // streamed form of do_upload_vorticity: _begin queues the three host -> device copies on the copy stream and
 // returns; _end makes the compute stream wait for them, then repacks and decomposes (utils.f90:160-165)
 static void do_upload_begin(Ctx& c, const double* vor_phys) {
-    if (c.upload_pending) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_begin called twice without upload_vorticity_end");
-    if (!c.stage3.p) c.stage3.alloc(3 * c.nnat);
+    if (c.upload_pending >= 2) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_begin: two uploads are already queued (call upload_vorticity_end)");
+    const int slot = (c.upload_head + c.upload_pending) & 1;
+    if (!c.stage3[slot].p) c.stage3[slot].alloc(3 * c.nnat);
 #ifndef PS3D_EMU
     if (!c.copy_stream) {
         PS_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-        PS_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream2, cudaStreamNonBlocking));
-        PS_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
-        PS_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy2, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) PS_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy[i], cudaEventDisableTiming));
     }
-    const bool two = getenv("PS3D_ONE_COPY_STREAM") == nullptr;
-    ps_stream_t s2 = two ? c.copy_stream2 : c.copy_stream;
-#else
-    ps_stream_t s2 = c.copy_stream;
 #endif
-    // halves of the buffer on the two streams (any split works: _end waits for both)
-    const size_t half = (3 * c.nnat / 2) & ~(size_t)1;
-    ps_h2d(c.stage3.p, vor_phys, half * sizeof(double), c.copy_stream);
-    ps_h2d(c.stage3.p + half, vor_phys + half, (3 * c.nnat - half) * sizeof(double), s2);
+    ps_h2d(c.stage3[slot].p, vor_phys, 3 * c.nnat * sizeof(double), c.copy_stream);
 #ifndef PS3D_EMU
-    PS_CUDA_TRY(cudaEventRecord(c.ev_copy, c.copy_stream));
-    PS_CUDA_TRY(cudaEventRecord(c.ev_copy2, s2));
+    PS_CUDA_TRY(cudaEventRecord(c.ev_copy[slot], c.copy_stream));
 #endif
-    c.upload_pending = true;
+    ++c.upload_pending;
 }
 
 static void do_upload_end(Ctx& c) {
-    if (!c.upload_pending) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_end without upload_vorticity_begin");
+    if (c.upload_pending < 1) fail(PS3D_ERR_BAD_ARGUMENT, "upload_vorticity_end without upload_vorticity_begin");
+    const int slot = c.upload_head;
 #ifndef PS3D_EMU
-    PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
-    PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy2, 0));
+    PS_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy[slot], 0));
 #endif
     for (int i = 0; i < 3; ++i) {
-        PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)(c.stage3.p + (size_t)i * c.nnat),
+        PS_LAUNCH((k_repack_in), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, (const double*)(c.stage3[slot].p + (size_t)i * c.nnat),
                   c.vor[i].p, c.nxl, c.ny, c.nzp, c.pz, (const int*)nullptr);
         ++c.launches;
         fft2d_fwd(c, c.vor[i].p, c.W[0].p);
@@ -1713,7 +1702,8 @@ static void do_upload_end(Ctx& c) {
     }
     vor_mean(c, 0);
     ps_sync(c.stream);
-    c.upload_pending = false;
+    c.upload_head ^= 1;
+    --c.upload_pending;
 }
 
 // pressure (fields_derived.f90:67-157), lazily: needs the five strain fields

@@ -201,12 +201,12 @@ class PS3DLib:
         """Queue the host -> device copies and return; `vor` (C-contiguous float64, ideally pinned) must stay alive
         until upload_vorticity_end()."""
         assert vor.dtype == np.float64 and vor.flags["C_CONTIGUOUS"] and vor.shape == (3,) + self.shape
-        self._pending_upload = vor
         self._call("ps3d_cuda_upload_vorticity_begin", _ptr(vor))
+        self._pending_uploads = getattr(self, "_pending_uploads", []) + [vor]      # keep the buffers alive (FIFO, depth <= 2)
 
     def upload_vorticity_end(self):
         self._call("ps3d_cuda_upload_vorticity_end")
-        self._pending_upload = None
+        self._pending_uploads = getattr(self, "_pending_uploads", [None])[1:]
 
     def vor2vel(self): self._call("ps3d_cuda_vor2vel")
     def source(self): self._call("ps3d_cuda_source")

@@ -353,10 +353,13 @@ def test_streamed_upload_matches_blocking_upload(emu):
         emu.upload_vorticity(v1)
         emu.upload_vorticity_begin(v2)
         assert np.array_equal(emu.download3("svor"), s1)
+        emu.upload_vorticity_begin(v1)                 # a second upload may be queued (two staging sets) ...
         with pytest.raises(Exception):
-            emu.upload_vorticity_begin(v2)
+            emu.upload_vorticity_begin(v2)             # ... a third may not
         emu.upload_vorticity_end()
-        assert np.array_equal(emu.download3("svor"), s2)
+        assert np.array_equal(emu.download3("svor"), s2)         # first in, first out
+        emu.upload_vorticity_end()
+        assert np.array_equal(emu.download3("svor"), s1)
         with pytest.raises(Exception):
             emu.upload_vorticity_end()
     finally:
