@@ -101,3 +101,20 @@ def test_cuda_trajectory_matches_golden(stepper, tag):
         assert np.max(np.abs(svor - g["svor_sample"])) < 1e-10 * float(g["svor_max"])
     finally:
         s.close()
+
+
+def test_gpu_series_512_matches_cpu_restatement_series():
+    """BASELINE config 4 at FULL size: tests/golden/beltrami512_cn2_series.json was generated by the CUDA path on one
+    B200 (tools/make_golden_512.py; bench.py checks every run against it), tests/golden/beltrami512_cn2_cpu_ref.json by
+    the C++ restatement of the reference with the literal stafft kernels on the host cores of the same kind of box
+    (tools/make_golden_512_cpu.py, ~2 min per step).  The two independent computations of the first steps of the
+    benchmark trajectory must agree within the north_star bar: dt 1e-11, KE / enstrophy / helicity 1e-10."""
+    import json
+    gpu = json.load(open(os.path.join(G, "beltrami512_cn2_series.json")))
+    cpu = json.load(open(os.path.join(G, "beltrami512_cn2_cpu_ref.json")))
+    n = len(cpu["dt"])
+    assert n >= 2 and cpu["grid"] == gpu["grid"] == 512
+    for i in range(n):
+        assert cpu["dt"][i] == pytest.approx(gpu["dt"][i], rel=1e-11), i
+        for k in ("ke", "en", "helicity"):
+            assert cpu[k][i] == pytest.approx(gpu[k][i], rel=1e-10), (k, i)
