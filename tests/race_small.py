@@ -26,6 +26,16 @@ for nx, ny, nz in [(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(8,
     errs = [np.max(np.abs(lib.download3(n) - getattr(s, n))) / np.max(np.abs(getattr(s, n))) for n in ("svor", "vor", "svel", "vel")]
     lib.source(); s.source()
     errs.append(np.max(np.abs(lib.download3("svorts") - s.svorts)) / np.max(np.abs(s.svorts)))
+    # the fused cn2 update of the source kernel (ps3d_cuda_advance) and the spectral diffz of the buoyancy build
+    d = lib.diagnostics()
+    lib.init_diffusion(d["ke"], d["en"])
+    s.init_diffusion(s.get_kinetic_energy(), s.get_enstrophy())
+    lib.stepper_setup("cn2")
+    lib.advance(0.0, 100.0); s.advance(0.0, 100.0, "cn2", literal=True)
+    errs.append(np.max(np.abs(lib.download3("svor") - s.svor)) / np.max(np.abs(s.svor)))
+    if (nz & (nz - 1)) == 0:
+        fs = s.field_decompose_physical(np.random.default_rng(3).uniform(-1, 1, (nx, ny, nz + 1)))
+        errs.append(np.max(np.abs(lib.diffz(fs) - s.diffz(fs))) / np.max(np.abs(s.diffz(fs))))
     print((nx, ny, nz), ["%.1e" % e for e in errs], flush=True)
     worst = max(worst, max(errs))
     lib.finalise()
