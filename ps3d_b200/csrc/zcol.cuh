@@ -311,9 +311,26 @@ __device__ __forceinline__ Theta hyp_theta(const Hyp& h, double zm, double zp, d
 // ---- z transforms on 4-slot shared-memory fields ------------------------------
 enum { XF_DST = 0, XF_DCT = 1 };
 
-// inclusive scan of (a, b) over the TPF consecutive threads of one FFT (u = index inside the FFT)
+// Barrier over the TPF threads of ONE FFT (its exchanges, the regrouping of its spectrum and its scan touch only its
+// own two column buffers and its own slice of wt): a named barrier when the group is whole warps, else the block's.
+// PS3D_ZBAR_BLOCK (build switch) falls back to block-wide barriers everywhere.  Every thread of the block makes the
+// same sequence of calls (inactive groups included), so the test-only emulator can map it onto __syncthreads.
 template <int TPF>
-__device__ __forceinline__ void group_scan2(double& a, double& b, int u, double* wt) {
+struct ZBar {
+    int id;         // 1 + index of the FFT inside the block
+    __device__ __forceinline__ void operator()() const {
+#if defined(PS3D_EMU) || defined(PS3D_ZBAR_BLOCK)
+        __syncthreads();
+#else
+        if (TPF >= 32 && TPF % 32 == 0) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TPF) : "memory");
+        else __syncthreads();
+#endif
+    }
+};
+
+// inclusive scan of (a, b) over the TPF consecutive threads of one FFT (u = index inside the FFT)
+template <int TPF, class BAR>
+__device__ __forceinline__ void group_scan2(double& a, double& b, int u, double* wt, const BAR& bar) {
     constexpr int W = (TPF < 32) ? TPF : 32;
 #pragma unroll
     for (int d = 1; d < W; d <<= 1) {
@@ -324,7 +341,7 @@ __device__ __forceinline__ void group_scan2(double& a, double& b, int u, double*
     if (TPF > 32) {
         const int w = u >> 5;
         if ((u & 31) == 31) { wt[2 * w] = a; wt[2 * w + 1] = b; }
-        __syncthreads();
+        bar();
         for (int v = 0; v < w; ++v) { a += wt[2 * v]; b += wt[2 * v + 1]; }
     }
 }
@@ -366,8 +383,9 @@ __device__ __forceinline__ void xform_tail(double (&vr)[8], double (&vi)[8], dou
                                            double* xa, double* xb, int kind, bool act, int u, double* wt, const ZScr<NZ>& sc) {
     constexpr int n = NZ, TPF = ZCfg<NZ>::TPF;
     const IxSwz ix;
-    block_cfft<n, false>(vr, vi, u, act, xa, xb, ix, TwSin<NZ>{sc.sintab});
-    __syncthreads();
+    const ZBar<TPF> bar{1 + (int)(threadIdx.x / TPF)};
+    block_cfft<n, false>(vr, vi, u, act, xa, xb, ix, TwSin<NZ>{sc.sintab}, bar);
+    bar();
     if (act) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -375,7 +393,7 @@ __device__ __forceinline__ void xform_tail(double (&vr)[8], double (&vi)[8], dou
             xa[idx] = vr[e]; xb[idx] = vi[e];
         }
     }
-    __syncthreads();
+    bar();
 
     // ---- post-process: thread u owns k = 4u .. 4u+3, i.e. output rows 8u .. 8u+7
     double oa[4], ob[4], ea[4], eb[4];
@@ -404,8 +422,8 @@ __device__ __forceinline__ void xform_tail(double (&vr)[8], double (&vi)[8], dou
 #pragma unroll
     for (int c = 1; c < 4; ++c) { oa[c] += oa[c - 1]; ob[c] += ob[c - 1]; }
     double ta = oa[3], tb = ob[3];
-    group_scan2<TPF>(ta, tb, u, wt + 4);
-    if (TPF <= 32) __syncthreads();            // every read of the spectrum is done before the rows are written
+    group_scan2<TPF>(ta, tb, u, wt + 4, bar);
+    if (TPF <= 32) bar();                      // every read of the spectrum is done before the rows are written
     const double pa = ta - oa[3], pb = tb - ob[3];      // exclusive prefix of this thread
     const double scl = sqrt(2.0 / (double)n);
     if (act) {
