@@ -158,7 +158,7 @@ struct Ctx {
     double last_advance_ms = 0.0;
     double last_diag[16] = {};           // diagnostics of the last adapt (advance.f90: set_netcdf_field_diagnostic)
     bool have_diag = false;
-    bool svorts_stale = false;           // the last source call carried the cn2 update and did not store svorts
+    bool svorts_stale = false;           // the last source call carried a stepper update and did not store svorts
 
     DevBuf<double> svor[3], vor[3], vel[3], svel[3], svorts[3], wa[3], wb[3], W[9];
     // one rank: the x-transformed velocity of the last vor2vel ([x][ky'][pz], the intermediate between the two sweeps
@@ -780,21 +780,26 @@ static void launch_v2v(Ctx& c, const V2VArgs& a) {
     }
 }
 
-template <int NZ>
-static void launch_src_n(Ctx& c, const SrcArgs& a) {
+template <int NZ, bool RK>
+static void launch_src_nr(Ctx& c, const SrcArgs& a) {
     const SpecGeom gf = c.geom_fast();
     if (gf.npf > 0) {
         const size_t sm = src_smem_bytes<NZ>(false);
-        allow_smem(k_source_spec<NZ, false>, sm);
-        PS_LAUNCH((k_source_spec<NZ, false>), dim3((c.nx / 2 + 1) * gf.npf), dim3(ZCfg<NZ>::NT), sm, c.stream, gf, a);
+        allow_smem(k_source_spec<NZ, false, RK>, sm);
+        PS_LAUNCH((k_source_spec<NZ, false, RK>), dim3((c.nx / 2 + 1) * gf.npf), dim3(ZCfg<NZ>::NT), sm, c.stream, gf, a);
         ++c.launches;
     }
     if (c.rank == 0) {
         const size_t sm = src_smem_bytes<NZ>(true);
-        allow_smem(k_source_spec<NZ, true>, sm);
-        PS_LAUNCH((k_source_spec<NZ, true>), dim3(c.nx / 2 + 1), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom_gen(), a);
+        allow_smem(k_source_spec<NZ, true, RK>, sm);
+        PS_LAUNCH((k_source_spec<NZ, true, RK>), dim3(c.nx / 2 + 1), dim3(ZCfg<NZ>::NT), sm, c.stream, c.geom_gen(), a);
         ++c.launches;
     }
+}
+template <int NZ>
+static void launch_src_n(Ctx& c, const SrcArgs& a) {
+    if (a.upd >= 11) launch_src_nr<NZ, true>(c, a);
+    else launch_src_nr<NZ, false>(c, a);
 }
 static void launch_src(Ctx& c, const SrcArgs& a) {
     if (c.gen[2]) {
@@ -1274,7 +1279,9 @@ static StepArgs buoy_step_args(Ctx& c);
 
 // upd < 0: svorts only.  upd = 0 / 1 (cn2, power-of-two nz): the Crank-Nicolson update of cn2.f90:120-135 /
 // :162-173 rides on the last stage of the source kernel, svorts is not stored (see SrcArgs)
-static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0) {
+// upd = 11..14 (impl-diff-rk4, power-of-two nz): substep one..four rides on it the same way (c1, c2 = the stage
+// coefficients, pq = epq or filt(0,:,:)); the buoyancy updates stay separate kernels (rk4_update_buoy)
+static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0, double c2 = 0.0, const double* pq = nullptr) {
     const double* fc = c.f_cor;              // vor + f_cor (inversion.f90:310-314; `vor` itself stays relative here)
     if (c.buoyancy) do_buoyancy_tendency(c); // inversion.f90:381-383; also leaves the semi-spectral b' in bsem
     const double *u = c.vel[0].p, *v = c.vel[1].p, *w = c.vel[2].p;
@@ -1295,13 +1302,14 @@ static void do_source(Ctx& c, int upd = -1, double dt2 = 0.0) {
     SrcArgs a;
     a.r = c.W[0].p; a.q = c.W[1].p; a.p = c.W[2].p;
     a.s0 = c.svorts[0].p; a.s1 = c.svorts[1].p; a.s2 = c.svorts[2].p;
-    a.upd = upd; a.c1 = dt2;
+    a.upd = upd; a.c1 = dt2; a.c2 = c2;
     const StepArgs st = step_args(c);
-    for (int i = 0; i < 3; ++i) { a.svor[i] = st.svor[i]; a.vortsm[i] = st.wa[i]; }
+    for (int i = 0; i < 3; ++i) { a.svor[i] = st.svor[i]; a.vortsm[i] = st.wa[i]; a.wb[i] = st.wb[i]; }
     a.f2d = st.f2d; a.filtz = st.filtz; a.vd = st.vd;
+    a.mq = st.mq; a.pq = pq ? pq : st.pq;
     launch_src(c, a);
     c.svorts_stale = (upd >= 0);
-    if (upd >= 0) vor_mean(c, 1);
+    if (upd >= 0 && upd < 11) vor_mean(c, 1);          // cn2: adjust_vorticity_mean after every update (cn2.f90:137, 175); rk4: once, at the end
 }
 
 static void vor_mean(Ctx& c, int mode) {
@@ -1419,13 +1427,16 @@ static void cn2_update_buoy(Ctx& c, double dt2, int stage) {
     ++c.launches;
 }
 
+static void rk4_update_buoy(Ctx& c, int stage, double c1, double c2, const double* pq) {
+    if (!c.buoyancy) return;                           // sbuoy (impl_rk4.f90:99-105, 124-131, 154-164, 187-195)
+    StepArgs b = buoy_step_args(c);
+    b.c1 = c1; b.c2 = c2; b.stage = stage; b.pq = (stage == 1) ? pq : c.bfac2.p;
+    PS_LAUNCH((k_rk4_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, b);
+    ++c.launches;
+}
+
 static void rk4_update(Ctx& c, int stage, double c1, double c2, const double* pq) {
-    if (c.buoyancy) {                                  // sbuoy first (impl_rk4.f90:99-105, 124-131, 154-164, 187-195)
-        StepArgs b = buoy_step_args(c);
-        b.c1 = c1; b.c2 = c2; b.stage = stage; b.pq = (stage == 1) ? pq : c.bfac2.p;
-        PS_LAUNCH((k_rk4_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, b);
-        ++c.launches;
-    }
+    rk4_update_buoy(c, stage, c1, c2, pq);
     StepArgs a = step_args(c);
     a.c1 = c1; a.c2 = c2; a.stage = stage; a.pq = pq;
     PS_LAUNCH((k_rk4_update), dim3(stream_blocks(c.nint)), dim3(256), 0, c.stream, a);
@@ -1446,6 +1457,8 @@ static void square_factor(Ctx& c, int mode) {                  // emq = emq**2 /
 
 // the cn2 update can ride on the source kernel (power-of-two nz; PS3D_NO_FUSED_UPDATE=1 keeps it separate)
 static bool cn2_fused(const Ctx& c) { return c.stepper == PS3D_STEPPER_CN2 && !c.gen[2] && c.fuse_update; }
+// ... and so can the four substeps of impl-diff-rk4
+static bool rk4_fused(const Ctx& c) { return c.stepper == PS3D_STEPPER_IMPL_RK4 && !c.gen[2] && c.fuse_update; }
 
 // first_update_done: the source call before this step already carried the first update (ps3d_cuda_advance)
 static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false) {
@@ -1467,6 +1480,29 @@ static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false
         *t += dt;
     } else {
         const double dt2 = 0.5 * dt, dt3 = dt / 3.0, dt6 = dt / 6.0;   // impl_rk4.f90:82-84
+        if (rk4_fused(c)) {
+            // every substep rides on the source kernel that produces its tendency (the factor tables are squared
+            // before the call that uses them: neither vor2vel nor the tendency read them)
+            if (!first_update_done) {
+                rk4_factors(c);                                // epq, emq (:87-89)
+                rk4_update(c, 1, dt2, dt6, c.filt2d.p);        // (the source call before this step was a plain one)
+            }
+            do_vor2vel(c);
+            do_source(c, 12, dt2, dt3, c.fac2.p);
+            rk4_update_buoy(c, 2, dt2, dt3, c.fac2.p);
+            *t += dt2;
+            square_factor(c, 2);                               // emq = emq**2 (:151)
+            do_vor2vel(c);
+            do_source(c, 13, dt, dt3, c.fac2.p);
+            rk4_update_buoy(c, 3, dt, dt3, c.fac2.p);
+            *t += dt2;
+            square_factor(c, 3);                               // epq = epq**2 (:185)
+            do_vor2vel(c);
+            do_source(c, 14, dt6, 0.0, c.fac2.p);
+            rk4_update_buoy(c, 4, dt6, 0.0, c.fac2.p);
+            vor_mean(c, 1);                                    // :205
+            return;
+        }
         rk4_factors(c);                                    // epq, emq (:87-89)
         // substep one filters the source with filt(0,:,:) (:227-229)
         rk4_update(c, 1, dt2, dt6, c.filt2d.p);
@@ -1944,6 +1980,11 @@ int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, i
     if (cn2_fused(c)) {
         do_source(c, 0, 0.5 * dt);                     // :95 + the first update of cn2_step (cn2.f90:120-137)
         cn2_update_buoy(c, 0.5 * dt, 0);               // cn2.f90:107-117
+        do_step(c, t, dt, true);                       // :102
+    } else if (rk4_fused(c)) {
+        rk4_factors(c);                                // impl_rk4.f90:87-95
+        do_source(c, 11, 0.5 * dt, dt / 6.0, c.filt2d.p);       // :95 + substep one (impl_rk4.f90:212-241)
+        rk4_update_buoy(c, 1, 0.5 * dt, dt / 6.0, c.filt2d.p);
         do_step(c, t, dt, true);                       // :102
     } else {
         do_source(c);                                  // :95

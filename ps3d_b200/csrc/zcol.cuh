@@ -1051,8 +1051,15 @@ struct SrcArgs {
     // Crank-Nicolson update folded into the last stage (cn2.f90:120-135, 162-173 with the combine -> vdiss ->
     // decompose pairs collapsed, see k_cn2_update): upd < 0: store svorts;  upd = 0: vortsm = svor + c1 S,
     // svor = fac (vortsm + c1 S);  upd = 1: svor = fac (vortsm + c1 S).  svorts is then not stored at all.
+    //   upd = 11..14: substep one..four of impl-diff-rk4 (impl_rk4.f90:212-364, pairs collapsed, see k_rk4_update):
+    //     S' = pq S;  11: svori = svor, svor = mq (svori + c1 S'), svorf = svori + c2 S';  12, 13: svor = mq (svori + c1 S'),
+    //     svorf += c2 S';  14: svor = mq (svorf + c1 S').  vortsm doubles as svori, wb is svorf.
     int upd;
-    double c1;                    // dt/2
+    double c2;                    // rk4: second stage coefficient
+    double* wb[3];                // rk4: svorf
+    const double* mq;             // rk4: emq per column
+    const double* pq;             // rk4: epq (or filt(0,:,:) in substep one) per column
+    double c1;                    // dt/2 (cn2); first stage coefficient (rk4)
     double* svor[3];
     double* vortsm[3];
     const double* f2d;            // vdiss * filt2d per column
@@ -1098,7 +1105,7 @@ __device__ __forceinline__ void rows_prefetch(double* buf, const double* __restr
 }
 
 // last stage of the source kernel for one component: svorts row -> memory, or the Crank-Nicolson update with it
-template <int NZ, bool GEN>
+template <int NZ, bool GEN, bool RK>
 __device__ __forceinline__ void src_finish(const SrcArgs& a, int comp, const double* S, const double* X, double* sv_out,
                                            const SpecGeom& g, const Grp& r, const double (&f2)[4]) {
 #pragma unroll
@@ -1107,7 +1114,23 @@ __device__ __forceinline__ void src_finish(const SrcArgs& a, int comp, const dou
         if (z < 0) continue;
         const Row4 sr = row_load_s<NZ>(S, z);
         if (a.upd < 0) { row_store_g<NZ>(sv_out, r, z, sr); continue; }
-        const Row4 x = row_load_s<NZ>(X, z);             // svor (upd = 0) or vortsm (upd = 1), prefetched
+        const Row4 x = row_load_s<NZ>(X, z);             // the prefetched operand: svor / vortsm (cn2), svor / svori / svorf (rk4)
+        if (RK) {
+            const int st = a.upd - 10;
+            Row4 wbv, out, wbo;
+            if (st == 2 || st == 3) wbv = row_load_g<NZ>(a.wb[comp], r, z);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const long long col = r.off[s] / g.pz;
+                const double sp = __ldg(&a.pq[col]) * sr.v[s];
+                out.v[s] = __ldg(&a.mq[col]) * (x.v[s] + a.c1 * sp);
+                wbo.v[s] = ((st == 1) ? x.v[s] : wbv.v[s]) + a.c2 * sp;
+            }
+            if (st == 1) row_store_g<NZ>(a.vortsm[comp], r, z, x);
+            if (st <= 3) row_store_g<NZ>(a.wb[comp], r, z, wbo);
+            row_store_g<NZ>(a.svor[comp], r, z, out);
+            continue;
+        }
         const double fz = __ldg(&a.filtz[z]);
         Row4 sm, out;
 #pragma unroll
@@ -1122,7 +1145,9 @@ __device__ __forceinline__ void src_finish(const SrcArgs& a, int comp, const dou
     }
 }
 
-template <int NZ, bool GEN>
+// RK: the instantiation that carries an impl-diff-rk4 substep (upd = 11..14); the other one (upd < 11: plain or cn2)
+// is the kernel of the headline path and stays free of the rk4 operands
+template <int NZ, bool GEN, bool RK = false>
 __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_source_spec(SpecGeom g, SrcArgs a) {
     PS_SMEM(double, sm);
     constexpr int BUF = ZCfg<NZ>::BUF;
@@ -1209,28 +1234,31 @@ __global__ void __launch_bounds__(ZCfg<NZ>::NT, ZCfg<NZ>::ctas(4, GEN)) k_source
     put_pre<NZ>(Q, XF_DST, sn, cs, c2r[0], c2r[1], nops);
     // per-slot factor of the update: vdiss * filt2d of the column ((0,0): vdiss, filt = 1)
     double f2[4] = {0.0, 0.0, 0.0, 0.0};
-    if (a.upd >= 0) {
+    if (!RK && a.upd >= 0) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const long long col = r.off[s] / g.pz;
             f2[s] = (GEN && r.g00 && s == 0) ? __ldg(&a.vd[0]) : __ldg(&a.f2d[col]);
         }
     }
-    const double* x0 = (a.upd == 0) ? a.svor[0] : a.vortsm[0];
-    const double* x1 = (a.upd == 0) ? a.svor[1] : a.vortsm[1];
-    const double* x2 = (a.upd == 0) ? a.svor[2] : a.vortsm[2];
+    // operand of the update: svor (cn2 first update, rk4 substep one), vortsm = svori (cn2 iterations, rk4 two / three),
+    // svorf (rk4 substep four)
+    const bool op_svor = (a.upd == 0 || a.upd == 11), op_wb = RK && (a.upd == 14);
+    const double* x0 = op_svor ? a.svor[0] : op_wb ? a.wb[0] : a.vortsm[0];
+    const double* x1 = op_svor ? a.svor[1] : op_wb ? a.wb[1] : a.vortsm[1];
+    const double* x2 = op_svor ? a.svor[2] : op_wb ? a.wb[2] : a.vortsm[2];
     // component 2 first (the half-filled transform round); its update operand lands in P, free since the curl
     if (a.upd >= 0) rows_prefetch<NZ>(P, x2, r);
     __syncthreads();
     xform2p<NZ>(Q, XF_DST, pkQ, nullptr, XF_DST, pkQ, scr);
     if (a.upd >= 0) ps_cp_async_wait();
-    src_finish<NZ, GEN>(a, 2, Q, P, a.s2, g, r, f2);
+    src_finish<NZ, GEN, RK>(a, 2, Q, P, a.s2, g, r, f2);
     // components 0, 1: operands into P and Q (this thread only ever touches its own rows of them from here on)
     if (a.upd >= 0) { rows_prefetch<NZ>(P, x0, r); rows_prefetch<NZ>(Q, x1, r); }
     xform2p<NZ>(R, XF_DST, pkR, T, XF_DST, pkT, scr);
     if (a.upd >= 0) ps_cp_async_wait();
-    src_finish<NZ, GEN>(a, 0, R, P, a.s0, g, r, f2);
-    src_finish<NZ, GEN>(a, 1, T, Q, a.s1, g, r, f2);
+    src_finish<NZ, GEN, RK>(a, 0, R, P, a.s0, g, r, f2);
+    src_finish<NZ, GEN, RK>(a, 1, T, Q, a.s1, g, r, f2);
 }
 
 }  // namespace ps3d
