@@ -23,12 +23,15 @@ def emu():
 
 
 def run_pair(lib, shape, lower, extent, *, filtering="Hou & Li", nnu=3, prediss=30.0, length_scale="Kolmogorov",
-             stepper="cn2", pretype="vorch", win=1000, limit=100.0, nsteps=2, seed=3):
+             stepper="cn2", pretype="vorch", win=1000, limit=100.0, nsteps=2, seed=3, f_cor=None):
     nx, ny, nz = shape
     lib.init(nx, ny, nz, np.asarray(lower, float), np.asarray(extent, float))
     lib.init_inversion(filtering)
     try:
         s = O.PS3D(nx, ny, nz, lower, extent, filtering)
+        if f_cor is not None:                       # planetary vorticity (physics.f90:163-169, inversion.f90:310-314)
+            s.f_cor = np.asarray(f_cor, float)
+            lib.set_physics(f_cor, 0.0)
         vor = np.random.default_rng(seed).uniform(-1, 1, (3, nx, ny, nz + 1))
         s.set_vorticity(vor, nnu=nnu, prediss=prediss, length_scale=length_scale)
         lib.upload_vorticity(vor)
@@ -67,3 +70,9 @@ def test_geophysical_length_scale_and_anisotropic_grid(emu):
 def test_time_limit_clips_dt(emu):
     t, to = run_pair(emu, (8, 8, 8), [-0.5 * math.pi] * 3, [math.pi] * 3, limit=0.03, nsteps=2)
     assert t == pytest.approx(0.03, rel=1e-12) and to == pytest.approx(0.03, rel=1e-12)
+
+
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_planetary_vorticity(emu, stepper):
+    """f_cor != 0 without buoyancy: vor + f_cor in the tendency (inversion.f90:310-314), lat = 45 deg scaled up."""
+    run_pair(emu, (8, 8, 8), [-0.5 * math.pi] * 3, [math.pi] * 3, stepper=stepper, f_cor=(0.0, 0.3, 0.3), nsteps=2)

@@ -36,3 +36,8 @@ def test_geophysical_length_scale_and_anisotropic_grid(lib):
 def test_time_limit_clips_dt(lib):
     t, to = run_pair(lib, (16, 16, 16), [-0.5 * math.pi] * 3, [math.pi] * 3, limit=0.03, nsteps=2)
     assert t == pytest.approx(0.03, rel=1e-12) and to == pytest.approx(0.03, rel=1e-12)
+
+
+@pytest.mark.parametrize("stepper", ["cn2", "impl-diff-rk4"])
+def test_planetary_vorticity(lib, stepper):
+    run_pair(lib, (32, 16, 32), [-0.5 * math.pi] * 3, [math.pi] * 3, stepper=stepper, f_cor=(0.0, 0.3, 0.3), nsteps=2)
