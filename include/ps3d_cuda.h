@@ -125,8 +125,7 @@ int ps3d_cuda_set_physics(const double f_cor[3], double bfsq);
  * (fields.f90:28-35, cn2.f90:31 bsm, impl_rk4.f90:67-72).  After ps3d_cuda_init_inversion, before the first step.
  * From then on source = buoyancy_tendency + vorticity_tendency with r = u eta - v xi + b (inversion.f90:232-292,
  * 316-331, 378-388), adapt evaluates bfmax (advance.f90:147-168) and the steppers advance sbuoy (cn2.f90:107-117,
- * 151-160; impl_rk4.f90:91-105, 124-131, 154-164, 187-195).  nz must be a power of two (the spectral diffz of
- * inversion_utils.f90:683-719 has no mixed-radix coverage kernel): PS3D_ERR_UNSUPPORTED otherwise. */
+ * 151-160; impl_rk4.f90:91-105, 124-131, 154-164, 187-195). */
 int ps3d_cuda_enable_buoyancy(void);
 /* setup_fields (utils.f90:149-158) after the host removed the basic state: b'(0:nz,y,x) -> sbuoy */
 int ps3d_cuda_upload_buoyancy(const double* buoy_phys);

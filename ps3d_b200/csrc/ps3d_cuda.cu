@@ -1846,7 +1846,6 @@ int ps3d_cuda_diffy(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DI
 int ps3d_cuda_central_diffz(const double* fs, double* ds) { PS_API_BEGIN zop_host(ZOP_DIFFZ, fs, ds); PS_API_END }
 int ps3d_cuda_diffz(const double* fs, double* ds) {        // mixed-spectral in, mixed-spectral out (buoyancy build)
     PS_API_BEGIN
-    if (ready().gen[2]) fail(PS3D_ERR_UNSUPPORTED, "diffz: nz must be a power of two");
     zop_host(ZOP_DIFFZ_SPEC, fs, ds);
     PS_API_END
 }
@@ -1905,7 +1904,6 @@ int ps3d_cuda_enable_buoyancy(void) {
     PS_API_BEGIN
     Ctx& c = ready();
     if (c.buoyancy) return PS3D_OK;
-    if (c.gen[2]) fail(PS3D_ERR_UNSUPPORTED, "buoyancy build: nz = %d is not a power of two (no coverage kernel for the spectral diffz)", c.nz);
     DevBuf<double>* f[] = {&c.sbuoy, &c.buoy, &c.sbuoys, &c.bsm, &c.bsem};
     for (auto* b : f) { b->alloc(c.nint); ps_memset(b->p, 0, c.nint * sizeof(double), c.stream); }
     const size_t ncol = (size_t)c.nx * c.nyl;

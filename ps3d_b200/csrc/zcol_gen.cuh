@@ -197,9 +197,46 @@ __global__ void __launch_bounds__(GEN_COL_THREADS) k_zop_gen(SpecGeom g, GenZ gz
         }
         return;
     }
-    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE) gphi_fill(sc, g, r);
+    if (op == ZOP_COMBINE || op == ZOP_DECOMPOSE || op == ZOP_DIFFZ_SPEC) gphi_fill(sc, g, r);
     for (int z = threadIdx.x; z <= nz; z += blockDim.x) grow_store_s(X, lc, z, row_load_g<0>(in, r, z));
     __syncthreads();
+    if (op == ZOP_DIFFZ_SPEC) {
+        // diffz (inversion_utils.f90:683-719), see k_zop: ds = fs(0) dphim + fs(nz) dphip + cosine(rkz fs), then decompose
+        double f0[4], fn[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { f0[s] = X[s * lc]; fn[s] = X[s * lc + nz]; }
+        __syncthreads();
+        for (int z = threadIdx.x; z <= nz; z += blockDim.x) {
+            const double rk = (z >= 1 && z < nz) ? __ldg(&g.rkz[z]) : 0.0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) X[s * lc + z] *= rk;
+        }
+        __syncthreads();
+        xform_gen(X, XF_DCT, sc, gz);
+        Hyp h[2];
+        h[0] = make_hyp(g, r, 0); h[1] = make_hyp(g, r, 1);
+        for (int z = threadIdx.x; z <= nz; z += blockDim.x) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                double dpm, dpp;
+                hyp_dphi(h[s & 1], g.Lz, sc.phim[(s & 1) * lc + z], sc.phip[(s & 1) * lc + z], dpm, dpp);
+                X[s * lc + z] += f0[s] * dpm + fn[s] * dpp;
+            }
+        }
+        __syncthreads();
+        double d0[4], dn[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { d0[s] = X[s * lc]; dn[s] = X[s * lc + nz]; }
+        __syncthreads();
+        for (int z = 1 + threadIdx.x; z < nz; z += blockDim.x) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) X[s * lc + z] -= d0[s] * sc.phim[(s & 1) * lc + z] + dn[s] * sc.phip[(s & 1) * lc + z];
+        }
+        __syncthreads();
+        xform_gen(X, XF_DST, sc, gz);
+        for (int z = threadIdx.x; z <= nz; z += blockDim.x) row_store_g<0>(out, r, z, grow_load_s(X, lc, z));
+        return;
+    }
     if (op == ZOP_DIFFZ) {
         for (int z = threadIdx.x; z <= nz; z += blockDim.x) {
             Row4 d;

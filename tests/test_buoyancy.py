@@ -127,3 +127,9 @@ def test_buoyancy_needs_enable(emu):
             emu.upload_buoyancy(np.zeros((8, 8, 9)))
     finally:
         emu.finalise()
+
+
+def test_buoyancy_non_power_of_two_grid(emu):
+    """nz = 12, ny = 12: the mixed-radix coverage kernels (k_zop_gen's spectral diffz, generic sweeps and updates)."""
+    run_diffz(emu, (8, 12, 12), [-0.5 * math.pi] * 3, [math.pi, 2 * math.pi, 1.0])
+    run_buoyancy(emu, (8, 12, 12), [-0.5 * math.pi] * 3, [math.pi] * 3, stepper="cn2", nsteps=2)

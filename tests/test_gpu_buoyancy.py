@@ -35,3 +35,8 @@ def test_buoyancy_prefactors_and_molecular_diffusion(lib):
 
 def test_buoyancy_64(lib):
     run_buoyancy(lib, (64, 64, 64), [-0.5 * math.pi] * 3, [math.pi] * 3, stepper="cn2", nsteps=2, f_cor=(0.0, 0.0, 0.0), bfsq=0.0)
+
+
+def test_buoyancy_non_power_of_two_grid(lib):
+    run_diffz(lib, (12, 24, 36), [-0.5 * math.pi] * 3, [math.pi, 2 * math.pi, 1.0])
+    run_buoyancy(lib, (24, 12, 36), [-0.5 * math.pi] * 3, [math.pi] * 3, stepper="cn2", nsteps=2)
