@@ -12,7 +12,7 @@ from ps3d_b200.lib import PS3DLib
 lib=PS3DLib(sys.argv[1])
 PI=math.pi
 def rel(a,b): return np.max(np.abs(a-b))/max(np.max(np.abs(b)),1e-300)
-for shape in [(8,8,8),(8,8,16),(16,8,64),(8,8,512),(8,8,1024),(12,10,6),(10,12,30),(16,8,100)]:
+for shape in [(8,8,8),(8,8,16),(8,8,32),(16,8,64),(8,8,128),(8,8,256),(8,8,512),(8,8,1024),(12,10,6),(10,12,30),(16,8,100)]:
     nx,ny,nz=shape
     lo=np.array([-0.5*PI,0.0,-1.0]); ex=np.array([PI,2*PI,2.0])
     lib.init(nx,ny,nz,lo,ex); lib.init_inversion("Hou & Li")
@@ -25,6 +25,11 @@ for shape in [(8,8,8),(8,8,16),(16,8,64),(8,8,512),(8,8,1024),(12,10,6),(10,12,3
     d=lib.diagnostics(); lib.init_diffusion(d["ke"],d["en"]); lib.stepper_setup("cn2")
     t,dt,_=lib.advance(0.0,100.0); to,dto=s.advance(0.0,100.0,"cn2",literal=True)
     lib.vor2vel(); lib.adapt(t,100.0); lib.field_stats(); lib.genspec(); lib.pressure(); s.vor2vel()
-    print(shape, "%.1e"%rel(lib.download3("svor"),s.svor), flush=True)
+    # buoyancy build (spectral diffz, tendency, bfmax, sbuoy updates) and an impl-diff-rk4 step (fused substeps)
+    lib.enable_buoyancy(); lib.upload_buoyancy(rng.uniform(-0.5,0.5,(nx,ny,nz+1))); lib.set_physics((0.0,0.1,0.2),0.5)
+    lib.init_diffusion_buoyancy(d["ke"],d["en"],3,20.0,"Kolmogorov","roll-mean-bfmax",2)
+    lib.diffz(f); lib.advance(t,100.0); lib.stepper_setup("impl-diff-rk4"); lib.advance(t,100.0); lib.pressure()
+    lib.upload_vorticity_begin(np.ascontiguousarray(vor)); lib.upload_vorticity_end()
+    print(shape, "ok", flush=True)
     lib.finalise()
 print("asan sweep done")
