@@ -110,6 +110,8 @@ int ps3d_cuda_adapt(double t, double t_limit, double alpha, int pretype_id, int 
                     double* dt, double diag_out[16]);
 int ps3d_cuda_stepper_setup(int stepper_id);                          /* cn2.f90:83 / impl_rk4.f90:57 */
 int ps3d_cuda_set_diffusion(double dt, double prefactor);             /* cn2.f90:40 / impl_rk4.f90:37 */
+/* needs ps3d_cuda_source for the current state, as bstep%step does (advance.f90:95-102): PS3D_ERR_NOT_INITIALISED
+ * when no source call happened since the last step */
 int ps3d_cuda_step(double* t, double dt);                             /* cn2.f90:92 / impl_rk4.f90:76 */
 /* advance (advance.f90:77-104) minus write_step */
 int ps3d_cuda_advance(double* t, double t_limit, double alpha, int pretype_id, int roll_mean_win_size,

@@ -1463,6 +1463,10 @@ static bool rk4_fused(const Ctx& c) { return c.stepper == PS3D_STEPPER_IMPL_RK4 
 // first_update_done: the source call before this step already carried the first update (ps3d_cuda_advance)
 static void do_step(Ctx& c, double* t, double dt, bool first_update_done = false) {
     if (!c.stepper_ready) fail(PS3D_ERR_NOT_INITIALISED, "stepper_setup has not been called");
+    // bstep%step consumes the tendency of the current state (advance.f90:95-102).  The time loop does not keep svorts
+    // when an update rode on the source kernel, so a step without a source call since the last one has nothing to consume
+    if (!first_update_done && c.svorts_stale)
+        fail(PS3D_ERR_NOT_INITIALISED, "ps3d_cuda_step: call ps3d_cuda_source for the current state first (advance.f90:95-102)");
     if (c.stepper == PS3D_STEPPER_CN2) {
         const double dt2 = 0.5 * dt;                       // cn2.f90:101
         if (!first_update_done) { cn2_update_buoy(c, dt2, 0); cn2_update(c, dt2, 0); }     // :107-137

@@ -364,3 +364,18 @@ def test_streamed_upload_matches_blocking_upload(emu):
             emu.upload_vorticity_end()
     finally:
         emu.finalise()
+
+
+def test_step_needs_a_source_call(emu):
+    """bstep%step consumes the tendency of the current state (advance.f90:95-102): after ps3d_cuda_advance (whose
+    source kernel carried the update and kept no svorts) a bare ps3d_cuda_step is refused; with a source call it runs."""
+    from ps3d_b200 import host
+    s = host.beltrami_solver(emu, 8, stepper="cn2")
+    try:
+        dt, _ = s.advance()
+        with pytest.raises(Exception):
+            emu.step(s.t, dt)
+        emu.vor2vel(); emu.source()
+        emu.step(s.t, dt)
+    finally:
+        s.close()
